@@ -1,0 +1,805 @@
+// engine.cu — asynchronous offload engine: save_blocks / load_blocks behind the reference's
+// StorageOffloadEngine surface (kv_connectors/llmd_fs_backend/csrc/storage/storage_offload.cpp).
+//
+// What is kept from the reference (so the vLLM plugin sees the same behaviour):
+//   * submit-only store/load, get_finished() draining (job_id, ok), wait_job() cancelling queued work
+//     (storage_offload.cpp:185-233,249-423);
+//   * two FIFO queues, loads (high) before stores (normal) with per-worker preference (thread_pool.cpp:169-190);
+//   * store skips files that already exist and bumps atime (storage_offload.cpp:299-304, file_io.cpp:144-149);
+//   * EMA-based dynamic write-queue limit that drops stores (storage_offload.cpp:80-108,272-288);
+//   * on-disk format of the CPU path: file of max(bpf*block_bytes, 16 MiB), blocks tail-aligned, written to a
+//     temp name and renamed (file_io.cpp:50-101, tensor_copier.cu:75-76).
+// What is different (B200-first):
+//   * the unit of GPU work is a CHUNK of whole files (tens of MiB), not one (block x tensor) fragment:
+//     one gather kernel packs the chunk in HBM, ONE large pinned-async D2H moves it (the reference issues
+//     blocks x tensors cudaMemcpyAsync calls of 16-64 KiB); loads are the inverse H2D -> scatter;
+//   * a host tier in pinned DRAM (KVB_TIER_HOST_ARENA) addressed by the same path strings, D2H lands
+//     directly in its final place (no staging copy on the host).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "kvb_internal.h"
+
+namespace kvb {
+
+constexpr int64_t kMinFileBytes = 16ll * 1024 * 1024;  // thread_pool.cpp:35 MIN_STAGING_BUFFER_SIZE
+constexpr double kEmaAlpha = 0.05;                       // storage_offload.cpp:78
+
+struct JobState {
+  int64_t id = 0;
+  std::atomic<int> completed{0};
+  int total = 0;
+  std::atomic<bool> ok{true};
+  std::atomic<bool> cancelled{false};
+};
+
+struct FilePart {
+  std::string path;
+  std::vector<int64_t> ids;
+};
+
+struct ChunkTask {
+  std::shared_ptr<JobState> job;
+  bool is_store = false;
+  std::vector<FilePart> files;  // whole files, total blocks <= blocks_per_chunk
+  int64_t n_blocks = 0;
+  cudaEvent_t ready = nullptr;  // caller-stream event (shared by the job's chunks, owned by last user)
+  std::shared_ptr<void> ready_owner;
+};
+
+// ---------------------------------------------------------------------------------- host arena
+class Arena {
+ public:
+  struct Entry {
+    int64_t off = 0;
+    int64_t n_blocks = 0;
+    int pins = 0;
+    bool valid = false;  // data landed
+    std::list<std::string>::iterator lru;
+  };
+  uint8_t* base = nullptr;
+  int64_t cap = 0;
+  std::mutex mu;
+  std::map<int64_t, int64_t> free_;  // offset -> size
+  std::unordered_map<std::string, Entry> entries;
+  std::list<std::string> lru;  // front = oldest
+
+  int init(int64_t bytes) {
+    cap = bytes;
+    cudaError_t e = cudaHostAlloc(&base, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+      set_error("host arena: cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+      base = nullptr;
+      return KVB_ERR_NOMEM;
+    }
+    free_[0] = bytes;
+    return KVB_OK;
+  }
+  void destroy() {
+    if (base) cudaFreeHost(base);
+    base = nullptr;
+  }
+  bool exists(const std::string& k) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = entries.find(k);
+    return it != entries.end() && it->second.valid;
+  }
+  void clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    entries.clear();
+    lru.clear();
+    free_.clear();
+    free_[0] = cap;
+  }
+  // reserve space for a new entry (pinned for writing); evicts unpinned LRU entries when full.
+  // returns nullptr if the key exists already (*existed=true) or no space can be made.
+  uint8_t* reserve(const std::string& k, int64_t n_blocks, int64_t bytes, bool* existed) {
+    std::lock_guard<std::mutex> lk(mu);
+    *existed = false;
+    if (entries.count(k)) {
+      *existed = true;
+      touch_locked(k);
+      return nullptr;
+    }
+    int64_t off = alloc_locked(bytes);
+    while (off < 0) {
+      if (!evict_one_locked()) return nullptr;
+      off = alloc_locked(bytes);
+    }
+    Entry e;
+    e.off = off;
+    e.n_blocks = n_blocks;
+    e.pins = 1;
+    e.valid = false;
+    lru.push_back(k);
+    e.lru = std::prev(lru.end());
+    entries.emplace(k, e);
+    bytes_of_[k] = bytes;
+    return base + off;
+  }
+  void commit(const std::string& k, bool ok) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = entries.find(k);
+    if (it == entries.end()) return;
+    it->second.pins--;
+    if (ok) {
+      it->second.valid = true;
+    } else {
+      erase_locked(it);
+    }
+  }
+  // pin an entry for reading the LAST n_blocks blocks of it (tail-aligned, like the file format)
+  const uint8_t* pin_read(const std::string& k, int64_t n_blocks, int64_t block_bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = entries.find(k);
+    if (it == entries.end() || !it->second.valid || it->second.n_blocks < n_blocks) return nullptr;
+    it->second.pins++;
+    touch_locked(k);
+    return base + it->second.off + (it->second.n_blocks - n_blocks) * block_bytes;
+  }
+  void unpin(const std::string& k) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = entries.find(k);
+    if (it != entries.end()) it->second.pins--;
+  }
+
+ private:
+  std::unordered_map<std::string, int64_t> bytes_of_;
+  void touch_locked(const std::string& k) {
+    auto it = entries.find(k);
+    if (it == entries.end()) return;
+    lru.erase(it->second.lru);
+    lru.push_back(k);
+    it->second.lru = std::prev(lru.end());
+  }
+  int64_t alloc_locked(int64_t bytes) {
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        int64_t off = it->first, sz = it->second;
+        free_.erase(it);
+        if (sz > bytes) free_[off + bytes] = sz - bytes;
+        return off;
+      }
+    }
+    return -1;
+  }
+  void free_locked(int64_t off, int64_t bytes) {
+    auto nx = free_.lower_bound(off);
+    if (nx != free_.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == off) {
+        off = pv->first;
+        bytes += pv->second;
+        free_.erase(pv);
+      }
+    }
+    if (nx != free_.end() && off + bytes == nx->first) {
+      bytes += nx->second;
+      free_.erase(nx);
+    }
+    free_[off] = bytes;
+  }
+  void erase_locked(std::unordered_map<std::string, Entry>::iterator it) {
+    free_locked(it->second.off, bytes_of_[it->first]);
+    lru.erase(it->second.lru);
+    bytes_of_.erase(it->first);
+    entries.erase(it);
+  }
+  bool evict_one_locked() {
+    for (auto li = lru.begin(); li != lru.end(); ++li) {
+      auto it = entries.find(*li);
+      if (it != entries.end() && it->second.pins == 0) {
+        erase_locked(it);
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+// ---------------------------------------------------------------------------------- file helpers
+static bool file_exists(const std::string& p) {
+  struct stat st;
+  return ::stat(p.c_str(), &st) == 0;
+}
+static void touch_atime(const std::string& p) {  // file_io.cpp:144-149
+  struct timespec times[2];
+  times[0].tv_sec = 0;
+  times[0].tv_nsec = UTIME_NOW;
+  times[1].tv_sec = 0;
+  times[1].tv_nsec = UTIME_OMIT;
+  ::utimensat(AT_FDCWD, p.c_str(), times, 0);
+}
+static bool mkdirs(const std::string& dir) {
+  if (dir.empty()) return true;
+  struct stat st;
+  if (::stat(dir.c_str(), &st) == 0) return S_ISDIR(st.st_mode);
+  size_t pos = dir.find_last_of('/');
+  if (pos != std::string::npos && pos > 0 && !mkdirs(dir.substr(0, pos))) return false;
+  if (::mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) return false;
+  return true;
+}
+static bool write_all(int fd, const uint8_t* p, int64_t n, int64_t off) {
+  while (n > 0) {
+    ssize_t w = ::pwrite(fd, p, (size_t)std::min<int64_t>(n, 1ll << 30), off);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += w;
+    n -= w;
+    off += w;
+  }
+  return true;
+}
+static bool read_all(int fd, uint8_t* p, int64_t n, int64_t off) {
+  while (n > 0) {
+    ssize_t r = ::pread(fd, p, (size_t)std::min<int64_t>(n, 1ll << 30), off);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    if (r == 0) return false;  // short file
+    p += r;
+    n -= r;
+    off += r;
+  }
+  return true;
+}
+
+}  // namespace kvb
+
+using namespace kvb;
+
+// ---------------------------------------------------------------------------------- engine object
+struct kvb_engine {
+  kvb_pool* pool = nullptr;
+  kvb_engine_opts_t opts{};
+  int device = 0;
+  int64_t block_bytes = 0;
+  int64_t blocks_per_chunk = 0;
+  int64_t file_bytes = 0;  // on-disk size of every file
+
+  struct Worker {
+    std::thread th;
+    bool high_first = false;
+    cudaStream_t stream = nullptr;
+    uint8_t* d_packed = nullptr;
+    uint8_t* h_stage = nullptr;  // file tier only
+    int64_t* d_ids = nullptr;
+    int64_t* h_ids = nullptr;
+    bool ready = false;
+  };
+  std::vector<std::unique_ptr<Worker>> workers;
+
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::deque<std::unique_ptr<ChunkTask>> q_high, q_normal;
+  bool stop = false;
+  std::atomic<int64_t> queued_store_files{0};
+
+  std::mutex jmu;
+  std::condition_variable jcv;
+  std::map<int64_t, std::shared_ptr<JobState>> jobs;
+
+  Arena arena;
+  std::atomic<uint64_t> avg_write_us{0};
+  std::string tmp_suffix;
+
+  // stats
+  std::atomic<int64_t> bytes_stored{0}, bytes_loaded{0}, files_stored{0}, files_loaded{0}, files_skipped{0},
+      writes_dropped{0}, load_failures{0}, kernels{0}, h2d{0}, d2h{0};
+
+  void task_done(const std::shared_ptr<JobState>& job, bool ok) {
+    if (!ok) job->ok = false;
+    job->completed.fetch_add(1);
+    std::lock_guard<std::mutex> lk(jmu);
+    jcv.notify_all();
+  }
+
+  void update_write_duration(uint64_t us) {  // storage_offload.cpp:81-95
+    if (us == 0) us = 1;
+    uint64_t old_val = avg_write_us.load(), new_val;
+    do {
+      new_val = old_val == 0 ? us : (uint64_t)(old_val * (1.0 - kEmaAlpha) + us * kEmaAlpha);
+    } while (!avg_write_us.compare_exchange_weak(old_val, new_val));
+  }
+  size_t dynamic_write_queue_limit() const {  // storage_offload.cpp:98-106
+    uint64_t avg = avg_write_us.load();
+    if (avg == 0 || opts.max_write_queued_seconds <= 0) return 0;
+    return (size_t)(workers.size() * opts.max_write_queued_seconds / (avg / 1e6));
+  }
+
+  bool worker_init(Worker& w);
+  void worker_loop(Worker* w);
+  bool run_store(Worker& w, ChunkTask& t);
+  bool run_load(Worker& w, ChunkTask& t);
+  bool write_file(const FilePart& f, const uint8_t* payload);
+  bool read_file(const FilePart& f, uint8_t* payload);
+  int submit(int64_t job_id, int32_t n_files, const char* const* files, const int64_t* ids, const int64_t* off,
+             void* caller_stream, bool is_store);
+};
+
+bool kvb_engine::worker_init(Worker& w) {
+  if (cudaSetDevice(device) != cudaSuccess) return false;
+  const size_t chunk = (size_t)(blocks_per_chunk * block_bytes);
+  if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (cudaMalloc(&w.d_packed, chunk) != cudaSuccess) return false;
+  if (cudaMalloc(&w.d_ids, blocks_per_chunk * sizeof(int64_t)) != cudaSuccess) return false;
+  if (cudaHostAlloc(&w.h_ids, blocks_per_chunk * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) return false;
+  if (opts.tier == KVB_TIER_FILE &&
+      cudaHostAlloc(&w.h_stage, chunk, cudaHostAllocDefault) != cudaSuccess)
+    return false;
+  w.ready = true;
+  return true;
+}
+
+// reference on-disk format, CPU path: full-size file, payload tail-aligned inside the bpf slots
+bool kvb_engine::write_file(const FilePart& f, const uint8_t* payload) {
+  const std::string& target = f.path;
+  size_t pos = target.find_last_of('/');
+  if (pos != std::string::npos && !mkdirs(target.substr(0, pos))) return false;
+  std::string tmp = target + tmp_suffix + std::to_string((uintptr_t)payload & 0xffffff);
+  int fd = ::open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  if (fd < 0) return false;
+  const int64_t n = (int64_t)f.ids.size();
+  const int64_t off = ((int64_t)opts.gpu_blocks_per_file - n) * block_bytes;
+  bool ok = ::ftruncate(fd, file_bytes) == 0 && write_all(fd, payload, n * block_bytes, off);
+  ok = (::close(fd) == 0) && ok;
+  if (ok && ::rename(tmp.c_str(), target.c_str()) != 0) ok = false;
+  if (!ok) ::unlink(tmp.c_str());
+  return ok;
+}
+
+bool kvb_engine::read_file(const FilePart& f, uint8_t* payload) {
+  int fd = ::open(f.path.c_str(), O_RDONLY);
+  if (fd < 0) return false;
+  const int64_t n = (int64_t)f.ids.size();
+  const int64_t off = ((int64_t)opts.gpu_blocks_per_file - n) * block_bytes;
+  bool ok = read_all(fd, payload, n * block_bytes, off);
+  ::close(fd);
+  return ok;
+}
+
+bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
+  // cancelled before start: nothing to do (storage_offload.cpp:294-297)
+  if (t.job->cancelled.load()) return true;
+  // drop files that already exist (storage_offload.cpp:299-304) and, in the arena tier, reserve their space
+  struct Dest {
+    const FilePart* f;
+    uint8_t* host;  // arena destination (arena tier) or offset into h_stage (file tier)
+    int64_t first_block;
+  };
+  std::vector<Dest> dests;
+  int64_t n = 0;
+  for (auto& f : t.files) {
+    const int64_t nb = (int64_t)f.ids.size();
+    if (nb == 0) continue;
+    if (opts.tier == KVB_TIER_HOST_ARENA) {
+      bool existed = false;
+      uint8_t* dst = arena.reserve(f.path, nb, nb * block_bytes, &existed);
+      if (existed) {
+        files_skipped++;
+        continue;
+      }
+      if (!dst) {
+        set_error("host arena full storing %s", f.path.c_str());
+        for (auto& d : dests) arena.commit(d.f->path, false);
+        return false;
+      }
+      dests.push_back({&f, dst, n});
+    } else {
+      if (file_exists(f.path)) {
+        touch_atime(f.path);
+        files_skipped++;
+        continue;
+      }
+      dests.push_back({&f, w.h_stage + n * block_bytes, n});
+    }
+    std::memcpy(w.h_ids + n, f.ids.data(), nb * sizeof(int64_t));
+    n += nb;
+  }
+  if (n == 0) return true;
+  auto t0 = std::chrono::steady_clock::now();
+  bool ok = true;
+  cudaError_t e = cudaSuccess;
+  if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);  // KV produced on the caller's stream
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
+  if (e == cudaSuccess) {
+    ok = launch_gather(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
+    kernels++;
+  }
+  if (e == cudaSuccess && ok) {
+    // D2H: merge destinations that are contiguous on the host into one copy
+    size_t i = 0;
+    while (i < dests.size() && e == cudaSuccess) {
+      size_t j = i;
+      int64_t bytes = (int64_t)dests[i].f->ids.size() * block_bytes;
+      while (j + 1 < dests.size() && dests[j + 1].host == dests[i].host + bytes) {
+        ++j;
+        bytes += (int64_t)dests[j].f->ids.size() * block_bytes;
+      }
+      e = cudaMemcpyAsync(dests[i].host, w.d_packed + dests[i].first_block * block_bytes, (size_t)bytes,
+                          cudaMemcpyDeviceToHost, w.stream);
+      d2h += bytes;
+      i = j + 1;
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+  if (e != cudaSuccess) {
+    set_error("store chunk: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    ok = false;
+  }
+  if (opts.tier == KVB_TIER_HOST_ARENA) {
+    for (auto& d : dests) arena.commit(d.f->path, ok);
+  } else if (ok) {
+    for (auto& d : dests) {
+      if (t.job->cancelled.load()) break;  // in-flight cancelled job skips the file write (storage_offload.cpp:228-229)
+      if (!write_file(*d.f, d.host)) {
+        set_error("store: writing %s failed: %s", d.f->path.c_str(), std::strerror(errno));
+        ok = false;
+      }
+    }
+  }
+  if (ok) {
+    bytes_stored += n * block_bytes;
+    files_stored += (int64_t)dests.size();
+  }
+  auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+  if (!dests.empty()) update_write_duration((uint64_t)(us / (int64_t)dests.size()));
+  return ok;
+}
+
+bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
+  struct Src {
+    const FilePart* f;
+    const uint8_t* host;
+    int64_t first_block;
+  };
+  std::vector<Src> srcs;
+  int64_t n = 0;
+  bool ok = true;
+  for (auto& f : t.files) {
+    const int64_t nb = (int64_t)f.ids.size();
+    if (nb == 0) continue;
+    if (opts.tier == KVB_TIER_HOST_ARENA) {
+      const uint8_t* src = arena.pin_read(f.path, nb, block_bytes);
+      if (!src) {
+        set_error("load: %s not in host arena (or holds fewer than %lld blocks)", f.path.c_str(), (long long)nb);
+        ok = false;
+        break;
+      }
+      srcs.push_back({&f, src, n});
+    } else {
+      uint8_t* dst = w.h_stage + n * block_bytes;
+      if (!read_file(f, dst)) {
+        set_error("load: reading %s failed", f.path.c_str());
+        ok = false;
+        break;
+      }
+      srcs.push_back({&f, dst, n});
+    }
+    std::memcpy(w.h_ids + n, f.ids.data(), nb * sizeof(int64_t));
+    n += nb;
+  }
+  cudaError_t e = cudaSuccess;
+  if (ok && n > 0) {
+    if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
+    size_t i = 0;
+    while (i < srcs.size() && e == cudaSuccess) {
+      size_t j = i;
+      int64_t bytes = (int64_t)srcs[i].f->ids.size() * block_bytes;
+      while (j + 1 < srcs.size() && srcs[j + 1].host == srcs[i].host + bytes) {
+        ++j;
+        bytes += (int64_t)srcs[j].f->ids.size() * block_bytes;
+      }
+      e = cudaMemcpyAsync(w.d_packed + srcs[i].first_block * block_bytes, srcs[i].host, (size_t)bytes,
+                          cudaMemcpyHostToDevice, w.stream);
+      h2d += bytes;
+      i = j + 1;
+    }
+    if (e == cudaSuccess) {
+      ok = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
+      kernels++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+    if (e != cudaSuccess) {
+      set_error("load chunk: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      ok = false;
+    }
+  }
+  if (opts.tier == KVB_TIER_HOST_ARENA)
+    for (auto& s : srcs) arena.unpin(s.f->path);
+  if (ok) {
+    bytes_loaded += n * block_bytes;
+    files_loaded += (int64_t)srcs.size();
+  } else {
+    load_failures++;
+  }
+  return ok;
+}
+
+void kvb_engine::worker_loop(Worker* w) {
+  bool inited = false;
+  for (;;) {
+    std::unique_ptr<ChunkTask> task;
+    {
+      std::unique_lock<std::mutex> lk(qmu);
+      qcv.wait(lk, [&] { return stop || !q_high.empty() || !q_normal.empty(); });
+      if (stop && q_high.empty() && q_normal.empty()) break;
+      auto& first = w->high_first ? q_high : q_normal;
+      auto& second = w->high_first ? q_normal : q_high;
+      auto& q = !first.empty() ? first : second;
+      task = std::move(q.front());
+      q.pop_front();
+    }
+    if (!inited) {
+      inited = worker_init(*w);
+      if (!inited) set_error("engine worker: CUDA resource allocation failed");
+    }
+    bool ok = false;
+    if (inited) {
+      try {
+        ok = task->is_store ? run_store(*w, *task) : run_load(*w, *task);
+      } catch (...) {
+        set_error("exception in engine worker");
+        ok = false;
+      }
+    }
+    if (!ok)  // reference logs failures at ERROR level (storage_offload.cpp:330-346,399-410)
+      fprintf(stderr, "[kvb][ERROR] %s chunk of job %lld failed: %s\n", task->is_store ? "store" : "load",
+              (long long)task->job->id, get_error());
+    if (task->is_store) {
+      queued_store_files -= (int64_t)task->files.size();
+    } else if (!ok && !opts.strict_load_errors) {
+      // reference parity: read failures are swallowed, the job still reports success
+      // (storage_offload.cpp:378-383); opts.strict_load_errors != 0 (strict) reports them
+      ok = true;
+    }
+    task_done(task->job, ok);
+  }
+  if (w->stream) {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(w->stream);
+    if (w->d_packed) cudaFree(w->d_packed);
+    if (w->d_ids) cudaFree(w->d_ids);
+    if (w->h_ids) cudaFreeHost(w->h_ids);
+    if (w->h_stage) cudaFreeHost(w->h_stage);
+    cudaStreamDestroy(w->stream);
+  }
+}
+
+int kvb_engine::submit(int64_t job_id, int32_t n_files, const char* const* files, const int64_t* ids,
+                       const int64_t* off, void* caller_stream, bool is_store) {
+  KVB_REQUIRE(n_files >= 0, "negative file count");
+  KVB_REQUIRE(n_files == 0 || (files && ids && off), "NULL argument");
+  for (int32_t i = 0; i < n_files; ++i) {
+    const int64_t nb = off[i + 1] - off[i];
+    KVB_REQUIRE(nb >= 0 && nb <= opts.gpu_blocks_per_file, "file %d holds %lld blocks, gpu_blocks_per_file is %d", i,
+                (long long)nb, opts.gpu_blocks_per_file);
+    KVB_REQUIRE(files[i] != nullptr, "file %d is NULL", i);
+    int rc = validate_ids(pool, ids + off[i], nb);
+    if (rc) return rc;
+  }
+  auto job = std::make_shared<JobState>();
+  job->id = job_id;
+
+  // order after the caller's stream (storage_offload.cpp:259-265)
+  cudaEvent_t ev = nullptr;
+  std::shared_ptr<void> ev_owner;
+  {
+    DeviceGuard g(device);
+    KVB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KVB_CUDA_TRY(cudaEventRecord(ev, static_cast<cudaStream_t>(caller_stream)));
+    ev_owner = std::shared_ptr<void>(ev, [](void* e) { cudaEventDestroy(static_cast<cudaEvent_t>(e)); });
+  }
+
+  std::vector<std::unique_ptr<ChunkTask>> tasks;
+  std::unique_ptr<ChunkTask> cur;
+  int dropped = 0;
+  for (int32_t i = 0; i < n_files; ++i) {
+    const int64_t nb = off[i + 1] - off[i];
+    if (is_store) {
+      // dynamic write-queue limit (storage_offload.cpp:272-288): dropped files count as done + success
+      size_t limit = dynamic_write_queue_limit();
+      if (limit > 0 && (size_t)queued_store_files.load() >= limit) {
+        ++dropped;
+        writes_dropped++;
+        continue;
+      }
+      queued_store_files++;
+    }
+    if (!cur || cur->n_blocks + nb > blocks_per_chunk) {
+      if (cur) tasks.push_back(std::move(cur));
+      cur.reset(new ChunkTask());
+      cur->job = job;
+      cur->is_store = is_store;
+      cur->ready = ev;
+      cur->ready_owner = ev_owner;
+    }
+    FilePart fp;
+    fp.path = files[i];
+    fp.ids.assign(ids + off[i], ids + off[i + 1]);
+    cur->files.push_back(std::move(fp));
+    cur->n_blocks += nb;
+  }
+  if (cur) tasks.push_back(std::move(cur));
+  job->total = (int)tasks.size();
+  {
+    std::lock_guard<std::mutex> lk(jmu);
+    jobs[job_id] = job;
+  }
+  {
+    std::lock_guard<std::mutex> lk(qmu);
+    for (auto& t : tasks) (is_store ? q_normal : q_high).push_back(std::move(t));
+  }
+  qcv.notify_all();
+  (void)dropped;
+  return KVB_OK;
+}
+
+extern "C" {
+
+void kvb_engine_default_opts(kvb_engine_opts_t* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->io_threads = 4;
+  o->gpu_blocks_per_file = 16;
+  o->read_preferring_workers = 3;
+  o->max_write_queued_seconds = 10.0f;  // worker.py:61 DEFAULT_MAX_WRITE_QUEUED_SECONDS
+  o->tier = KVB_TIER_FILE;
+  o->copy_flags = KVB_COPY_DEFAULT;
+  o->host_arena_bytes = 0;
+  o->chunk_bytes = 64ll << 20;
+  o->num_slots = 0;
+  o->strict_load_errors = 0;
+}
+
+int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engine_t** out) {
+  KVB_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  KVB_REQUIRE(pool != nullptr && opts != nullptr, "NULL argument");
+  KVB_REQUIRE(opts->gpu_blocks_per_file > 0, "gpu_blocks_per_file must be > 0");  // tensor_copier.cu:35-36
+  KVB_REQUIRE(opts->io_threads > 0 && opts->io_threads <= 256, "io_threads out of range");
+  KVB_REQUIRE(opts->tier == KVB_TIER_FILE || opts->tier == KVB_TIER_HOST_ARENA, "unknown tier %d", opts->tier);
+  std::unique_ptr<kvb_engine> e(new kvb_engine());
+  e->pool = pool;
+  e->opts = *opts;
+  e->device = pool->device;
+  e->block_bytes = pool->frag_bytes * pool->num_tensors;
+  int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : (64ll << 20);
+  int64_t bpc = chunk / e->block_bytes;
+  if (bpc < opts->gpu_blocks_per_file) bpc = opts->gpu_blocks_per_file;  // a chunk always holds whole files
+  e->blocks_per_chunk = bpc;
+  e->file_bytes = std::max<int64_t>((int64_t)opts->gpu_blocks_per_file * e->block_bytes, kMinFileBytes);
+  e->tmp_suffix = "_" + std::to_string((long long)::getpid()) + "_" +
+                  std::to_string((unsigned long long)(uintptr_t)e.get() & 0xffffff) + ".tmp";
+  DeviceGuard g(e->device);
+  if (!g.ok) {
+    set_error("cannot select CUDA device %d", e->device);
+    return KVB_ERR_CUDA;
+  }
+  if (opts->tier == KVB_TIER_HOST_ARENA) {
+    KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
+    int rc = e->arena.init(opts->host_arena_bytes);
+    if (rc) return rc;
+  }
+  const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);
+  for (int i = 0; i < opts->io_threads; ++i) {
+    auto w = std::make_unique<kvb_engine::Worker>();
+    w->high_first = i < n_high;  // thread_pool.cpp:52-57
+    e->workers.push_back(std::move(w));
+  }
+  for (auto& w : e->workers) w->th = std::thread([eng = e.get(), wp = w.get()] { eng->worker_loop(wp); });
+  *out = e.release();
+  return KVB_OK;
+}
+
+void kvb_engine_destroy(kvb_engine_t* e) {
+  if (!e) return;
+  {
+    std::lock_guard<std::mutex> lk(e->qmu);
+    e->stop = true;
+  }
+  e->qcv.notify_all();
+  for (auto& w : e->workers)
+    if (w->th.joinable()) w->th.join();
+  e->arena.destroy();
+  delete e;
+}
+
+int kvb_engine_store(kvb_engine_t* e, int64_t job_id, int32_t n_files, const char* const* files,
+                     const int64_t* block_ids, const int64_t* file_off, void* caller_stream) {
+  KVB_REQUIRE(e != nullptr, "engine is NULL");
+  return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, true);
+}
+int kvb_engine_load(kvb_engine_t* e, int64_t job_id, int32_t n_files, const char* const* files,
+                    const int64_t* block_ids, const int64_t* file_off, void* caller_stream) {
+  KVB_REQUIRE(e != nullptr, "engine is NULL");
+  return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, false);
+}
+
+int kvb_engine_poll(kvb_engine_t* e, int64_t* job_ids, int32_t* ok, int32_t cap) {
+  KVB_REQUIRE(e != nullptr, "engine is NULL");
+  KVB_REQUIRE(cap >= 0 && (cap == 0 || (job_ids && ok)), "bad output buffers");
+  std::lock_guard<std::mutex> lk(e->jmu);
+  int n = 0;
+  for (auto it = e->jobs.begin(); it != e->jobs.end() && n < cap;) {
+    if (it->second->completed.load() == it->second->total) {  // storage_offload.cpp:196-201
+      job_ids[n] = it->first;
+      ok[n] = it->second->ok.load() ? 1 : 0;
+      ++n;
+      it = e->jobs.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  return n;
+}
+
+int kvb_engine_wait(kvb_engine_t* e, int64_t job_id) {
+  KVB_REQUIRE(e != nullptr, "engine is NULL");
+  std::shared_ptr<JobState> job;
+  {
+    std::lock_guard<std::mutex> lk(e->jmu);
+    auto it = e->jobs.find(job_id);
+    if (it == e->jobs.end()) return KVB_OK;  // storage_offload.cpp:221: unknown job returns
+    job = it->second;
+  }
+  job->cancelled = true;  // queued tasks bail early (storage_offload.cpp:226-229)
+  std::unique_lock<std::mutex> lk(e->jmu);
+  e->jcv.wait(lk, [&] { return job->completed.load() == job->total; });
+  return KVB_OK;
+}
+
+int kvb_engine_exists(kvb_engine_t* e, const char* file) {
+  if (!e || !file) return 0;
+  if (e->opts.tier == KVB_TIER_HOST_ARENA) return e->arena.exists(file) ? 1 : 0;
+  return file_exists(file) ? 1 : 0;
+}
+
+int kvb_engine_arena_clear(kvb_engine_t* e) {
+  KVB_REQUIRE(e != nullptr, "engine is NULL");
+  if (e->opts.tier == KVB_TIER_HOST_ARENA) e->arena.clear();
+  return KVB_OK;
+}
+
+int kvb_engine_get_stats(kvb_engine_t* e, kvb_engine_stats_t* s) {
+  KVB_REQUIRE(e && s, "NULL argument");
+  s->bytes_stored = e->bytes_stored;
+  s->bytes_loaded = e->bytes_loaded;
+  s->files_stored = e->files_stored;
+  s->files_loaded = e->files_loaded;
+  s->files_skipped_existing = e->files_skipped;
+  s->writes_dropped = e->writes_dropped;
+  s->load_failures = e->load_failures;
+  s->kernels_launched = e->kernels;
+  s->h2d_bytes = e->h2d;
+  s->d2h_bytes = e->d2h;
+  return KVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,289 @@
+// hash_kernels.cu — chained kvblock prefix hash on the device.
+//
+// Replaces chunkedTokenDatabase.{hash,prefixHashes,TokensToKVBlockKeys}
+// (pkg/kvcache/kvblock/token_processor.go:123-205):
+//     key_i = FNV64a( 0x83 | U(parent) | ARR(chunk_i) | X(extra_i) ),  parent = key_{i-1}
+// with U/ARR the RFC 8949 shortest-form heads the reference gets from fxamacker/cbor v2.7.0
+// CanonicalEncOptions (token_processor.go:97).  The payload is never materialised: every
+// CBOR byte is folded into the FNV state as it is produced.
+//
+// Parallelism: FNV-1a is a serial byte chain and keys chain across blocks, so one prompt is
+// one serial chain.  One THREAD per prompt (32 chains per warp); per token the 1..5 CBOR bytes
+// are folded with predicated steps so lanes holding 1/2/3/5-byte tokens do not diverge.
+// Latency/ALU-bound (about 10 cycles per payload byte per chain), not HBM-bound: the only
+// memory traffic is 4 B/token in and 8 B/key out.
+#include <cstring>
+#include <vector>
+
+#include "kvb_internal.h"
+
+namespace kvb {
+
+constexpr uint64_t kFnvOffset = 0xcbf29ce484222325ull;
+constexpr uint64_t kFnvPrime = 0x100000001b3ull;
+
+__device__ __forceinline__ uint64_t fold(uint64_t h, uint32_t byte) { return (h ^ (uint64_t)byte) * kFnvPrime; }
+
+// CBOR head for major type `major` (already shifted <<5) with argument n, shortest form.
+__device__ __forceinline__ uint64_t fold_head64(uint64_t h, uint32_t major, uint64_t n) {
+  if (n < 24) return fold(h, major | (uint32_t)n);
+  if (n < 0x100ull) {
+    h = fold(h, major | 24);
+    return fold(h, (uint32_t)n);
+  }
+  if (n < 0x10000ull) {
+    h = fold(h, major | 25);
+    h = fold(h, (uint32_t)(n >> 8));
+    return fold(h, (uint32_t)n & 0xff);
+  }
+  if (n < 0x100000000ull) {
+    h = fold(h, major | 26);
+#pragma unroll
+    for (int s = 24; s >= 0; s -= 8) h = fold(h, (uint32_t)(n >> s) & 0xff);
+    return h;
+  }
+  h = fold(h, major | 27);
+#pragma unroll
+  for (int s = 56; s >= 0; s -= 8) h = fold(h, (uint32_t)(n >> s) & 0xff);
+  return h;
+}
+
+// One uint32 token as a CBOR unsigned int: 1, 2, 3 or 5 bytes, folded with predicated steps.
+__device__ __forceinline__ uint64_t fold_token(uint64_t h, uint32_t t) {
+  uint64_t stream;  // byte k of the encoding sits in bits [8k, 8k+8)
+  int nb;
+  if (t < 24u) {
+    stream = t;
+    nb = 1;
+  } else if (t < 0x100u) {
+    stream = 0x18u | (t << 8);
+    nb = 2;
+  } else if (t < 0x10000u) {
+    stream = 0x19u | ((t >> 8) << 8) | ((t & 0xffu) << 16);
+    nb = 3;
+  } else {
+    stream = 0x1aull | ((uint64_t)__byte_perm(t, 0, 0x0123) << 8);
+    nb = 5;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const uint64_t hn = fold(h, (uint32_t)(stream >> (8 * k)) & 0xffu);
+    h = (k < nb) ? hn : h;
+  }
+  return h;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restrict__ tokens,
+                                                         const int64_t* __restrict__ prompt_off,
+                                                         const uint64_t* __restrict__ parents, int32_t n_prompts,
+                                                         int32_t block_size_rt, const uint8_t* __restrict__ extra,
+                                                         const int64_t* __restrict__ extra_off,
+                                                         uint64_t* __restrict__ out_keys,
+                                                         const int64_t* __restrict__ key_off) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_prompts) return;
+  const int bs = BS > 0 ? BS : block_size_rt;
+  const int64_t t0 = prompt_off[p];
+  const int64_t nblk = (prompt_off[p + 1] - t0) / bs;  // tail tokens dropped (token_processor.go:166-168)
+  const int64_t k0 = key_off[p];
+  const uint32_t* tk = tokens + t0;
+  uint64_t parent = parents[p];
+
+  uint32_t cur[BS > 0 ? BS : 1];
+  if (BS > 0 && nblk > 0) {
+#pragma unroll
+    for (int j = 0; j < BS; ++j) cur[j] = __ldg(tk + j);
+  }
+  for (int64_t i = 0; i < nblk; ++i) {
+    uint32_t nxt[BS > 0 ? BS : 1];
+    if (BS > 0 && i + 1 < nblk) {  // prefetch the next block's tokens under this block's fold chain
+#pragma unroll
+      for (int j = 0; j < BS; ++j) nxt[j] = __ldg(tk + (i + 1) * BS + j);
+    }
+    uint64_t h = fold(kFnvOffset, 0x83u);          // array(3)
+    h = fold_head64(h, 0x00u, parent);              // parent: unsigned int
+    h = fold_head64(h, 0x80u, (uint64_t)bs);        // chunk: array(bs)
+    if (BS > 0) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) h = fold_token(h, cur[j]);
+    } else {
+      for (int j = 0; j < bs; ++j) h = fold_token(h, __ldg(tk + i * bs + j));
+    }
+    bool text = true;
+    if (extra_off != nullptr) {                     // pre-encoded X(extra_i), host-built (extra_keys.go)
+      const int64_t e0 = extra_off[k0 + i], e1 = extra_off[k0 + i + 1];
+      if (e1 > e0) {
+        text = false;
+        for (int64_t e = e0; e < e1; ++e) h = fold(h, extra[e]);
+      }
+    }
+    if (text) h = fold(h, 0xf6u);                   // nil extra -> CBOR null
+    out_keys[k0 + i] = h;
+    parent = h;
+    if (BS > 0) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) cur[j] = nxt[j];
+    }
+  }
+}
+
+// getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
+__global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__ name, uint32_t len,
+                                 uint64_t* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t h = fold(kFnvOffset, 0x83u);
+  h = fold_head64(h, 0x00u, seed_hash);
+  h = fold(h, 0xf6u);
+  h = fold_head64(h, 0x60u, len);
+  for (uint32_t i = 0; i < len; ++i) h = fold(h, name[i]);
+  *out = h;
+}
+
+int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents, int32_t n_prompts,
+                       int32_t block_size, const uint8_t* extra, const int64_t* extra_off, uint64_t* out_keys,
+                       const int64_t* key_off, cudaStream_t s) {
+  if (n_prompts <= 0) return KVB_OK;
+  // small batches: 32-thread CTAs so the chains spread over the SMs; large: 128
+  const int threads = n_prompts >= 148 * 128 ? 128 : 32;
+  const int grid = (n_prompts + threads - 1) / threads;
+  switch (block_size) {
+    case 16:
+      hash_chain_kernel<16><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
+                                                     extra_off, out_keys, key_off);
+      break;
+    case 4:
+      hash_chain_kernel<4><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
+                                                    extra_off, out_keys, key_off);
+      break;
+    default:
+      hash_chain_kernel<0><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
+                                                    extra_off, out_keys, key_off);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("hash kernel launch failed: %s", cudaGetErrorString(e));
+    return KVB_ERR_CUDA;
+  }
+  count_launch();
+  return KVB_OK;
+}
+
+}  // namespace kvb
+
+using namespace kvb;
+
+extern "C" {
+
+uint64_t kvb_fnv64a(const void* data, size_t len) {
+  // seed hash only (token_processor.go:90-95): once per processor, a handful of bytes
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint64_t h = kFnvOffset;
+  for (size_t i = 0; i < len; ++i) h = (h ^ p[i]) * kFnvPrime;
+  return h;
+}
+
+int kvb_init_hash(int device, uint64_t seed_hash, const char* model_name, size_t model_len, uint64_t* out) {
+  KVB_REQUIRE(out != nullptr, "out is NULL");
+  KVB_REQUIRE(model_name != nullptr || model_len == 0, "model_name is NULL");
+  KVB_REQUIRE(model_len < (1u << 31), "model name too long");
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("cannot select CUDA device %d", device);
+    return KVB_ERR_CUDA;
+  }
+  uint8_t* d = nullptr;
+  KVB_CUDA_TRY(cudaMalloc(&d, model_len + 8 + 8));
+  uint64_t* d_out = reinterpret_cast<uint64_t*>(d);
+  uint8_t* d_name = d + 8;
+  cudaError_t e = cudaSuccess;
+  if (model_len) e = cudaMemcpy(d_name, model_name, model_len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    init_hash_kernel<<<1, 32>>>(seed_hash, d_name, (uint32_t)model_len, d_out);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  KVB_CUDA_TRY(e);
+  return KVB_OK;
+}
+
+int kvb_hash_token_blocks_dev(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
+                              int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
+                              uint64_t* out_keys, const int64_t* key_off, void* stream) {
+  KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);  // token_processor.go:86-88
+  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+  if (n_prompts == 0) return KVB_OK;
+  KVB_REQUIRE(tokens && prompt_off && parents && out_keys && key_off, "NULL argument");
+  DeviceGuard g(device);
+  return launch_hash_blocks(tokens, prompt_off, parents, n_prompts, block_size, extra, extra_off, out_keys, key_off,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int kvb_hash_token_blocks(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
+                          int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
+                          uint64_t* out_keys, int64_t* out_key_off, void* stream) {
+  KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
+  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+  KVB_REQUIRE(out_key_off != nullptr, "out_key_off is NULL");
+  out_key_off[0] = 0;
+  if (n_prompts == 0) return KVB_OK;
+  KVB_REQUIRE(prompt_off && parents, "NULL argument");
+  for (int32_t p = 0; p < n_prompts; ++p) {
+    KVB_REQUIRE(prompt_off[p + 1] >= prompt_off[p], "prompt_off not monotonic at %d", p);
+    out_key_off[p + 1] = out_key_off[p] + (prompt_off[p + 1] - prompt_off[p]) / block_size;
+  }
+  const int64_t total_keys = out_key_off[n_prompts];
+  const int64_t total_tok = prompt_off[n_prompts] - prompt_off[0];
+  if (total_keys == 0) return KVB_OK;
+  KVB_REQUIRE(tokens && out_keys, "NULL argument");
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("cannot select CUDA device %d", device);
+    return KVB_ERR_CUDA;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t extra_bytes = extra_off ? extra_off[total_keys] : 0;
+  // one device scratch: [tokens | prompt_off | key_off | parents | keys | extra_off | extra]
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_tok = 0;
+  const size_t o_poff = o_tok + al(total_tok * 4);
+  const size_t o_koff = o_poff + al((n_prompts + 1) * 8);
+  const size_t o_par = o_koff + al((n_prompts + 1) * 8);
+  const size_t o_keys = o_par + al(n_prompts * 8);
+  const size_t o_eoff = o_keys + al(total_keys * 8);
+  const size_t o_ext = o_eoff + (extra_off ? al((total_keys + 1) * 8) : 0);
+  const size_t total = o_ext + (extra_off ? al(extra_bytes) : 0) + 256;
+  uint8_t* d = nullptr;
+  KVB_CUDA_TRY(cudaMallocAsync(&d, total, s));
+  std::vector<int64_t> poff_rel(n_prompts + 1);
+  for (int32_t p = 0; p <= n_prompts; ++p) poff_rel[p] = prompt_off[p] - prompt_off[0];
+  cudaError_t e = cudaMemcpyAsync(d + o_tok, tokens + prompt_off[0], total_tok * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d + o_poff, poff_rel.data(), (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_koff, out_key_off, (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_par, parents, n_prompts * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && extra_off) {
+    e = cudaMemcpyAsync(d + o_eoff, extra_off, (total_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && extra_bytes)
+      e = cudaMemcpyAsync(d + o_ext, extra, extra_bytes, cudaMemcpyHostToDevice, s);
+  }
+  int rc = KVB_OK;
+  if (e == cudaSuccess) {
+    rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(d + o_tok), reinterpret_cast<int64_t*>(d + o_poff),
+                            reinterpret_cast<uint64_t*>(d + o_par), n_prompts, block_size,
+                            extra_off ? d + o_ext : nullptr,
+                            extra_off ? reinterpret_cast<int64_t*>(d + o_eoff) : nullptr,
+                            reinterpret_cast<uint64_t*>(d + o_keys), reinterpret_cast<int64_t*>(d + o_koff), s);
+    if (rc == KVB_OK) e = cudaMemcpyAsync(out_keys, d + o_keys, total_keys * 8, cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(s);  // poff_rel and the caller's buffers must outlive the copies
+  cudaFreeAsync(d, s);
+  if (rc != KVB_OK) return rc;
+  KVB_CUDA_TRY(e);
+  KVB_CUDA_TRY(e2);
+  return KVB_OK;
+}
+
+}  // extern "C"

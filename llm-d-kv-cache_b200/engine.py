@@ -1,0 +1,114 @@
+"""StorageOffloadEngine — same constructor and methods as the reference's pybind class
+(kv_connectors/llmd_fs_backend/csrc/storage/storage_offload_bindings.cpp:25-94), i.e. the
+StorageEngine Protocol of llmd_fs_backend/worker.py:36-52, implemented by libkvb.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineOpts, EngineStats, check
+from .pool import KVPool, _stream_ptr
+
+
+class StorageOffloadEngine:
+    """Async KV-block offload between the GPU KV cache and a storage tier.
+
+    Positional arguments are the reference's (storage_offload_bindings.cpp:30-41).  Keyword-only
+    extensions select the B200-native host tier:
+      tier="file"        reference on-disk format under the given file paths (default, drop-in)
+      tier="host_arena"  pinned host DRAM arena of ``host_arena_bytes`` keyed by the same path strings
+    """
+
+    def __init__(self, io_threads: int, gpu_blocks_per_file: int, tensors: Sequence, read_preferring_workers: int,
+                 gds_mode: str = "disabled", max_write_queued_seconds: float = 10.0, *, tier: str = "file",
+                 host_arena_bytes: int = 0, chunk_bytes: int = 0, copy_variant: int = 0,
+                 strict_load_errors: bool = False):
+        if gds_mode != "disabled":
+            # GDS file tier is SURVEY §8(f) "next"; the reference itself falls back to the CPU
+            # staging path when GDS is unavailable (storage_offload.cpp:129-134).
+            gds_mode = "disabled"
+        lib = _lib.load()
+        self.pool = tensors if isinstance(tensors, KVPool) else KVPool(tensors)
+        opts = EngineOpts()
+        lib.kvb_engine_default_opts(C.byref(opts))
+        opts.io_threads = int(io_threads)
+        opts.gpu_blocks_per_file = int(gpu_blocks_per_file)
+        opts.read_preferring_workers = int(read_preferring_workers)
+        opts.max_write_queued_seconds = float(max_write_queued_seconds)
+        opts.tier = {"file": _lib.TIER_FILE, "host_arena": _lib.TIER_HOST_ARENA}[tier]
+        opts.copy_flags = int(copy_variant)
+        opts.host_arena_bytes = int(host_arena_bytes)
+        if chunk_bytes:
+            opts.chunk_bytes = int(chunk_bytes)
+        opts.strict_load_errors = 1 if strict_load_errors else 0
+        h = C.c_void_p()
+        check(lib.kvb_engine_create(self.pool.handle, C.byref(opts), C.byref(h)))
+        self._h = h
+        self.gpu_blocks_per_file = int(gpu_blocks_per_file)
+        self.tier = tier
+
+    # -- submit ---------------------------------------------------------------------------------
+    def _submit(self, fn, job_id: int, files: Sequence[str], all_block_ids: Sequence[Sequence[int]], stream):
+        if len(files) != len(all_block_ids):
+            raise ValueError("files and block id lists differ in length")
+        n = len(files)
+        paths = (C.c_char_p * max(n, 1))(*[f.encode() for f in files])
+        off = np.zeros(n + 1, dtype=np.int64)
+        for i, ids in enumerate(all_block_ids):
+            off[i + 1] = off[i] + len(ids)
+        flat = np.empty(int(off[-1]), dtype=np.int64)
+        for i, ids in enumerate(all_block_ids):
+            flat[off[i]:off[i + 1]] = np.asarray(ids, dtype=np.int64)
+        rc = fn(self._h, int(job_id), n, paths, flat.ctypes.data_as(C.POINTER(C.c_int64)),
+                off.ctypes.data_as(C.POINTER(C.c_int64)), _stream_ptr(stream))
+        if rc < 0:  # reference returns bool; errors are logged, not raised (storage_offload.cpp:338-347)
+            import sys
+            print(f"[kvb][ERROR] submit failed: {_lib.load().kvb_last_error().decode()}", file=sys.stderr)
+            return False
+        return True
+
+    def async_store_gpu_blocks(self, job_id: int, dst_files, all_block_ids, stream=None) -> bool:
+        return self._submit(_lib.load().kvb_engine_store, job_id, dst_files, all_block_ids, stream)
+
+    def async_load_gpu_blocks(self, job_id: int, src_files, all_block_ids, stream=None) -> bool:
+        return self._submit(_lib.load().kvb_engine_load, job_id, src_files, all_block_ids, stream)
+
+    # -- completion -----------------------------------------------------------------------------
+    def get_finished(self) -> list:
+        cap = 256
+        ids = (C.c_int64 * cap)()
+        ok = (C.c_int32 * cap)()
+        out = []
+        while True:
+            n = check(_lib.load().kvb_engine_poll(self._h, ids, ok, cap))
+            out.extend((int(ids[i]), bool(ok[i])) for i in range(n))
+            if n < cap:
+                return out
+
+    def wait_job(self, job_id: int) -> None:
+        check(_lib.load().kvb_engine_wait(self._h, int(job_id)))
+
+    def exists(self, file: str) -> bool:
+        return bool(_lib.load().kvb_engine_exists(self._h, file.encode()))
+
+    def arena_clear(self) -> None:
+        check(_lib.load().kvb_engine_arena_clear(self._h))
+
+    def stats(self) -> dict:
+        s = EngineStats()
+        check(_lib.load().kvb_engine_get_stats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in EngineStats._fields_}
+
+    def shutdown(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.load().kvb_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.shutdown()
+        except Exception:
+            pass

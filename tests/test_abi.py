@@ -1,0 +1,45 @@
+"""The C-ABI library loads and exports every symbol include/kvb.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "kvb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kvb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(kvb):
+    names = _declared()
+    assert len(names) >= 40
+    lib = ctypes.CDLL(os.path.join(ROOT, "llm-d-kv-cache_b200", "libkvb.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in kvb.h but not exported: {missing}"
+
+
+def test_binding_covers_header(kvb):
+    from importlib import import_module
+    sig = import_module("llm-d-kv-cache_b200._lib").SIGNATURES
+    assert sorted(sig) == _declared()
+
+
+def test_abi_version_and_no_device_is_loud(kvb):
+    assert kvb.lib.kvb_abi_version() == 1
+    if kvb.lib.kvb_device_count() == 0:
+        # no CPU fallback: compute entry points must fail, not silently compute on the host
+        tp = kvb.kvblock.ChunkedTokenDatabase(16, "")
+        import pytest
+        with pytest.raises(Exception):
+            tp.tokens_to_kv_block_keys(0, list(range(32)), "m")
+        with pytest.raises(Exception):
+            kvb.kvblock.Index(size=16)
+
+
+def test_header_cites_reference():
+    src = open(os.path.join(ROOT, "include", "kvb.h")).read()
+    for needle in ("tensor_copier.cu", "storage_offload.cpp", "token_processor.go", "in_memory.go",
+                   "kvblock_scorer.go", "indexer.go"):
+        assert needle in src
