@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""bench.py — KV-block offload throughput (save + load) on N x B200, one process per GPU.
+
+Metric (BASELINE.json): KV-block offload GB/s (save+load); blocks/sec.
+Workload at N=1 = BASELINE config #2: Llama-3-8B fp16 paged KV, 16-token blocks
+  64 canonical tensors x (12288 blocks x 32768 B), 10 000 random non-contiguous block ids,
+  one step = save the 10 000 blocks + load them back (2 x 20.97 GB of payload).
+Every rank runs the same workload on its own GPU / KV partition (weak scaling, no data-path collective).
+
+  value   device-resident: paged pool -> packed HBM (gather kernel) and back (scatter kernel); inputs in HBM.
+  e2e     through the reference-facing engine API (StorageOffloadEngine.async_store_gpu_blocks /
+          async_load_gpu_blocks, host-arena tier): D2H of every saved block to pinned host memory and H2D of
+          every loaded block inside the timed region.
+  roofline  gather kernel: 2 x payload bytes / CUDA-event time per launch vs the measured HBM copy peak.
+  cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref, built from /root/reference's own
+          csrc) storing to and loading from /dev/shm with its default per-(block x tensor) cudaMemcpyAsync path,
+          on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import importlib.util
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# ---- workload: BASELINE config #2 -------------------------------------------------------------------------
+T_TENSORS = 64          # K and V of 32 layers
+FRAG_BYTES = 32768      # 16 tok x 8 kv heads x 128 x fp16
+POOL_BLOCKS = int(os.environ.get("KVB_BENCH_POOL_BLOCKS", "12288"))   # env overrides exist ONLY for ncu captures
+N_BLOCKS = int(os.environ.get("KVB_BENCH_BLOCKS", "10000"))           # (a reduced run says so in config)
+BLOCK_BYTES = T_TENSORS * FRAG_BYTES          # 2 MiB
+BLOCKS_PER_FILE = 16                           # reference default: 256-token files / 16-token blocks (spec.py:50-85)
+REF_SAMPLE_BLOCKS = min(2048, N_BLOCKS)        # bounded sample for the reference arm (4.3 GB each way)
+
+
+def env_int(name, d):
+    v = os.environ.get(name)
+    return int(v) if v else d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_reference_engine():
+    """The unmodified reference engine built into oracle/_ref by oracle/ref_build/build_ref.py (or None)."""
+    so = os.path.join(ROOT, "oracle", "_ref", "storage_offload_ref.so")
+    if not os.path.exists(so):
+        return None, "oracle/_ref/storage_offload_ref.so not built"
+    try:
+        import torch  # noqa: F401  (libtorch must be loaded first)
+        spec = importlib.util.spec_from_file_location("storage_offload_ref", so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod, None
+    except Exception as e:
+        return None, f"cannot load reference engine: {e}"
+
+
+def reference_step(mod, tensors, ids, step_tag, io_threads, root="/dev/shm/kvb_ref_bench"):
+    """One save+load of `ids` through the reference engine (default memcpy path), files on tmpfs.
+    Returns seconds for (store, load)."""
+    import torch
+    bpf = BLOCKS_PER_FILE
+    n_files = (len(ids) + bpf - 1) // bpf
+    files = [f"{root}/{step_tag}/{i:06d}.bin" for i in range(n_files)]
+    first = len(ids) % bpf or bpf
+    groups, pos, take = [], 0, first
+    for _ in range(n_files):
+        groups.append([int(x) for x in ids[pos:pos + take]])
+        pos += take
+        take = bpf
+    eng = reference_step.engines.get(id(tensors[0]))
+    if eng is None:
+        eng = mod.StorageOffloadEngine(io_threads, bpf, tensors, max(1, int(io_threads * 0.75)), "disabled", 0.0)
+        reference_step.engines[id(tensors[0])] = eng
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.async_store_gpu_blocks(1, files, groups)
+    _drain(eng, 1)
+    t1 = time.perf_counter()
+    eng.async_load_gpu_blocks(2, files, groups)
+    _drain(eng, 2)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    shutil.rmtree(f"{root}/{step_tag}", ignore_errors=True)
+    return t1 - t0, t2 - t1
+
+
+reference_step.engines = {}
+
+
+def _drain(eng, job_id, timeout=600.0):
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < timeout:
+        for jid, ok in eng.get_finished():
+            if jid == job_id:
+                if not ok:
+                    raise RuntimeError(f"job {job_id} failed")
+                return
+        time.sleep(0.0005)
+    raise TimeoutError(f"job {job_id}")
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier_sync(dist):
+    import torch
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, x: float) -> float:
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    import torch
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    mod, why = load_reference_engine()
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
+    cores = os.cpu_count() or 1
+    io_threads = min(64, cores)
+    big = torch.empty((T_TENSORS, POOL_BLOCKS, FRAG_BYTES), dtype=torch.int8, device="cuda")
+    big.view(torch.uint8).random_(0, 256)
+    tensors = list(big.unbind(0))
+    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
+    kind = "reference"
+    if mod is None:
+        # oracle port: numpy pack/unpack of the same bytes on the host (single thread)
+        kind = "port"
+        from oracle import offload_oracle as oo
+        host = [t.cpu().numpy().view(np.uint8) for t in tensors]
+
+        def step(tag):
+            t0 = time.perf_counter()
+            p = oo.pack_blocks(host, ids)
+            oo.unpack_blocks(host, ids, p)
+            return time.perf_counter() - t0
+        io_threads = 1
+    else:
+        def step(tag):
+            a, b = reference_step(mod, tensors, ids, tag, io_threads)
+            return a + b
+    for w in range(args.warmup):
+        step(f"w{w}")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(f"s{k}")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    gbs = 2 * payload * args.steps / dt / 1e9
+    sample = (f"{REF_SAMPLE_BLOCKS} of the workload's {N_BLOCKS} blocks (seed-1 permutation prefix), "
+              f"save+load per step, {BLOCKS_PER_FILE} blocks/file on /dev/shm, default cudaMemcpyAsync copy path")
+    line = {
+        "impl": "reference", "metric": "kv_block_offload_gbps_save_plus_load", "value": gbs, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "blocks_per_s": 2 * REF_SAMPLE_BLOCKS * args.steps / dt,
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": io_threads, "kind": kind, "sample": sample,
+                         "host_cores": cores, **({"note": why} if why else {})},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    reference_step.engines.clear()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE config #2: Llama-3-8B fp16 paged-KV, 16-tok blocks, save+load 10k blocks GPU<->host",
+            "tensors": T_TENSORS, "fragment_bytes": FRAG_BYTES, "block_bytes": BLOCK_BYTES, "pool_blocks": POOL_BLOCKS,
+            "blocks_per_step": N_BLOCKS, "block_ids": f"rng(1).permutation({POOL_BLOCKS})[:{N_BLOCKS}] (non-contiguous, unsorted)",
+            "gpu_blocks_per_file": BLOCKS_PER_FILE, "partitioning": f"{n_gpus} independent KV partitions (one per GPU)",
+            "l2_policy": "inputs_exceed_l2 (20.97 GB per pass vs 126 MB L2)"}
+
+
+def run_ours(args):
+    import torch
+    rank, world, local, dist = dist_setup(args.gpus)
+    kvb = importlib.import_module("llm-d-kv-cache_b200")
+    lib = kvb.lib
+
+    # ---- data: pool resident in HBM, random bytes, random block table
+    big = torch.empty((T_TENSORS, POOL_BLOCKS, FRAG_BYTES), dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(42 + rank)
+    big.random_(0, 256, generator=g)
+    tensors = list(big.unbind(0))
+    pool = kvb.pool.KVPool(tensors)
+    ids_np = np.random.default_rng(1).permutation(POOL_BLOCKS)[:N_BLOCKS].astype(np.int64)
+    ids_dev = torch.from_numpy(ids_np).cuda()
+    packed = torch.empty(N_BLOCKS * BLOCK_BYTES, dtype=torch.uint8, device="cuda")
+    payload = N_BLOCKS * BLOCK_BYTES
+    check_ids = ids_dev[:: max(1, N_BLOCKS // 64)]
+    check_ref = [t[check_ids].clone() for t in tensors[::8]]
+
+    # ---- device-resident arm: gather + scatter, every launch timed with CUDA events on its own stream
+    def dev_step(evs=None):
+        if evs is not None:
+            evs[0].record()
+        pool.gather_dev(ids_dev, packed)
+        if evs is not None:
+            evs[1].record()
+        pool.scatter_dev(ids_dev, packed)
+        if evs is not None:
+            evs[2].record()
+
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local)
+    launches0 = lib.kvb_launch_count()
+    barrier_sync(dist)
+    if rank == 0:
+        sampler.start()
+    ev_sets = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.steps):
+        dev_step(ev_sets[k])
+    stop.record()
+    barrier_sync(dist)
+    dev_ms = max_over_ranks(dist, start.elapsed_time(stop))
+    launches_dev = lib.kvb_launch_count() - launches0
+    gather_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev_sets]))
+    scatter_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev_sets]))
+    for t, r in zip(tensors[::8], check_ref):
+        assert torch.equal(t[check_ids], r), "device-resident save+load did not restore the pool bit-exact"
+    value = world * 2 * payload * args.steps / (dev_ms / 1e3) / 1e9
+    del packed
+    torch.cuda.empty_cache()
+
+    # ---- e2e arm: reference-facing engine API, host-arena tier, D2H + H2D inside the timed region
+    bpf = BLOCKS_PER_FILE
+    n_files = N_BLOCKS // bpf
+    groups = [ids_np[i * bpf:(i + 1) * bpf].tolist() for i in range(n_files)]
+    eng = kvb.engine.StorageOffloadEngine(env_int("KVB_BENCH_IO_THREADS", 4), bpf, tensors, 3, "disabled", 0.0,
+                                          tier="host_arena", host_arena_bytes=payload + (64 << 20),
+                                          chunk_bytes=env_int("KVB_BENCH_CHUNK_MB", 64) << 20)
+    job = [0]
+
+    def e2e_step(tag):
+        files = [f"{tag}/{i:06d}" for i in range(n_files)]
+        job[0] += 1
+        assert eng.async_store_gpu_blocks(job[0], files, groups)
+        _drain(eng, job[0])
+        t_mid = time.perf_counter()
+        job[0] += 1
+        assert eng.async_load_gpu_blocks(job[0], files, groups)
+        _drain(eng, job[0])
+        eng.arena_clear()
+        return t_mid
+
+    for w in range(args.warmup):
+        e2e_step(f"w{w}")
+    stats0 = eng.stats()
+    launches1 = lib.kvb_launch_count()
+    barrier_sync(dist)
+    t0 = time.perf_counter()
+    store_s = 0.0
+    for k in range(args.steps):
+        ts = time.perf_counter()
+        store_s += e2e_step(f"s{k}") - ts
+    barrier_sync(dist)
+    e2e_s = max_over_ranks(dist, time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_e2e = lib.kvb_launch_count() - launches1
+    stats1 = eng.stats()
+    for t, r in zip(tensors[::8], check_ref):
+        assert torch.equal(t[check_ids], r), "engine save+load did not restore the pool bit-exact"
+    e2e_gbs = world * 2 * payload * args.steps / e2e_s / 1e9
+    h2d = (stats1["h2d_bytes"] - stats0["h2d_bytes"]) // args.steps
+    d2h = (stats1["d2h_bytes"] - stats0["d2h_bytes"]) // args.steps
+    eng.shutdown()
+
+    # ---- cpu baseline (rank 0, N=1 only): the reference engine on a bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(tensors)
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        achieved = 2 * payload / (gather_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gather_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_bench")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "kv_block_offload_gbps_save_plus_load", "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world),
+            "blocks_per_s": world * 2 * N_BLOCKS * args.steps / (dev_ms / 1e3),
+            "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "blocks_per_s": world * 2 * N_BLOCKS * args.steps / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "store_gbs": world * payload * args.steps / store_s / 1e9,
+                    "load_gbs": world * payload * args.steps / max(e2e_s - store_s, 1e-9) / 1e9,
+                    "api": "StorageOffloadEngine.async_store_gpu_blocks/async_load_gpu_blocks/get_finished, tier=host_arena (pinned)"},
+            "gpu_launches": int(launches_dev + launches_e2e),
+            "roofline": {"kernel": "paged_copy_bulk_kernel<gather>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 2 * payload, "gather_ms": gather_ms, "scatter_ms": scatter_ms,
+                         "scatter_achieved": 2 * payload / (scatter_ms / 1e3) / 1e9,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cpu_baseline(tensors):
+    """Reference engine (oracle/_ref) on a bounded sample of the same workload, same box, same run."""
+    import torch
+    cores = os.cpu_count() or 1
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
+    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
+    mod, why = load_reference_engine()
+    sample = (f"{REF_SAMPLE_BLOCKS} of the workload's {N_BLOCKS} blocks, save+load once after one warm-up pass, "
+              f"{BLOCKS_PER_FILE} blocks/file on /dev/shm")
+    if mod is not None:
+        io_threads = min(64, cores)
+        i8 = [t.view(torch.int8) for t in tensors]
+        try:
+            reference_step(mod, i8, ids[:256], "warm", io_threads)
+            a, b = reference_step(mod, i8, ids, "base", io_threads)
+            reference_step.engines.clear()
+            return {"value": 2 * payload / (a + b) / 1e9, "unit": "GB/s", "cores": io_threads, "kind": "reference",
+                    "sample": sample + ", default cudaMemcpyAsync path, io_threads=min(64,nproc)",
+                    "store_gbs": payload / a / 1e9, "load_gbs": payload / b / 1e9, "host_cores": cores}
+        except Exception as e:
+            why = f"reference engine failed: {e}"
+    from oracle import offload_oracle as oo
+    n = 256
+    host = [t[:2048].cpu().numpy() for t in tensors]
+    sub = np.random.default_rng(1).permutation(2048)[:n].astype(np.int64)
+    t0 = time.perf_counter()
+    p = oo.pack_blocks(host, sub)
+    oo.unpack_blocks(host, sub, p)
+    dt = time.perf_counter() - t0
+    return {"value": 2 * n * BLOCK_BYTES / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"{n} blocks of the same shape, numpy pack+unpack (oracle port)", "note": why, "host_cores": cores}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -262,7 +262,7 @@ static const Tuning& tuning() {
     x.default_variant = env_int("KVB_COPY_VARIANT", KVB_COPY_BULK);
     x.ldg_unroll = env_int("KVB_LDG_UNROLL", 4);
     x.ldg_ctas_per_sm = env_int("KVB_LDG_CTAS_PER_SM", 8);
-    x.bulk_piece = env_int("KVB_BULK_PIECE", 16384);
+    x.bulk_piece = env_int("KVB_BULK_PIECE", 8192);
     x.bulk_ctas_per_sm = env_int("KVB_BULK_CTAS_PER_SM", 2);
     x.bulk_deep = env_int("KVB_BULK_DEEP", 0);
     return x;
@@ -280,9 +280,14 @@ static cudaError_t launch_ldg_v(const CopyArgs& a, int grid, int unroll, cudaStr
   return cudaGetLastError();
 }
 
+// flags layout (debug / tuning sweeps; 0 everywhere = library defaults):
+//   bits 0-7  KVB_COPY_* variant      bits 8-11  LDG unroll (2/4/8) or BULK depth code+1 (1..3)
+//   bits 12-19 CTAs per SM            bits 20-23 BULK piece = 1 KiB << code (code 1..6)
 template <int MODE>
-static cudaError_t launch_ldg(CopyArgs a, int vec, int device, cudaStream_t s) {
-  const Tuning& t = tuning();
+static cudaError_t launch_ldg(CopyArgs a, int vec, int device, cudaStream_t s, int flags) {
+  Tuning t = tuning();
+  if ((flags >> 8) & 0xf) t.ldg_unroll = (flags >> 8) & 0xf;
+  if ((flags >> 12) & 0xff) t.ldg_ctas_per_sm = (flags >> 12) & 0xff;
   int unroll = (t.ldg_unroll == 2 || t.ldg_unroll == 8) ? t.ldg_unroll : 4;
   a.piece = (uint32_t)(kLdgThreads * unroll * vec);
   a.ppf = (uint32_t)((a.frag + a.piece - 1) / a.piece);
@@ -302,27 +307,31 @@ static cudaError_t launch_ldg(CopyArgs a, int vec, int device, cudaStream_t s) {
 template <int MODE, int STAGES, int LOOKAHEAD>
 static cudaError_t launch_bulk_cfg(const CopyArgs& a, int grid, size_t smem, cudaStream_t s) {
   auto k = paged_copy_bulk_kernel<MODE, STAGES, LOOKAHEAD>;
-  static std::once_flag once[8];  // per device would be ideal; attribute is per-function-per-device
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  (void)once;
   if (e != cudaSuccess) return e;
   k<<<grid, 32, smem, s>>>(a);
   return cudaGetLastError();
 }
 
 template <int MODE>
-static cudaError_t launch_bulk(CopyArgs a, int device, cudaStream_t s) {
-  const Tuning& t = tuning();
+static cudaError_t launch_bulk(CopyArgs a, int device, cudaStream_t s, int flags) {
+  Tuning t = tuning();
+  if ((flags >> 8) & 0xf) t.bulk_deep = ((flags >> 8) & 0xf) - 1;
+  if ((flags >> 12) & 0xff) t.bulk_ctas_per_sm = (flags >> 12) & 0xff;
+  if ((flags >> 20) & 0xf) t.bulk_piece = 1024 << ((flags >> 20) & 0xf);
   int piece = t.bulk_piece;
   if (piece < 1024 || piece % 16) piece = 16384;
+  const int stages = t.bulk_deep == 2 ? 12 : (t.bulk_deep == 1 ? 8 : 6);
+  const int ctas = std::max(1, t.bulk_ctas_per_sm);
+  // the rings of all resident CTAs must fit the SM's 227 KB of shared memory
+  while (piece > 1024 && (size_t)piece * stages * ctas > 224u * 1024u) piece >>= 1;
   if ((int64_t)piece > a.frag) piece = (int)a.frag;  // frag is a multiple of 16 here
   a.piece = (uint32_t)piece;
   a.ppf = (uint32_t)((a.frag + a.piece - 1) / a.piece);
   const uint64_t frags = a.total_items;
   a.total_items = frags * a.ppf;
-  const int stages = t.bulk_deep == 2 ? 12 : (t.bulk_deep == 1 ? 8 : 6);
   size_t smem = (size_t)stages * a.piece;
-  uint64_t cap = (uint64_t)sm_count(device) * (uint64_t)std::max(1, t.bulk_ctas_per_sm);
+  uint64_t cap = (uint64_t)sm_count(device) * (uint64_t)ctas;
   int grid = (int)std::min<uint64_t>(a.total_items, cap);
   if (grid < 1) grid = 1;
   switch (stages) {
@@ -339,7 +348,8 @@ static int launch_copy(CopyArgs a, int vec, int device, cudaStream_t s, int flag
   if (variant == KVB_COPY_DEFAULT) variant = tuning().default_variant;
   // TMA bulk copies need 16 B aligned addresses and sizes; other shapes take the vector mover
   if (variant == KVB_COPY_BULK && vec != 16) variant = KVB_COPY_LDG;
-  cudaError_t e = (variant == KVB_COPY_BULK) ? launch_bulk<MODE>(a, device, s) : launch_ldg<MODE>(a, vec, device, s);
+  cudaError_t e = (variant == KVB_COPY_BULK) ? launch_bulk<MODE>(a, device, s, flags)
+                                             : launch_ldg<MODE>(a, vec, device, s, flags);
   if (e != cudaSuccess) {
     set_error("paged copy launch failed: %s", cudaGetErrorString(e));
     return KVB_ERR_CUDA;

@@ -143,7 +143,7 @@ class ChunkedTokenDatabase:
         parents = np.empty(n, dtype=np.uint64)
         for i in range(n):
             pk = 0 if parent_keys is None else int(parent_keys[i])
-            parents[i] = pk if pk != EMPTY_BLOCK_HASH else self.get_init_hash(model_names[i])  # :181-186
+            parents[i] = np.uint64(pk if pk != EMPTY_BLOCK_HASH else self.get_init_hash(model_names[i]))  # :181-186
         nblk = lens // self._block_size
         extra = extra_off = None
         if extra_features is not None and any(ef is not None for ef in extra_features):
@@ -320,7 +320,12 @@ class Index:
         for i in range(min(int(cut.value), keys.size)):
             c = int(counts[i])
             if c > 0:
-                out[int(keys[i])] = [self._entry_from_c(ents[i * MAX_PODS_PER_KEY + e]) for e in range(c)]
+                found = [self._entry_from_c(ents[i * MAX_PODS_PER_KEY + e]) for e in range(c)]
+                k = int(keys[i])
+                if nf and k in out:
+                    out[k].extend(found)  # filtered path APPENDS per occurrence of a repeated key (in_memory.go:131-137)
+                else:
+                    out[k] = found        # unfiltered path assigns (in_memory.go:128-130)
         return out
 
     def __len__(self) -> int:

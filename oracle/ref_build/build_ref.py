@@ -39,6 +39,12 @@ def build(verbose: bool = False) -> str | None:
         if os.path.getmtime(so) >= newest:
             return so
     os.makedirs(OUT, exist_ok=True)
+    # The image's default CXX (/opt/gcc/bin/g++ wrapper) links libstdc++ STATICALLY; a second libstdc++ inside a
+    # torch extension segfaults at first iostream use (the reference's own setup.py:52-56 warns about this), so
+    # build with the distribution compiler, which links libstdc++.so.6 dynamically.
+    for var, exe in (("CXX", "/usr/bin/g++"), ("CC", "/usr/bin/gcc")):
+        if os.path.exists(exe):
+            os.environ[var] = exe
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
     os.environ.setdefault("MAX_JOBS", "8")
     from torch.utils.cpp_extension import load
@@ -53,7 +59,7 @@ def build(verbose: bool = False) -> str | None:
             os.path.join(CSRC, "backends/fs_gds"),
         ],
         extra_cflags=["-O3", "-std=c++17", "-fopenmp"],
-        extra_cuda_cflags=["-O3", "-std=c++17", "-Xcompiler", "-fopenmp"],
+        extra_cuda_cflags=["-O3", "-std=c++17", "-Xcompiler", "-fopenmp", "-ccbin", os.environ.get("CXX", "g++")],
         extra_ldflags=["-ldl"],
         build_directory=OUT,
         is_python_module=False,

@@ -1,0 +1,264 @@
+"""Offload engine (save_blocks / load_blocks) through the reference-shaped handlers: bit-exact round trips,
+reference file layout, host-arena tier, skip-existing, cancel and failure behaviour."""
+import hashlib
+import math
+import os
+import shutil
+import struct
+import time
+
+import numpy as np
+import pytest
+
+from oracle import offload_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+TMP_DIR = "/tmp/kvb-shared-kv-test"
+
+
+def _kv_tensors(torch, num_layers, num_blocks, block_size, num_heads, head_size, dtype, seed=42):
+    """Same construction as the reference test (tests/test_fs_backend.py:45-58): (2, N, bs, H, D) per layer."""
+    torch.manual_seed(seed)
+    shape = (2, num_blocks, block_size, num_heads, head_size)
+    return [torch.rand(shape, dtype=dtype, device="cuda") for _ in range(num_layers)]
+
+
+def _canonical(torch, kv_tensors):
+    """K and V halves of every layer as (num_blocks, page_bytes) int8 views (tests/test_fs_backend.py:61-97)."""
+    out = []
+    for t in kv_tensors:
+        n = t.shape[1]
+        half = t.stride(1) * t.element_size()
+        raw = torch.tensor([], dtype=torch.int8, device=t.device).set_(t.untyped_storage()).view(2, n, half)
+        out.extend(raw.unbind(0))
+    return out
+
+
+def _hash(tokens):
+    buf = b"".join(struct.pack("<I", int(t) & 0xFFFFFFFF) for t in tokens)
+    return int.from_bytes(hashlib.sha256(buf).digest()[:8], "big").to_bytes(8, "little")
+
+
+def _hashes(n, start=0):
+    return [_hash(range(100 + (start + i) * 100, 117 + (start + i) * 100)) for i in range(n)]
+
+
+def _wait(handler, job_id, timeout=20.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        for r in handler.get_finished():
+            if r.job_id == job_id:
+                return r
+        time.sleep(0.002)
+    raise TimeoutError(job_id)
+
+
+def _mapper(kvb, bpf, root=TMP_DIR, dtype="torch.float16"):
+    return kvb.file_mapper.FileMapper(root, "llama3-70b", 16, bpf, 1, 1, 1, 0, dtype)
+
+
+@pytest.fixture(autouse=True)
+def _clean():
+    shutil.rmtree(TMP_DIR, ignore_errors=True)
+    yield
+    shutil.rmtree(TMP_DIR, ignore_errors=True)
+
+
+@pytest.mark.parametrize("tier", ["file", "host_arena"])
+@pytest.mark.parametrize("gpu_blocks_per_file", [1, 2, 4, 8])
+@pytest.mark.parametrize("start_idx", [0, 3])
+def test_roundtrip_param(kvb, torch_cuda, tier, gpu_blocks_per_file, start_idx):
+    """Mirror of test_fs_backend_roundtrip_param (tests/test_fs_backend.py:353-411): Llama-70B-like shapes,
+    8 blocks, write all, read back blocks start_idx.. into a zeroed cache, bit-exact."""
+    torch = torch_cuda
+    W, M = kvb.worker, kvb.mediums
+    num_layers, block_size, num_heads, head_size, num_blocks = 80, 16, 64, 128, 8
+    original = _kv_tensors(torch, num_layers, num_blocks, block_size, num_heads, head_size, torch.float16)
+    restored = [torch.zeros_like(t) for t in original]
+    write_ids, read_ids = list(range(num_blocks)), list(range(start_idx, num_blocks))
+    fm = _mapper(kvb, gpu_blocks_per_file)
+    extra = {"tier": tier, "host_arena_bytes": 1 << 30}
+    put_files = math.ceil(len(write_ids) / gpu_blocks_per_file)
+    hashes = _hashes(put_files)
+
+    h_put = W.StorageOffloadingHandlers(_canonical(torch, original), fm, 16, gpu_blocks_per_file, 8, extra_config=extra)
+    put = h_put.gpu_to_storage_handler
+    assert put.transfer_async(1, (M.GPULoadStoreSpec(write_ids), M.SharedStorageLoadStoreSpec(hashes)))
+    r = _wait(put, 1)
+    assert r.success and r.transfer_size > 0 and r.transfer_time > 0 and r.transfer_type == ("GPU", "SHARED_STORAGE")
+    for h in hashes:
+        assert h_put.engine.exists(fm.get_file_name(h))
+        if tier == "file":
+            assert os.path.exists(fm.get_file_name(h))
+
+    if tier == "file":   # a second engine (fresh process state) reads what the first one wrote
+        h_get = W.StorageOffloadingHandlers(_canonical(torch, restored), fm, 16, gpu_blocks_per_file, 8, extra_config=extra)
+        get = h_get.storage_to_gpu_handler
+    else:                # the arena lives inside the engine: reuse it, but load into the zeroed cache
+        h_get = None
+        eng = h_put.engine
+        pool2 = kvb.pool.KVPool(_canonical(torch, restored))
+    get_files = math.ceil(len(read_ids) / gpu_blocks_per_file)
+    get_hashes = hashes[len(hashes) - get_files:]
+    if tier == "file":
+        assert get.transfer_async(2, (M.SharedStorageLoadStoreSpec(get_hashes), M.GPULoadStoreSpec(read_ids)))
+        r = _wait(get, 2)
+        assert r.success and r.transfer_type == ("SHARED_STORAGE", "GPU")
+        for o_t, r_t in zip(original, restored):
+            for b in read_ids:
+                assert torch.equal(o_t[:, b], r_t[:, b])
+            for b in range(start_idx):
+                assert int(r_t[:, b].abs().sum()) == 0        # blocks that were not requested stay untouched
+    else:
+        # zero the source cache, load back into it through the same engine, compare with a saved copy
+        saved = [t.clone() for t in original]
+        for t in original:
+            t.zero_()
+        get = h_put.storage_to_gpu_handler
+        assert get.transfer_async(2, (M.SharedStorageLoadStoreSpec(get_hashes), M.GPULoadStoreSpec(read_ids)))
+        assert _wait(get, 2).success
+        for s_t, o_t in zip(saved, original):
+            for b in read_ids:
+                assert torch.equal(s_t[:, b], o_t[:, b])
+            for b in range(start_idx):
+                assert int(o_t[:, b].abs().sum()) == 0
+
+
+def test_file_bytes_match_reference_layout(kvb, torch_cuda):
+    """The bytes on disk are the reference CPU-path image: max(bpf*block,16MiB) long, blocks tail-aligned."""
+    torch = torch_cuda
+    T, N, frag, bpf = 6, 32, 4096, 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tensors = [torch.randint(0, 256, (N, frag), dtype=torch.uint8, device="cuda", generator=g) for _ in range(T)]
+    np_t = [t.cpu().numpy() for t in tensors]
+    eng = kvb.engine.StorageOffloadEngine(4, bpf, tensors, 3, "disabled", 0.0)
+    os.makedirs(TMP_DIR, exist_ok=True)
+    groups = [[5, 9], [1, 2, 3, 4], [31, 0, 30, 7]]                # first file partial, like the handlers produce
+    files = [f"{TMP_DIR}/a/b/f{i}.bin" for i in range(3)]
+    assert eng.async_store_gpu_blocks(7, files, groups)
+    eng.wait_job(7)   # NB: wait cancels *queued* work only; poll below confirms completion
+    t0 = time.time()
+    done = []
+    while not done and time.time() - t0 < 10:
+        done = [j for j in eng.get_finished() if j[0] == 7]
+    assert done == [(7, True)]
+    for f, ids in zip(files, groups):
+        if not os.path.exists(f):
+            continue
+        img = np.fromfile(f, dtype=np.uint8)
+        assert np.array_equal(img, oo.file_image(np_t, ids, bpf))
+    # partial tail read: asking the 4-block file for its last 2 blocks returns blocks 3 and 4's data
+    zero = [torch.zeros_like(t) for t in tensors]
+    eng2 = kvb.engine.StorageOffloadEngine(2, bpf, zero, 1, "disabled", 0.0)
+    if os.path.exists(files[1]):
+        assert eng2.async_load_gpu_blocks(8, [files[1]], [[10, 11]])
+        while not eng2.get_finished():
+            time.sleep(0.001)
+        for z, t in zip(zero, tensors):
+            assert torch.equal(z[10], t[3]) and torch.equal(z[11], t[4])
+    eng.shutdown()
+    eng2.shutdown()
+
+
+def test_store_skips_existing_and_counts(kvb, torch_cuda):
+    torch = torch_cuda
+    tensors = [torch.randint(0, 256, (16, 1024), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    for tier in ("file", "host_arena"):
+        eng = kvb.engine.StorageOffloadEngine(2, 2, tensors, 1, "disabled", 0.0, tier=tier, host_arena_bytes=1 << 24)
+        f = [f"{TMP_DIR}/{tier}/x.bin", f"{TMP_DIR}/{tier}/y.bin"]
+        assert eng.async_store_gpu_blocks(1, f, [[0, 1], [2, 3]])
+        while not eng.get_finished():
+            time.sleep(0.001)
+        keep = [t.clone() for t in tensors]
+        for t in tensors:
+            t[0:4] = 7                                            # change the blocks, store again under the same names
+        assert eng.async_store_gpu_blocks(2, f, [[0, 1], [2, 3]])
+        while not eng.get_finished():
+            time.sleep(0.001)
+        st = eng.stats()
+        assert st["files_stored"] == 2 and st["files_skipped_existing"] == 2   # second store wrote nothing
+        for t in tensors:
+            t[0:4] = 0
+        assert eng.async_load_gpu_blocks(3, f, [[0, 1], [2, 3]])
+        while not eng.get_finished():
+            time.sleep(0.001)
+        for t, k in zip(tensors, keep):
+            assert torch.equal(t[0:4], k[0:4])                   # the FIRST version is what the tier holds
+        eng.shutdown()
+
+
+def test_missing_file_load_reporting(kvb, torch_cuda):
+    torch = torch_cuda
+    tensors = [torch.zeros((8, 512), dtype=torch.uint8, device="cuda")]
+    # reference behaviour: read failures are swallowed, job still succeeds (storage_offload.cpp:378-383)
+    eng = kvb.engine.StorageOffloadEngine(1, 1, tensors, 1, "disabled", 0.0)
+    assert eng.async_load_gpu_blocks(1, [f"{TMP_DIR}/nope.bin"], [[0]])
+    res = []
+    while not res:
+        res = eng.get_finished()
+    assert res == [(1, True)] and eng.stats()["load_failures"] == 1
+    eng.shutdown()
+    strict = kvb.engine.StorageOffloadEngine(1, 1, tensors, 1, "disabled", 0.0, strict_load_errors=True)
+    assert strict.async_load_gpu_blocks(2, [f"{TMP_DIR}/nope.bin"], [[0]])
+    res = []
+    while not res:
+        res = strict.get_finished()
+    assert res == [(2, False)]
+    # invalid submissions are refused up front (False), not crashed on
+    assert not strict.async_store_gpu_blocks(3, ["a"], [[99]])          # block id out of range
+    assert not strict.async_store_gpu_blocks(4, ["a"], [[0, 1]])        # more blocks than gpu_blocks_per_file
+    strict.wait_job(12345)                                               # unknown job: returns
+    strict.shutdown()
+
+
+def test_many_jobs_priority_and_wait(kvb, torch_cuda):
+    """Several concurrent jobs in both directions; every job is reported exactly once."""
+    torch = torch_cuda
+    T, N, frag, bpf = 8, 256, 8192, 4
+    g = torch.Generator(device="cuda").manual_seed(3)
+    tensors = [torch.randint(0, 256, (N, frag), dtype=torch.uint8, device="cuda", generator=g) for _ in range(T)]
+    ref = [t.clone() for t in tensors]
+    eng = kvb.engine.StorageOffloadEngine(4, bpf, tensors, 3, "disabled", 0.0, tier="host_arena",
+                                          host_arena_bytes=N * T * frag * 2, chunk_bytes=1 << 20)
+    perm = np.random.default_rng(0).permutation(N)
+    jobs = {}
+    for j in range(8):
+        ids = perm[j * 32:(j + 1) * 32]
+        files = [f"job{j}/f{i}" for i in range(8)]
+        groups = [ids[i * 4:(i + 1) * 4].tolist() for i in range(8)]
+        jobs[j] = (files, groups)
+        assert eng.async_store_gpu_blocks(j, files, groups)
+    seen = {}
+    t0 = time.time()
+    while len(seen) < 8 and time.time() - t0 < 30:
+        for jid, ok in eng.get_finished():
+            assert jid not in seen
+            seen[jid] = ok
+    assert seen == {j: True for j in range(8)}
+    for t in tensors:
+        t.zero_()
+    for j in range(8):
+        assert eng.async_load_gpu_blocks(100 + j, *jobs[j])
+    for j in range(8):
+        eng.wait_job(100 + j)
+    fin = dict(eng.get_finished())
+    assert fin == {100 + j: True for j in range(8)}
+    for t, r in zip(tensors, ref):
+        assert torch.equal(t, r)
+    st = eng.stats()
+    assert st["bytes_stored"] == st["bytes_loaded"] == N * T * frag
+    eng.shutdown()
+
+
+def test_arena_eviction_lru(kvb, torch_cuda):
+    torch = torch_cuda
+    tensors = [torch.randint(0, 256, (8, 1 << 16), dtype=torch.uint8, device="cuda")]
+    eng = kvb.engine.StorageOffloadEngine(1, 1, tensors, 1, "disabled", 0.0, tier="host_arena",
+                                          host_arena_bytes=3 << 16)      # room for 3 blocks
+    for i in range(5):
+        assert eng.async_store_gpu_blocks(i, [f"k{i}"], [[i]])
+        while not eng.get_finished():
+            time.sleep(0.001)
+    assert [eng.exists(f"k{i}") for i in range(5)] == [False, False, True, True, True]
+    eng.shutdown()

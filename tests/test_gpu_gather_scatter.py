@@ -1,0 +1,141 @@
+"""Parity of the paged-KV gather / scatter kernels (through the C ABI) against the oracle layout."""
+import numpy as np
+import pytest
+
+from oracle import offload_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+LDG, BULK = 1, 2
+
+
+def _make_pool(torch, T, N, frag, seed=42, separate=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if separate:
+        tensors = [torch.randint(0, 256, (N, frag), dtype=torch.uint8, device="cuda", generator=g) for _ in range(T)]
+    else:  # one allocation, T views (like K/V halves of a layer tensor)
+        big = torch.randint(0, 256, (T, N, frag), dtype=torch.uint8, device="cuda", generator=g)
+        tensors = list(big.unbind(0))
+    return tensors
+
+
+def _np(tensors):
+    return [t.cpu().numpy() for t in tensors]
+
+
+@pytest.mark.parametrize("variant", [LDG, BULK])
+@pytest.mark.parametrize("T,N,frag", [(4, 64, 32768), (64, 40, 32768), (160, 24, 16384), (3, 50, 4096),
+                                      (2, 33, 48), (5, 17, 16400), (1, 9, 1 << 20)])
+def test_gather_matches_oracle(kvb, torch_cuda, variant, T, N, frag):
+    torch = torch_cuda
+    tensors = _make_pool(torch, T, N, frag)
+    pool = kvb.pool.KVPool(tensors)
+    ids = np.random.default_rng(1).permutation(N)[: max(1, N // 2)].astype(np.int64)
+    packed = torch.zeros(ids.size * T * frag, dtype=torch.uint8, device="cuda")
+    pool.gather(ids, packed, flags=variant)
+    torch.cuda.synchronize()
+    assert np.array_equal(packed.cpu().numpy(), oo.pack_blocks(_np(tensors), ids))
+
+
+@pytest.mark.parametrize("variant", [LDG, BULK])
+@pytest.mark.parametrize("T,N,frag", [(4, 64, 32768), (160, 24, 16384), (2, 33, 48), (5, 17, 16400)])
+def test_scatter_matches_oracle(kvb, torch_cuda, variant, T, N, frag):
+    torch = torch_cuda
+    tensors = _make_pool(torch, T, N, frag, seed=3)
+    before = _np(tensors)
+    pool = kvb.pool.KVPool(tensors)
+    ids = np.random.default_rng(2).permutation(N)[: max(1, N // 3)].astype(np.int64)
+    packed_np = np.random.default_rng(5).integers(0, 256, ids.size * T * frag, dtype=np.uint8)
+    packed = torch.from_numpy(packed_np).cuda()
+    pool.scatter(ids, packed, flags=variant)
+    torch.cuda.synchronize()
+    oo.unpack_blocks(before, ids, packed_np)
+    for t, ref in zip(tensors, before):
+        assert np.array_equal(t.cpu().numpy(), ref)   # listed blocks rewritten, every other block untouched
+
+
+@pytest.mark.parametrize("frag", [1, 3, 4, 6, 8, 20, 100, 1000, 4097])
+def test_ragged_fragment_sizes(kvb, torch_cuda, frag):
+    """Sizes that are not multiples of 16 B take the narrower vector movers (1/4/8 B)."""
+    torch = torch_cuda
+    tensors = _make_pool(torch, 3, 21, frag, seed=9)
+    pool = kvb.pool.KVPool(tensors)
+    ids = np.array([20, 0, 7, 13], dtype=np.int64)
+    packed = torch.zeros(ids.size * 3 * frag, dtype=torch.uint8, device="cuda")
+    pool.gather(ids, packed)
+    torch.cuda.synchronize()
+    assert np.array_equal(packed.cpu().numpy(), oo.pack_blocks(_np(tensors), ids))
+
+
+def test_views_of_one_allocation_and_offset_packed(kvb, torch_cuda):
+    torch = torch_cuda
+    tensors = _make_pool(torch, 6, 30, 8192, separate=False)
+    pool = kvb.pool.KVPool(tensors)
+    ids = np.arange(29, -1, -3, dtype=np.int64)
+    buf = torch.zeros(ids.size * 6 * 8192 + 64, dtype=torch.uint8, device="cuda")
+    packed = buf[16:16 + ids.size * 6 * 8192]
+    pool.gather(ids, packed, flags=BULK)
+    torch.cuda.synchronize()
+    assert np.array_equal(packed.cpu().numpy(), oo.pack_blocks(_np(tensors), ids))
+    assert int(buf[:16].sum()) == 0 and int(buf[16 + ids.size * 6 * 8192:].sum()) == 0
+
+
+def test_empty_and_invalid(kvb, torch_cuda):
+    torch = torch_cuda
+    tensors = _make_pool(torch, 2, 8, 256)
+    pool = kvb.pool.KVPool(tensors)
+    packed = torch.zeros(8 * 2 * 256, dtype=torch.uint8, device="cuda")
+    pool.gather(np.zeros(0, dtype=np.int64), packed)            # empty list is a no-op
+    for bad in ([8], [-1], [0, 99]):
+        with pytest.raises(Exception):
+            pool.gather(np.array(bad, dtype=np.int64), packed)  # out-of-range ids are rejected, not clamped
+    with pytest.raises(Exception):
+        kvb.pool.KVPool([])
+    # repeated ids in a gather are legal (same block packed twice)
+    pool.gather(np.array([3, 3, 1], dtype=np.int64), packed)
+    torch.cuda.synchronize()
+    assert np.array_equal(packed.cpu().numpy()[: 3 * 512], oo.pack_blocks(_np(tensors), [3, 3, 1]))
+
+
+@pytest.mark.parametrize("variant", [LDG, BULK])
+def test_full_size_roundtrip_llama8b(kvb, torch_cuda, variant):
+    """BASELINE config #2 shape at reduced block count: gather -> zero pool -> scatter restores bit-exact,
+    and the packed buffer's checksum equals the checksum of the gathered pages (size-independent properties)."""
+    torch = torch_cuda
+    T, frag, N, n = 64, 32768, 1536, 1200
+    tensors = _make_pool(torch, T, N, frag, seed=42)
+    ref = [t.clone() for t in tensors]
+    pool = kvb.pool.KVPool(tensors)
+    ids = np.random.default_rng(1).permutation(N)[:n].astype(np.int64)
+    ids_dev = torch.from_numpy(ids).cuda()
+    packed = torch.empty(n * T * frag, dtype=torch.uint8, device="cuda")
+    pool.gather_dev(ids_dev, packed, flags=variant)
+    s_packed = int(packed.view(torch.int64).sum().item())
+    s_pages = sum(int(t[ids_dev].contiguous().view(torch.int64).sum().item()) for t in ref)
+    assert (s_packed - s_pages) % (1 << 64) == 0
+    for t in tensors:
+        t[ids_dev] = 0
+    pool.scatter_dev(ids_dev, packed, flags=variant)
+    torch.cuda.synchronize()
+    for t, r in zip(tensors, ref):
+        assert torch.equal(t, r)
+
+
+def test_migrate_same_device(kvb, torch_cuda):
+    """page -> page copy between two pools on one GPU (the kernel used for cross-GPU migration)."""
+    torch = torch_cuda
+    src_t = _make_pool(torch, 8, 40, 16384, seed=1)
+    dst_t = [torch.zeros_like(t) for t in src_t]
+    src, dst = kvb.pool.KVPool(src_t), kvb.pool.KVPool(dst_t)
+    rng = np.random.default_rng(3)
+    s_ids = rng.permutation(40)[:25].astype(np.int64)
+    d_ids = rng.permutation(40)[:25].astype(np.int64)
+    for variant in (LDG, BULK):
+        for t in dst_t:
+            t.zero_()
+        kvb.migrate.migrate_blocks(src, dst, s_ids, d_ids, flags=variant)
+        torch.cuda.synchronize()
+        for s, d in zip(src_t, dst_t):
+            exp = np.zeros((40, 16384), dtype=np.uint8)
+            exp[d_ids] = s.cpu().numpy()[s_ids]
+            assert np.array_equal(d.cpu().numpy(), exp)

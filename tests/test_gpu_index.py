@@ -1,0 +1,202 @@
+"""Index contract + scorer parity (through the C ABI) against the oracle and the reference's known answers."""
+import numpy as np
+import pytest
+
+from oracle import kvblock_oracle as o
+from tests import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pe(kvb, pod, tier, spec=False):
+    return kvb.kvblock.PodEntry(pod, tier, spec)
+
+
+def _as_tuples(d):
+    return {int(k): [(e.pod_identifier, e.device_tier, bool(e.speculative)) for e in v] for k, v in d.items()}
+
+
+@pytest.mark.parametrize("case", sc.SCORER_CASES, ids=lambda c: c[0])
+def test_scorer_known_answers(kvb, torch_cuda, case):
+    _, weights, keys, hit, want = case
+    idx = kvb.kvblock.Index(medium_weights=weights)
+    for k, pods in hit.items():
+        idx.add([k], [k], [_pe(kvb, p, t) for p, t in pods])
+    got = kvb.indexer.LongestPrefixScorer(idx).score(keys)
+    assert got == want
+
+
+@pytest.mark.parametrize("case", sc.INDEXER_CASES, ids=lambda c: c[0])
+def test_indexer_known_answers(kvb, torch_cuda, case):
+    _, keys, entries, flt, want = case
+    idx = kvb.kvblock.Index()
+    for k, pods in entries.items():
+        idx.add([k], [k], [_pe(kvb, p, t) for p, t in pods])
+    got = kvb.indexer.LongestPrefixScorer(idx).score(keys, flt)
+    oidx = o.InMemoryIndex()
+    for k, pods in entries.items():
+        oidx.add([k], [k], [o.PodEntry(p, t) for p, t in pods])
+    exact = o.longest_prefix_score(keys, oidx.lookup(keys, flt))
+    assert got == exact                                   # bit-exact float64 against the oracle
+    assert set(got) == set(want) and all(abs(got[p] - want[p]) < 1e-4 for p in want)
+
+
+def test_score_tokens_end_to_end(kvb, torch_cuda):
+    """Indexer.ScoreTokens: hash -> lookup -> score, vs the oracle Indexer on the same state."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(0)
+    tokens = rng.integers(0, 128256, 1000).astype(np.uint32)           # BASELINE config #1
+    model = "meta-llama/Llama-3-8B"
+    tp, otp = K.ChunkedTokenDatabase(16, ""), o.TokenProcessor(16, "")
+    keys = tp.tokens_to_kv_block_keys(0, tokens, model)
+    assert len(keys) == 62
+    ix = kvb.indexer.Indexer(tp)
+    oix = o.Indexer(otp)
+    for i in range(4):
+        held = keys[: 62 * (i + 1) // 4]
+        ix.index.add(held, held, [_pe(kvb, "pod-%d" % i, "gpu")])
+        oix.index.add(held, held, [o.PodEntry("pod-%d" % i, "gpu")])
+    ix.index.add(keys[:20], keys[:20], [_pe(kvb, "pod-3", "cpu")])
+    oix.index.add(keys[:20], keys[:20], [o.PodEntry("pod-3", "cpu")])
+    want = oix.score_tokens([int(t) for t in tokens], model)
+    assert ix.score_tokens(tokens, model) == want
+    assert want == {"pod-0": 15.0, "pod-1": 31.0, "pod-2": 46.0, "pod-3": 62.0}
+    assert ix.score_tokens(tokens, model, ["pod-1", "pod-2"]) == oix.score_tokens([int(t) for t in tokens], model, ["pod-1", "pod-2"])
+    assert ix.score_tokens(tokens[:10], model) is None                   # no full block -> nil
+    assert ix.score_tokens(tokens, "other-model") == {}
+
+
+def test_index_contract(kvb, torch_cuda):
+    """index_test.go:119-264,589-735; in_memory_test.go:45-236 — same assertions as tests/test_oracle_kvblock.py."""
+    K = kvb.kvblock
+    P = lambda p, t, s=False: K.PodEntry(p, t, s)
+    idx = K.Index()
+    with pytest.raises(ValueError):
+        idx.lookup([])
+    with pytest.raises(ValueError):
+        idx.add([1], [], [P("p", "gpu")])
+    with pytest.raises(ValueError):
+        idx.evict(1, K.ENGINE_KEY, [])
+    idx.add([1, 2], [11, 12], [P("p1", "gpu"), P("p2", "gpu")])
+    assert idx.lookup([11, 12]) == {11: [P("p1", "gpu"), P("p2", "gpu")], 12: [P("p1", "gpu"), P("p2", "gpu")]}
+    idx.add([1], [11], [P("p1", "gpu")])
+    assert len(idx.lookup([11])[11]) == 2
+    assert idx.lookup([11, 12], {"p1"}) == {11: [P("p1", "gpu")], 12: [P("p1", "gpu")]}
+    assert idx.lookup([11], {"nobody"}) == {}
+    assert idx.lookup([999, 11]).keys() == {11}
+    idx.add([3], [13], [P("p3", "gpu"), P("p3", "cpu")])
+    idx.evict(3, K.ENGINE_KEY, [P("p3", "cpu")])
+    assert idx.lookup([13]) == {13: [P("p3", "gpu")]}
+    idx.add([20, 21, 22, 23], [30], [P("p", "gpu")])
+    assert idx.get_request_key(20) == 30 and idx.get_request_key(23) == 30
+    idx.evict(21, K.ENGINE_KEY, [P("p", "gpu")])
+    assert idx.lookup([30]) == {}
+    idx.add([40], [50, 51, 52, 53], [P("p", "gpu")])
+    assert idx.get_request_key(40) == 53
+    with pytest.raises(KeyError):
+        idx.get_request_key(12345)
+    idx.evict(777, K.ENGINE_KEY, [P("p", "gpu")])
+    idx.add(None, [60], [P("p", "gpu", True)])
+    idx.add([61], [60], [P("p", "gpu", False)])
+    assert idx.lookup([60])[60] == [P("p", "gpu", True), P("p", "gpu", False)]
+    idx.evict(60, K.REQUEST_KEY, [P("p", "gpu", True)])
+    assert idx.lookup([60])[60] == [P("p", "gpu", False)]
+    small = K.Index(size=2, pod_cache_size=2)
+    for k in (1, 2, 3):
+        small.add([k], [k], [P("p", "gpu")])
+    assert small.lookup([1, 2, 3]).keys() == {2, 3}
+    small.add([2], [2], [P("a", "gpu"), P("b", "gpu"), P("c", "gpu")])
+    assert small.lookup([2])[2] == [P("b", "gpu"), P("c", "gpu")]
+    with pytest.raises(Exception):
+        K.Index(pod_cache_size=14)      # more than a device bucket holds: refused, not truncated
+
+
+def test_random_ops_match_oracle(kvb, torch_cuda):
+    """Random Add / Evict / Lookup / Score traffic: every read must equal the oracle's, including LRU effects."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(123)
+    idx, oidx = K.Index(size=300, pod_cache_size=4, expected_keys=64), o.InMemoryIndex(size=300, pod_cache_size=4)
+    pods = ["pod-%d" % i for i in range(12)]
+    tiers = ["gpu", "cpu", "GPU", "disk"]
+    keyspace = [int(x) for x in rng.integers(1, 1 << 63, 500)]
+    for step in range(1500):
+        op = rng.random()
+        if op < 0.45:
+            n = int(rng.integers(1, 6))
+            rks = [keyspace[int(i)] for i in rng.integers(0, len(keyspace), n)]
+            mode = rng.integers(0, 3)
+            eks = None if mode == 0 else [int(x) for x in rng.integers(1, 200, n if mode == 1 else 1)]
+            ents = [(pods[int(rng.integers(0, 12))], tiers[int(rng.integers(0, 4))], bool(rng.integers(0, 2)))
+                    for _ in range(int(rng.integers(1, 4)))]
+            idx.add(eks, rks, [K.PodEntry(*e) for e in ents])
+            oidx.add(eks, rks, [o.PodEntry(*e) for e in ents])
+        elif op < 0.65:
+            ents = [(pods[int(rng.integers(0, 12))], tiers[int(rng.integers(0, 4))], bool(rng.integers(0, 2)))
+                    for _ in range(int(rng.integers(1, 3)))]
+            if rng.random() < 0.5:
+                k, kt = int(rng.integers(1, 200)), 0
+            else:
+                k, kt = keyspace[int(rng.integers(0, len(keyspace)))], 1
+            idx.evict(k, kt, [K.PodEntry(*e) for e in ents])
+            oidx.evict(k, kt, [o.PodEntry(*e) for e in ents])
+        else:
+            ks = [keyspace[int(i)] for i in rng.integers(0, len(keyspace), int(rng.integers(1, 40)))]
+            flt = [] if rng.random() < 0.5 else [pods[int(i)] for i in rng.integers(0, 12, 3)] + ["unknown-pod"]
+            got = _as_tuples(idx.lookup(ks, flt))
+            want = _as_tuples(oidx.lookup(ks, flt))
+            assert got == want, step
+            sgot = kvb.indexer.LongestPrefixScorer(idx).score(ks, flt)
+            assert sgot == o.longest_prefix_score(ks, oidx.lookup(ks, flt), {"gpu": 1.0, "cpu": 0.8}), step
+        if step % 100 == 0:
+            assert len(idx) == len(oidx.data)
+
+
+def test_batch_scoring_matches_oracle(kvb, torch_cuda):
+    """Config #5 in miniature: many prompts x many pods against a larger index, fused tokens->scores."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(2)
+    tp, otp = K.ChunkedTokenDatabase(16, ""), o.TokenProcessor(16, "")
+    idx, oidx = K.Index(expected_keys=1 << 16), o.InMemoryIndex()
+    model = "m"
+    pods = ["10.0.0.%d" % i for i in range(64)]
+    prompts = []
+    for p in range(96):
+        n = int(rng.integers(0, 1100))
+        prompts.append(rng.integers(0, 128256, n).astype(np.uint32))
+    # index a random prefix of every prompt on random pods / tiers
+    for p, toks in enumerate(prompts):
+        keys = otp.tokens_to_kv_block_keys(0, [int(t) for t in toks], model) or []
+        for _ in range(int(rng.integers(0, 5))):
+            depth = int(rng.integers(0, len(keys) + 1))
+            if depth == 0:
+                continue
+            ent = (pods[int(rng.integers(0, 64))], "gpu" if rng.random() < 0.8 else "cpu")
+            idx.add(None, keys[:depth], [K.PodEntry(*ent)])
+            oidx.add(None, keys[:depth], [o.PodEntry(*ent)])
+    ix = kvb.indexer.Indexer(tp, idx)
+    got = ix.score_tokens_batch(prompts, model)
+    oix = o.Indexer(otp, oidx)
+    for p, toks in enumerate(prompts):
+        assert got[p] == oix.score_tokens([int(t) for t in toks], model), p
+    flt = pods[:7]
+    gotf = ix.score_tokens_batch(prompts, model, flt)
+    for p, toks in enumerate(prompts):
+        assert gotf[p] == oix.score_tokens([int(t) for t in toks], model, flt), p
+
+
+def test_table_growth_and_tombstones(kvb, torch_cuda):
+    K = kvb.kvblock
+    idx, oidx = K.Index(expected_keys=16), o.InMemoryIndex()
+    keys = [int(x) for x in np.random.default_rng(4).integers(1, 1 << 63, 20000)]
+    e, oe = [K.PodEntry("p", "gpu")], [o.PodEntry("p", "gpu")]
+    for i in range(0, 20000, 1000):
+        idx.add(None, keys[i:i + 1000], e)
+        oidx.add(None, keys[i:i + 1000], oe)
+        assert set(idx.lookup(keys[i:i + 1000])) == set(keys[i:i + 1000])
+    for k in keys[:5000]:
+        idx.evict(k, K.REQUEST_KEY, e)
+        oidx.evict(k, o.REQUEST_KEY, oe)
+    idx.add(None, keys[:2500], e)
+    oidx.add(None, keys[:2500], oe)
+    got = idx.lookup(keys)
+    assert set(got) == set(oidx.lookup(keys)) and len(got) == 17500
