@@ -356,6 +356,11 @@ def run_ours(args):
     d2h = (stats1["d2h_bytes"] - stats0["d2h_bytes"]) // args.steps
     eng.shutdown()
 
+    # ---- cross-GPU migration over NVLink (only where there is a peer)
+    migration = None
+    if world > 1 and not args.no_migration:
+        migration = run_migration(kvb, dist, rank, world, local, tensors, pool, args.steps, args.warmup)
+
     # ---- cpu baseline (rank 0, N=1 only): the reference engine on a bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -392,10 +397,105 @@ def run_ours(args):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if migration is not None:
+            line["migration"] = migration
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+MIGRATE_BLOCKS = 2048   # BASELINE config #4: 32k-token context = 2048 blocks of the 8B shape (4.29 GB)
+
+
+def run_migration(kvb, dist, rank, world, local, tensors, pool, steps, warmup):
+    """Cross-GPU block migration over NVLink (BASELINE config #4), all-pairs ring r -> r+1 and, for world > 2,
+    fan-out rank 0 -> every peer.  One kernel per destination reads local pages and writes the peer's pages
+    (CUDA IPC mapping); torch.distributed carries descriptors and checksums only."""
+    import torch
+    part, mig = kvb.partition, kvb.migrate
+    descs = part.exchange_objects(mig.export_pool(pool), dist)
+    dst_rank, src_rank = part.ring_peers(rank, world)
+    n = min(MIGRATE_BLOCKS, POOL_BLOCKS // 4)
+    payload = n * BLOCK_BYTES
+    # source pages: a prefix of this rank's permutation; destination pages: the UPPER part of the peer's pool
+    # permutation so ring traffic never overwrites pages that are being read
+    src_ids = np.random.default_rng(10 + rank).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64)
+    dst_ids = (POOL_BLOCKS // 2 + np.random.default_rng(20 + rank).permutation(POOL_BLOCKS // 2)[:n]).astype(np.int64)
+    remote = mig.RemotePool(descs[dst_rank], local)
+    out = {"blocks": n, "bytes_per_destination": payload}
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        barrier_sync(dist)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier_sync(dist)
+        return max_over_ranks(dist, a.elapsed_time(b)) / steps
+
+    ring_ms = timed(lambda: mig.migrate_blocks(pool, remote, src_ids, dst_ids))
+    # verify: what my ring source wrote into my pool equals what it read
+    src_sum = part.page_checksum_torch(tensors, torch.from_numpy(src_ids).cuda())
+    sums = part.exchange_objects({"sum": src_sum, "dst_ids": dst_ids.tolist()}, dist)
+    got = part.page_checksum_torch(tensors, torch.tensor(sums[src_rank]["dst_ids"], device="cuda"))
+    ok = got == sums[src_rank]["sum"]
+    oks = part.exchange_objects(bool(ok), dist)
+    out["ring"] = {"ms": ring_ms, "egress_gbs_per_gpu": payload / ring_ms / 1e6,
+                   "aggregate_gbs": world * payload / ring_ms / 1e6, "bit_exact": all(oks),
+                   "frac_of_900": payload / ring_ms / 1e6 / 900.0, "frac_of_measured_770": payload / ring_ms / 1e6 / 770.0}
+
+    # NCCL baseline for the same exchange: gather -> packed -> send/recv -> scatter (library collective path)
+    packed_s = torch.empty(payload, dtype=torch.uint8, device="cuda")
+    packed_r = torch.empty(payload, dtype=torch.uint8, device="cuda")
+    src_dev, dst_dev = torch.from_numpy(src_ids).cuda(), torch.tensor(sums[src_rank]["dst_ids"], device="cuda")
+
+    def nccl_step():
+        pool.gather_dev(src_dev, packed_s)
+        ops = [dist.P2POp(dist.isend, packed_s, dst_rank), dist.P2POp(dist.irecv, packed_r, src_rank)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        pool.scatter_dev(dst_dev, packed_r)
+
+    nccl_ms = timed(nccl_step)
+    out["ring_nccl_staged"] = {"ms": nccl_ms, "egress_gbs_per_gpu": payload / nccl_ms / 1e6,
+                               "note": "gather kernel -> ncclSend/ncclRecv of the packed buffer -> scatter kernel"}
+    del packed_s, packed_r
+
+    if world > 2:
+        # fan-out: rank 0 pushes a different prefix to every peer, one kernel per peer on its own stream
+        peers = [r for r in range(world) if r != 0]
+        if rank == 0:
+            remotes = {p: (remote if p == dst_rank else mig.RemotePool(descs[p], local)) for p in peers}
+            streams = {p: torch.cuda.Stream() for p in peers}
+            fan_src = {p: np.random.default_rng(30 + p).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64) for p in peers}
+
+            def fan():
+                cur = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                for p in peers:
+                    streams[p].wait_event(ev)
+                    mig.migrate_blocks(pool, remotes[p], fan_src[p], dst_ids, stream=streams[p])
+                for p in peers:
+                    cur.wait_stream(streams[p])
+        else:
+            def fan():
+                pass
+        fan_ms = timed(fan)
+        out["fanout_rank0"] = {"ms": fan_ms, "destinations": len(peers),
+                               "egress_gbs_rank0": len(peers) * payload / fan_ms / 1e6,
+                               "frac_of_900": len(peers) * payload / fan_ms / 1e6 / 900.0}
+        if rank == 0:
+            for p, r in remotes.items():
+                if r is not remote:
+                    r.close()
+    barrier_sync(dist)
+    remote.close()
+    return out
 
 
 def run_cpu_baseline(tensors):
@@ -438,6 +538,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-migration", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -360,6 +360,21 @@ class Index:
             out_n.ctypes.data, out_pods.ctypes.data, out_scores.ctypes.data))
         return self._unpack_scores(n, out_n, out_pods, out_scores)
 
+    def score_tokens_flat(self, block_size: int, tokens: np.ndarray, prompt_off: np.ndarray, parents: np.ndarray,
+                          pod_identifiers=None, touch_lru: bool = False, out=None):
+        """Same fused call on pre-flattened arrays (uint32 tokens, int64 offsets, uint64 parents); returns the raw
+        (n, pods, scores) arrays — the zero-copy form a host-language shim would use."""
+        n = len(prompt_off) - 1
+        filt, nf = self._filter(pod_identifiers)
+        if out is None:
+            out = (np.zeros(max(n, 1), dtype=np.int32), np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.uint16),
+                   np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.float64))
+        check(_lib.load().kvb_index_score_tokens_batch(
+            self._h, tokens.ctypes.data, prompt_off.ctypes.data, parents.ctypes.data, n, int(block_size), None, None,
+            None if filt is None else filt.ctypes.data, nf, _lib.SCORE_TOUCH_LRU if touch_lru else 0,
+            out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        return out
+
     def score_tokens_batch(self, tp: ChunkedTokenDatabase, prompts, model_names, pod_identifiers=None,
                            extra_features=None, touch_lru: bool = False, raw: bool = False):
         """Fused tokens -> keys -> lookup -> score on the device for a batch of prompts."""
