@@ -226,11 +226,12 @@ def run_reference(args):
     for w in range(args.warmup):
         step(f"w{w}")
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    # timed region = the store and load phases of every step; deleting the previous step's tmpfs files (several GB of
+    # page frees) is housekeeping between steps and is NOT charged to the reference
+    dt = 0.0
     for k in range(args.steps):
-        step(f"s{k}")
+        dt += step(f"s{k}")
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
     gbs = 2 * payload * args.steps / dt / 1e9
     sample = (f"{REF_SAMPLE_BLOCKS} of the workload's {N_BLOCKS} blocks (seed-1 permutation prefix), "
               f"save+load per step, {BLOCKS_PER_FILE} blocks/file on /dev/shm, default cudaMemcpyAsync copy path")
@@ -361,10 +362,15 @@ def run_ours(args):
     if world > 1 and not args.no_migration:
         migration = run_migration(kvb, dist, rank, world, local, tensors, pool, args.steps, args.warmup)
 
-    # ---- cpu baseline (rank 0, N=1 only): the reference engine on a bounded sample
+    # ---- cpu baseline (rank 0, N=1 only): the reference engine on a bounded sample, and OUR engine writing the
+    # same reference-format files to the same tmpfs on the same sample (like-for-like tier)
     cpu_baseline = None
+    file_tier = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_baseline(tensors)
+        file_tier = run_file_tier(kvb, tensors)
+        for t, r in zip(tensors[::8], check_ref):
+            assert torch.equal(t[check_ids], r), "file-tier save+load did not restore the pool bit-exact"
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -399,10 +405,50 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline
         if migration is not None:
             line["migration"] = migration
+        if file_tier is not None:
+            line["e2e_file_tier"] = file_tier
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def run_file_tier(kvb, tensors, root="/dev/shm/kvb_file_bench"):
+    """Our engine, tier=file: the reference's on-disk format on the same tmpfs, same bounded sample and file grouping
+    as the reference arm (cpu_baseline) — the like-for-like comparison for the storage tier."""
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
+    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
+    bpf = BLOCKS_PER_FILE
+    n_files = (len(ids) + bpf - 1) // bpf
+    first = len(ids) % bpf or bpf
+    groups, pos, take = [], 0, first
+    for _ in range(n_files):
+        groups.append(ids[pos:pos + take].tolist())
+        pos += take
+        take = bpf
+    threads = min(env_int("KVB_BENCH_FILE_THREADS", 16), os.cpu_count() or 1)
+    eng = kvb.engine.StorageOffloadEngine(threads, bpf, tensors, max(1, int(threads * 0.75)), "disabled", 0.0,
+                                          tier="file", chunk_bytes=bpf * BLOCK_BYTES)
+    res = {}
+    try:
+        for tag in ("warm", "base"):
+            files = [f"{root}/{tag}/{i:06d}.bin" for i in range(n_files)]
+            t0 = time.perf_counter()
+            assert eng.async_store_gpu_blocks(1, files, groups)
+            _drain(eng, 1)
+            t1 = time.perf_counter()
+            assert eng.async_load_gpu_blocks(2, files, groups)
+            _drain(eng, 2)
+            t2 = time.perf_counter()
+            shutil.rmtree(f"{root}/{tag}", ignore_errors=True)
+            res = {"value": 2 * payload / (t2 - t0) / 1e9, "unit": "GB/s", "store_gbs": payload / (t1 - t0) / 1e9,
+                   "load_gbs": payload / (t2 - t1) / 1e9, "io_threads": threads,
+                   "sample": f"{REF_SAMPLE_BLOCKS} blocks, {bpf} blocks/file, reference .bin format on /dev/shm "
+                             "(same sample and grouping as cpu_baseline)"}
+    finally:
+        eng.shutdown()
+        shutil.rmtree(root, ignore_errors=True)
+    return res
 
 
 MIGRATE_BLOCKS = 2048   # BASELINE config #4: 32k-token context = 2048 blocks of the 8B shape (4.29 GB)

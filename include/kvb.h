@@ -38,6 +38,10 @@ extern "C" {
 int kvb_abi_version(void);
 const char* kvb_last_error(void);
 int kvb_device_count(void);
+/* pinned (page-locked, portable) host memory: buffers allocated here are read/written by the copy engines in place,
+ * pageable buffers are staged through an internal pinned scratch first */
+int kvb_host_alloc(size_t bytes, void** out);
+int kvb_host_free(void* p);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Paged-KV pool + gather / scatter  (HBM <-> packed HBM)

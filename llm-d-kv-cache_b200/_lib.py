@@ -54,6 +54,8 @@ SIGNATURES = {
     "kvb_abi_version": (C.c_int, []),
     "kvb_last_error": (C.c_char_p, []),
     "kvb_device_count": (C.c_int, []),
+    "kvb_host_alloc": (C.c_int, [C.c_size_t, _P(_vp)]),
+    "kvb_host_free": (C.c_int, [_vp]),
     "kvb_pool_create": (C.c_int, [C.c_int, _P(_vp), _i32, _i64, _i64, _i64, _P(_vp)]),
     "kvb_pool_destroy": (None, [_vp]),
     "kvb_pool_block_bytes": (_i64, [_vp]),

@@ -9,8 +9,8 @@
 //
 // Parallelism: FNV-1a is a serial byte chain and keys chain across blocks, so one prompt is
 // one serial chain.  One THREAD per prompt (32 chains per warp); per token the 1..5 CBOR bytes
-// are folded with predicated steps so lanes holding 1/2/3/5-byte tokens do not diverge.
-// Latency/ALU-bound (about 10 cycles per payload byte per chain), not HBM-bound: the only
+// are folded under per-token predicates so lanes holding 1/2/3/5-byte tokens do not diverge.
+// Latency/ALU-bound (two dependent 32-bit ops per payload byte per chain), not HBM-bound: the only
 // memory traffic is 4 B/token in and 8 B/key out.
 #include <cstring>
 #include <vector>
@@ -22,55 +22,58 @@ namespace kvb {
 constexpr uint64_t kFnvOffset = 0xcbf29ce484222325ull;
 constexpr uint64_t kFnvPrime = 0x100000001b3ull;
 
-__device__ __forceinline__ uint64_t fold(uint64_t h, uint32_t byte) { return (h ^ (uint64_t)byte) * kFnvPrime; }
+// FNV-1a state kept as two 32-bit halves.  h * 0x100000001b3 = h * 0x1b3 + (h << 40), so per byte:
+//   x = lo ^ b;  lo' = x * 0x1b3 (low half);  hi' = hi * 0x1b3 + mulhi(x, 0x1b3) + (x << 8)
+// The serial dependency is xor -> mul.lo on the low half (2 ops per byte); the high half trails it with one
+// multiply-add per byte.  (A plain 64-bit multiply compiles to ~5 dependent IMADs + selects per byte.)
+struct Fnv {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ void fold(Fnv& h, uint32_t byte) {
+  const uint32_t x = h.lo ^ byte;
+  const uint32_t carry = __umulhi(x, 0x1b3u) + (x << 8);
+  h.hi = h.hi * 0x1b3u + carry;
+  h.lo = x * 0x1b3u;
+}
+__device__ __forceinline__ Fnv fnv_init() { return Fnv{(uint32_t)kFnvOffset, (uint32_t)(kFnvOffset >> 32)}; }
+__device__ __forceinline__ uint64_t fnv_value(const Fnv& h) { return ((uint64_t)h.hi << 32) | h.lo; }
 
 // CBOR head for major type `major` (already shifted <<5) with argument n, shortest form.
-__device__ __forceinline__ uint64_t fold_head64(uint64_t h, uint32_t major, uint64_t n) {
-  if (n < 24) return fold(h, major | (uint32_t)n);
-  if (n < 0x100ull) {
-    h = fold(h, major | 24);
-    return fold(h, (uint32_t)n);
-  }
-  if (n < 0x10000ull) {
-    h = fold(h, major | 25);
-    h = fold(h, (uint32_t)(n >> 8));
-    return fold(h, (uint32_t)n & 0xff);
-  }
-  if (n < 0x100000000ull) {
-    h = fold(h, major | 26);
+__device__ __forceinline__ void fold_head64(Fnv& h, uint32_t major, uint64_t n) {
+  if (n < 24) {
+    fold(h, major | (uint32_t)n);
+  } else if (n < 0x100ull) {
+    fold(h, major | 24);
+    fold(h, (uint32_t)n);
+  } else if (n < 0x10000ull) {
+    fold(h, major | 25);
+    fold(h, (uint32_t)(n >> 8));
+    fold(h, (uint32_t)n & 0xff);
+  } else if (n < 0x100000000ull) {
+    fold(h, major | 26);
 #pragma unroll
-    for (int s = 24; s >= 0; s -= 8) h = fold(h, (uint32_t)(n >> s) & 0xff);
-    return h;
-  }
-  h = fold(h, major | 27);
+    for (int s = 24; s >= 0; s -= 8) fold(h, (uint32_t)(n >> s) & 0xff);
+  } else {
+    fold(h, major | 27);
 #pragma unroll
-  for (int s = 56; s >= 0; s -= 8) h = fold(h, (uint32_t)(n >> s) & 0xff);
-  return h;
+    for (int s = 56; s >= 0; s -= 8) fold(h, (uint32_t)(n >> s) & 0xff);
+  }
 }
 
-// One uint32 token as a CBOR unsigned int: 1, 2, 3 or 5 bytes, folded with predicated steps.
-__device__ __forceinline__ uint64_t fold_token(uint64_t h, uint32_t t) {
-  uint64_t stream;  // byte k of the encoding sits in bits [8k, 8k+8)
-  int nb;
-  if (t < 24u) {
-    stream = t;
-    nb = 1;
-  } else if (t < 0x100u) {
-    stream = 0x18u | (t << 8);
-    nb = 2;
-  } else if (t < 0x10000u) {
-    stream = 0x19u | ((t >> 8) << 8) | ((t & 0xffu) << 16);
-    nb = 3;
-  } else {
-    stream = 0x1aull | ((uint64_t)__byte_perm(t, 0, 0x0123) << 8);
-    nb = 5;
-  }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const uint64_t hn = fold(h, (uint32_t)(stream >> (8 * k)) & 0xffu);
-    h = (k < nb) ? hn : h;
-  }
-  return h;
+// One uint32 token as a CBOR unsigned int (1, 2, 3 or 5 bytes).  Bytes 2..5 are folded under per-token
+// predicates (short if-bodies that ptxas predicates), so lanes holding tokens of different widths do not diverge.
+__device__ __forceinline__ void fold_token(Fnv& h, uint32_t t) {
+  const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
+  // byte 0: the value itself (<24) or the head 0x18 / 0x19 / 0x1a
+  const uint32_t b0 = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
+  // big-endian payload bytes; for the 2- and 3-byte forms they are the low bytes of t
+  const uint32_t b1 = ge64k ? (t >> 24) : (ge256 ? ((t >> 8) & 0xffu) : t);
+  const uint32_t b2 = ge64k ? ((t >> 16) & 0xffu) : (t & 0xffu);
+  fold(h, b0);
+  if (ge24) fold(h, b1);
+  if (ge256) fold(h, b2);
+  if (ge64k) fold(h, (t >> 8) & 0xffu);
+  if (ge64k) fold(h, t & 0xffu);
 }
 
 template <int BS>
@@ -101,26 +104,27 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
 #pragma unroll
       for (int j = 0; j < BS; ++j) nxt[j] = __ldg(tk + (i + 1) * BS + j);
     }
-    uint64_t h = fold(kFnvOffset, 0x83u);          // array(3)
-    h = fold_head64(h, 0x00u, parent);              // parent: unsigned int
-    h = fold_head64(h, 0x80u, (uint64_t)bs);        // chunk: array(bs)
+    Fnv h = fnv_init();
+    fold(h, 0x83u);                                 // array(3)
+    fold_head64(h, 0x00u, parent);                  // parent: unsigned int
+    fold_head64(h, 0x80u, (uint64_t)bs);            // chunk: array(bs)
     if (BS > 0) {
 #pragma unroll
-      for (int j = 0; j < BS; ++j) h = fold_token(h, cur[j]);
+      for (int j = 0; j < BS; ++j) fold_token(h, cur[j]);
     } else {
-      for (int j = 0; j < bs; ++j) h = fold_token(h, __ldg(tk + i * bs + j));
+      for (int j = 0; j < bs; ++j) fold_token(h, __ldg(tk + i * bs + j));
     }
     bool text = true;
     if (extra_off != nullptr) {                     // pre-encoded X(extra_i), host-built (extra_keys.go)
       const int64_t e0 = extra_off[k0 + i], e1 = extra_off[k0 + i + 1];
       if (e1 > e0) {
         text = false;
-        for (int64_t e = e0; e < e1; ++e) h = fold(h, extra[e]);
+        for (int64_t e = e0; e < e1; ++e) fold(h, extra[e]);
       }
     }
-    if (text) h = fold(h, 0xf6u);                   // nil extra -> CBOR null
-    out_keys[k0 + i] = h;
-    parent = h;
+    if (text) fold(h, 0xf6u);                       // nil extra -> CBOR null
+    parent = fnv_value(h);
+    out_keys[k0 + i] = parent;
     if (BS > 0) {
 #pragma unroll
       for (int j = 0; j < BS; ++j) cur[j] = nxt[j];
@@ -132,12 +136,13 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
 __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__ name, uint32_t len,
                                  uint64_t* __restrict__ out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint64_t h = fold(kFnvOffset, 0x83u);
-  h = fold_head64(h, 0x00u, seed_hash);
-  h = fold(h, 0xf6u);
-  h = fold_head64(h, 0x60u, len);
-  for (uint32_t i = 0; i < len; ++i) h = fold(h, name[i]);
-  *out = h;
+  Fnv h = fnv_init();
+  fold(h, 0x83u);
+  fold_head64(h, 0x00u, seed_hash);
+  fold(h, 0xf6u);
+  fold_head64(h, 0x60u, len);
+  for (uint32_t i = 0; i < len; ++i) fold(h, name[i]);
+  *out = fnv_value(h);
 }
 
 int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents, int32_t n_prompts,

@@ -784,13 +784,24 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
   for (int32_t p = 0; p <= n_prompts; ++p) h_koff[p] = key_off[p] - key_off[0];
   KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, ((size_t)n_prompts + 1) * 8, cudaMemcpyHostToDevice, s));
   if (from_tokens) {
-    std::memcpy(H + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4);
     int64_t* h_poff = reinterpret_cast<int64_t*>(H + o_poff);
     for (int32_t p = 0; p <= n_prompts; ++p) h_poff[p] = prompt_off[p] - prompt_off[0];
     std::memcpy(H + o_par, parents, (size_t)n_prompts * 8);
-    // tokens, prompt_off and parents are adjacent in the scratch: one copy
-    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, H + o_tok, (o_par + (size_t)n_prompts * 8) - o_tok,
-                                 cudaMemcpyHostToDevice, s));
+    // a caller that keeps its tokens in pinned memory (kvb_host_alloc / cudaHostAlloc / registered) is read by the
+    // copy engine in place; pageable tokens are staged through the pinned scratch first
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, tokens) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    if (pinned) {
+      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
+      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_poff, H + o_poff, (o_par + (size_t)n_prompts * 8) - o_poff,
+                                   cudaMemcpyHostToDevice, s));
+    } else {
+      std::memcpy(H + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4);
+      // tokens, prompt_off and parents are adjacent in the scratch: one copy
+      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, H + o_tok, (o_par + (size_t)n_prompts * 8) - o_tok,
+                                   cudaMemcpyHostToDevice, s));
+    }
     if (extra_off) {
       std::memcpy(H + o_eoff, extra_off, ((size_t)total_keys + 1) * 8);
       if (extra_bytes) std::memcpy(H + o_ext, extra, (size_t)extra_bytes);

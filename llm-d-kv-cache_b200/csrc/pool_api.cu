@@ -193,6 +193,17 @@ int kvb_scatter_blocks_dev(kvb_pool_t* pool, const int64_t* ids_dev, int64_t n, 
   return launch_scatter(pool, ids_dev, n, packed, static_cast<cudaStream_t>(stream), flags);
 }
 
+// pinned host memory for callers that want zero staging copies (token buffers, host-tier staging)
+int kvb_host_alloc(size_t bytes, void** out) {
+  KVB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
+  KVB_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return KVB_OK;
+}
+int kvb_host_free(void* p) {
+  if (p) KVB_CUDA_TRY(cudaFreeHost(p));
+  return KVB_OK;
+}
+
 // ------------------------------------------------------------------------------- migration / IPC
 int kvb_ipc_export(int device, const void* dev_ptr, kvb_ipc_mem_t* out) {
   KVB_REQUIRE(dev_ptr && out, "NULL argument");
