@@ -400,6 +400,9 @@ int launch_migrate(const kvb_pool* src, const kvb_pool* dst, const int64_t* src_
   a.T = (uint32_t)src->num_tensors;
   a.total_items = (uint64_t)n * (uint64_t)src->num_tensors;
   int vec = std::min(src->vec_bytes, dst->vec_bytes);
+  // NVLink peer stores: the 16 B LDG/STG mover (unroll 4, 8 CTAs/SM) sustains more than the bulk mover
+  // (688 vs 675 GB/s per GPU in the ring sweep, profiles/r01_tune_migrate_8b_n2.log); local HBM keeps bulk
+  if ((flags & 0xff) == KVB_COPY_DEFAULT && dst->peer && vec == 16) flags = KVB_COPY_LDG | (4 << 8) | (8 << 12);
   return launch_copy<kMigrate>(a, vec, src->device, s, flags);
 }
 

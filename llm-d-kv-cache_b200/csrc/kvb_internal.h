@@ -65,6 +65,7 @@ struct kvb_pool {
   const uint8_t** d_tensor_ptrs = nullptr;  // device array [T]
   const uint8_t** h_tensor_ptrs = nullptr;  // host copy [T]
   int vec_bytes = 16;                        // widest aligned vector usable for every fragment (16/8/4/1)
+  bool peer = false;                         // tensors live on another GPU (peer / CUDA-IPC mapping)
   // small pinned + device scratch for uploading block ids
   int64_t* h_ids = nullptr;
   int64_t* d_ids = nullptr;

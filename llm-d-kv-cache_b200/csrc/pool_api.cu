@@ -124,6 +124,14 @@ int kvb_pool_create(int device, const void* const* tensor_ptrs, int32_t num_tens
     while (vec > 1 && (reinterpret_cast<uintptr_t>(tensor_ptrs[i]) % vec)) vec >>= 1;
   }
   p->vec_bytes = vec;
+  {  // tensors that live on another GPU (peer-enabled or CUDA-IPC mapped): remember it for kernel selection
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, tensor_ptrs[0]) == cudaSuccess) {
+      p->peer = attr.type == cudaMemoryTypeDevice && attr.device != device;
+    } else {
+      cudaGetLastError();
+    }
+  }
   cudaError_t e = cudaMalloc(&p->d_tensor_ptrs, sizeof(void*) * num_tensors);
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_tensor_ptrs, p->h_tensor_ptrs, sizeof(void*) * num_tensors, cudaMemcpyHostToDevice);
