@@ -578,6 +578,10 @@ def run_cpu_baseline(tensors):
 
 
 def main():
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (the image's default under torchrun);
+    # stdout must carry exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

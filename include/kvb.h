@@ -63,6 +63,9 @@ int kvb_pool_create(int device, const void* const* tensor_ptrs, int32_t num_tens
                     int64_t frag_bytes, int64_t block_stride_bytes, kvb_pool_t** out);
 void kvb_pool_destroy(kvb_pool_t* pool);
 int64_t kvb_pool_block_bytes(const kvb_pool_t* pool); /* T * frag_bytes */
+/* declare that the pool's tensors live on another GPU (peer-enabled or CUDA-IPC mapped): kvb_migrate_blocks then
+ * defaults to the mover tuned for NVLink stores.  Auto-detected when the driver reports the owning device. */
+int kvb_pool_mark_peer(kvb_pool_t* pool, int is_peer);
 
 /* block_ids: HOST array of n ids.  packed: DEVICE (or device-mapped / peer) buffer of n*T*frag bytes. */
 int kvb_gather_blocks(kvb_pool_t* pool, const int64_t* block_ids, int64_t n, void* packed, void* stream, int flags);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "kvb_pool_create": (C.c_int, [C.c_int, _P(_vp), _i32, _i64, _i64, _i64, _P(_vp)]),
     "kvb_pool_destroy": (None, [_vp]),
     "kvb_pool_block_bytes": (_i64, [_vp]),
+    "kvb_pool_mark_peer": (C.c_int, [_vp, C.c_int]),
     "kvb_gather_blocks": (C.c_int, [_vp, _P(_i64), _i64, _vp, _vp, C.c_int]),
     "kvb_scatter_blocks": (C.c_int, [_vp, _P(_i64), _i64, _vp, _vp, C.c_int]),
     "kvb_gather_blocks_dev": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int]),

@@ -16,6 +16,8 @@
 //   * a host tier in pinned DRAM (KVB_TIER_HOST_ARENA) addressed by the same path strings, D2H lands
 //     directly in its final place (no staging copy on the host).
 #include <fcntl.h>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -215,6 +217,53 @@ class Arena {
   }
 };
 
+// ---------------------------------------------------------------------------------- NUMA placement
+// The reference pins its I/O threads to the GPU-local NUMA node and prefers that node for staging memory
+// (thread_pool.cpp:73-131, numa_utils.cpp).  Same intent without libnuma: read the GPU's node from sysfs and set the
+// affinity of the threads that allocate (first touch => local pages) and drive the copies.
+static int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+static std::vector<int> cpus_of_node(int node) {
+  std::vector<int> cpus;
+  if (node < 0) return cpus;
+  std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return cpus;
+  char buf[4096] = {0};
+  if (!fgets(buf, sizeof(buf), f)) buf[0] = 0;
+  fclose(f);
+  for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+    int a = 0, b = 0;
+    if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+      for (int c = a; c <= b; ++c) cpus.push_back(c);
+    } else if (sscanf(tok, "%d", &a) == 1) {
+      cpus.push_back(a);
+    }
+  }
+  return cpus;
+}
+static void bind_this_thread(const std::vector<int>& cpus) {
+  if (cpus.empty()) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int c : cpus)
+    if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof(set), &set);  // best effort
+}
+
 // ---------------------------------------------------------------------------------- file helpers
 static bool file_exists(const std::string& p) {
   struct stat st;
@@ -301,6 +350,7 @@ struct kvb_engine {
   std::map<int64_t, std::shared_ptr<JobState>> jobs;
 
   Arena arena;
+  std::vector<int> local_cpus;  // CPUs of the GPU's NUMA node (empty: unknown, no binding)
   std::atomic<uint64_t> avg_write_us{0};
   std::string tmp_suffix;
 
@@ -543,6 +593,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
 }
 
 void kvb_engine::worker_loop(Worker* w) {
+  bind_this_thread(local_cpus);
   bool inited = false;
   for (;;) {
     std::unique_ptr<ChunkTask> task;
@@ -702,10 +753,24 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
     set_error("cannot select CUDA device %d", e->device);
     return KVB_ERR_CUDA;
   }
+  if (!std::getenv("KVB_NO_NUMA_BIND")) e->local_cpus = cpus_of_node(gpu_numa_node(e->device));
   if (opts->tier == KVB_TIER_HOST_ARENA) {
     KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
-    int rc = e->arena.init(opts->host_arena_bytes);
-    if (rc) return rc;
+    // allocate (and thereby first-touch / pin) the arena from a thread bound to the GPU-local node, without
+    // disturbing the caller's own affinity
+    int rc = KVB_OK;
+    std::string err;
+    std::thread t([&] {
+      bind_this_thread(e->local_cpus);
+      cudaSetDevice(e->device);
+      rc = e->arena.init(opts->host_arena_bytes);
+      if (rc) err = get_error();
+    });
+    t.join();
+    if (rc) {
+      set_error("%s", err.c_str());
+      return rc;
+    }
   }
   const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);
   for (int i = 0; i < opts->io_threads; ++i) {

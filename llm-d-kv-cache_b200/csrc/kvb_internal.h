@@ -66,11 +66,17 @@ struct kvb_pool {
   const uint8_t** h_tensor_ptrs = nullptr;  // host copy [T]
   int vec_bytes = 16;                        // widest aligned vector usable for every fragment (16/8/4/1)
   bool peer = false;                         // tensors live on another GPU (peer / CUDA-IPC mapping)
-  // small pinned + device scratch for uploading block ids
-  int64_t* h_ids = nullptr;
-  int64_t* d_ids = nullptr;
-  int64_t ids_cap = 0;
-  cudaEvent_t ids_free = nullptr;  // h_ids may be rewritten once this event completed
+  // ring of pinned + device scratch slots for uploading block ids: a slot is rewritten only after the kernel that
+  // read it has finished (event), and calls on different streams use different slots, so they do not serialise
+  static constexpr int kIdSlots = 8;
+  struct IdSlot {
+    int64_t* h_ids = nullptr;
+    int64_t* d_ids = nullptr;
+    int64_t cap = 0;
+    cudaEvent_t free_ev = nullptr;
+  } id_slots[kIdSlots];
+  int next_slot = 0;
+  cudaEvent_t last_ids_ev = nullptr;  // event of the slot handed out by the latest upload_ids()
 };
 
 namespace kvb {
@@ -81,6 +87,8 @@ int launch_scatter(const kvb_pool* pool, const int64_t* ids_dev, int64_t n, cons
                    int flags);
 int launch_migrate(const kvb_pool* src, const kvb_pool* dst, const int64_t* src_ids_dev, const int64_t* dst_ids_dev,
                    int64_t n, cudaStream_t s, int flags);
+// copies ids into a free scratch slot and enqueues the H2D on s; after launching the kernel that reads *out_dev the
+// caller records pool->last_ids_ev on s (release of the slot)
 int upload_ids(kvb_pool* pool, const int64_t* ids_host, int64_t n, cudaStream_t s, const int64_t** out_dev);
 int validate_ids(const kvb_pool* pool, const int64_t* ids_host, int64_t n);
 

@@ -45,30 +45,29 @@ int validate_ids(const kvb_pool* pool, const int64_t* ids, int64_t n) {
   return KVB_OK;
 }
 
-// Upload ids through the pool's pinned scratch.  The scratch is reused once the previous upload's
-// copy has completed (event), so back-to-back calls on different streams stay correct.
+// Upload ids through one slot of the pool's scratch ring (see kvb_internal.h).
 int upload_ids(kvb_pool* pool, const int64_t* ids_host, int64_t n, cudaStream_t s, const int64_t** out_dev) {
-  if (n > pool->ids_cap) {
-    if (pool->ids_free) cudaEventSynchronize(pool->ids_free);
-    if (pool->h_ids) cudaFreeHost(pool->h_ids);
-    if (pool->d_ids) {
-      // device buffer may still be read by an earlier kernel on another stream
-      cudaDeviceSynchronize();
-      cudaFree(pool->d_ids);
-    }
-    pool->h_ids = nullptr;
-    pool->d_ids = nullptr;
+  kvb_pool::IdSlot& sl = pool->id_slots[pool->next_slot];
+  pool->next_slot = (pool->next_slot + 1) % kvb_pool::kIdSlots;
+  if (!sl.free_ev) KVB_CUDA_TRY(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
+  // previous user of this slot (pinned source AND device copy) must be done
+  KVB_CUDA_TRY(cudaEventSynchronize(sl.free_ev));
+  if (n > sl.cap) {
+    if (sl.h_ids) cudaFreeHost(sl.h_ids);
+    if (sl.d_ids) cudaFree(sl.d_ids);
+    sl.h_ids = nullptr;
+    sl.d_ids = nullptr;
+    sl.cap = 0;
     int64_t cap = 1024;
     while (cap < n) cap <<= 1;
-    KVB_CUDA_TRY(cudaHostAlloc(&pool->h_ids, cap * sizeof(int64_t), cudaHostAllocDefault));
-    KVB_CUDA_TRY(cudaMalloc(&pool->d_ids, cap * sizeof(int64_t)));
-    pool->ids_cap = cap;
+    KVB_CUDA_TRY(cudaHostAlloc(&sl.h_ids, cap * sizeof(int64_t), cudaHostAllocDefault));
+    KVB_CUDA_TRY(cudaMalloc(&sl.d_ids, cap * sizeof(int64_t)));
+    sl.cap = cap;
   }
-  // previous user of the scratch (pinned source AND device copy) must be done
-  KVB_CUDA_TRY(cudaEventSynchronize(pool->ids_free));
-  std::memcpy(pool->h_ids, ids_host, n * sizeof(int64_t));
-  KVB_CUDA_TRY(cudaMemcpyAsync(pool->d_ids, pool->h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  *out_dev = pool->d_ids;
+  std::memcpy(sl.h_ids, ids_host, n * sizeof(int64_t));
+  KVB_CUDA_TRY(cudaMemcpyAsync(sl.d_ids, sl.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  *out_dev = sl.d_ids;
+  pool->last_ids_ev = sl.free_ev;
   return KVB_OK;
 }
 
@@ -135,7 +134,6 @@ int kvb_pool_create(int device, const void* const* tensor_ptrs, int32_t num_tens
   cudaError_t e = cudaMalloc(&p->d_tensor_ptrs, sizeof(void*) * num_tensors);
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_tensor_ptrs, p->h_tensor_ptrs, sizeof(void*) * num_tensors, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ids_free, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     set_error("kvb_pool_create: %s", cudaGetErrorString(e));
     if (p->d_tensor_ptrs) cudaFree(p->d_tensor_ptrs);
@@ -152,14 +150,22 @@ void kvb_pool_destroy(kvb_pool_t* p) {
   DeviceGuard g(p->device);
   cudaDeviceSynchronize();
   if (p->d_tensor_ptrs) cudaFree(p->d_tensor_ptrs);
-  if (p->d_ids) cudaFree(p->d_ids);
-  if (p->h_ids) cudaFreeHost(p->h_ids);
-  if (p->ids_free) cudaEventDestroy(p->ids_free);
+  for (auto& sl : p->id_slots) {
+    if (sl.d_ids) cudaFree(sl.d_ids);
+    if (sl.h_ids) cudaFreeHost(sl.h_ids);
+    if (sl.free_ev) cudaEventDestroy(sl.free_ev);
+  }
   delete[] p->h_tensor_ptrs;
   delete p;
 }
 
 int64_t kvb_pool_block_bytes(const kvb_pool_t* p) { return p ? p->frag_bytes * p->num_tensors : 0; }
+
+int kvb_pool_mark_peer(kvb_pool_t* p, int is_peer) {
+  KVB_REQUIRE(p != nullptr, "pool is NULL");
+  p->peer = is_peer != 0;
+  return KVB_OK;
+}
 
 static int gs_host(kvb_pool_t* pool, const int64_t* ids, int64_t n, void* packed, void* stream, int flags,
                    bool gather) {
@@ -175,7 +181,7 @@ static int gs_host(kvb_pool_t* pool, const int64_t* ids, int64_t n, void* packed
   rc = upload_ids(pool, ids, n, s, &d);
   if (rc) return rc;
   rc = gather ? launch_gather(pool, d, n, packed, s, flags) : launch_scatter(pool, d, n, packed, s, flags);
-  cudaEventRecord(pool->ids_free, s);
+  cudaEventRecord(pool->last_ids_ev, s);
   return rc;
 }
 
@@ -304,7 +310,7 @@ int kvb_migrate_blocks(kvb_pool_t* src, kvb_pool_t* dst, const int64_t* src_ids,
   rc = upload_ids(src, both.data(), 2 * n, s, &d);
   if (rc) return rc;
   rc = launch_migrate(src, dst, d, d + n, n, s, flags);
-  cudaEventRecord(src->ids_free, s);
+  cudaEventRecord(src->last_ids_ev, s);
   return rc;
 }
 

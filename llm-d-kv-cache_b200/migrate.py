@@ -48,6 +48,7 @@ class RemotePool(KVPool):
             ptrs.append(base + offset)
         super().__init__(None, local_device, ptrs=ptrs, num_blocks=desc["num_blocks"],
                          frag_bytes=desc["frag_bytes"], stride_bytes=desc["frag_bytes"])
+        check(lib.kvb_pool_mark_peer(self.handle, 1))
 
     def close(self):
         super().close()
