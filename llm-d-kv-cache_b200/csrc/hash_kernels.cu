@@ -12,6 +12,7 @@
 // are folded under per-token predicates so lanes holding 1/2/3/5-byte tokens do not diverge.
 // Latency/ALU-bound (two dependent 32-bit ops per payload byte per chain), not HBM-bound: the only
 // memory traffic is 4 B/token in and 8 B/key out.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -60,20 +61,40 @@ __device__ __forceinline__ void fold_head64(Fnv& h, uint32_t major, uint64_t n) 
   }
 }
 
-// One uint32 token as a CBOR unsigned int (1, 2, 3 or 5 bytes).  Bytes 2..5 are folded under per-token
-// predicates (short if-bodies that ptxas predicates), so lanes holding tokens of different widths do not diverge.
-__device__ __forceinline__ void fold_token(Fnv& h, uint32_t t) {
+// Token bytes are produced in two passes per block so that a lone warp (one chain per lane, nothing else on its
+// scheduler to hide latency) issues as few instructions as possible:
+//   pass 1 (independent across tokens, full ILP): every token's CBOR unsigned-int encoding (1, 2, 3 or 5 bytes) is
+//           written to the lane's private strip of shared memory with five unconditional byte stores — bytes past
+//           the encoding's length are overwritten by the next token, so there is no branch on the token width;
+//   pass 2 (the serial chain): the strip is read back a word at a time and folded byte by byte.
+constexpr int kStageTokens = 16;  // tokens staged per pass
+constexpr int kStageWords = 23;   // 92 B strip: 16 x 5 B + 4 B of slack; odd word count => lanes hit distinct banks
+
+__device__ __forceinline__ int stage_token(uint8_t* buf, int n, uint32_t t) {
   const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
-  // byte 0: the value itself (<24) or the head 0x18 / 0x19 / 0x1a
-  const uint32_t b0 = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
-  // big-endian payload bytes; for the 2- and 3-byte forms they are the low bytes of t
-  const uint32_t b1 = ge64k ? (t >> 24) : (ge256 ? ((t >> 8) & 0xffu) : t);
-  const uint32_t b2 = ge64k ? ((t >> 16) & 0xffu) : (t & 0xffu);
-  fold(h, b0);
-  if (ge24) fold(h, b1);
-  if (ge256) fold(h, b2);
-  if (ge64k) fold(h, (t >> 8) & 0xffu);
-  if (ge64k) fold(h, t & 0xffu);
+  const uint32_t head = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
+  // payload, left-aligned big-endian: 4 bytes (>= 65536), 2 bytes (>= 256) or 1 byte (>= 24)
+  const uint32_t pay = ge64k ? t : (ge256 ? (t << 16) : (t << 24));
+  buf[n] = (uint8_t)head;
+  buf[n + 1] = (uint8_t)(pay >> 24);
+  buf[n + 2] = (uint8_t)(pay >> 16);
+  buf[n + 3] = (uint8_t)(pay >> 8);
+  buf[n + 4] = (uint8_t)pay;
+  return n + (ge64k ? 5 : (ge256 ? 3 : (ge24 ? 2 : 1)));
+}
+
+__device__ __forceinline__ void fold_staged(Fnv& h, const uint8_t* buf, int n) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(buf);
+  int k = 0;
+#pragma unroll 2
+  for (; k + 4 <= n; k += 4) {
+    const uint32_t v = w[k >> 2];
+    fold(h, v & 0xffu);
+    fold(h, (v >> 8) & 0xffu);
+    fold(h, (v >> 16) & 0xffu);
+    fold(h, v >> 24);
+  }
+  for (; k < n; ++k) fold(h, buf[k]);
 }
 
 template <int BS>
@@ -84,6 +105,8 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
                                                          const int64_t* __restrict__ extra_off,
                                                          uint64_t* __restrict__ out_keys,
                                                          const int64_t* __restrict__ key_off) {
+  __shared__ uint32_t strips[128 * kStageWords];
+  uint8_t* buf = reinterpret_cast<uint8_t*>(strips + threadIdx.x * kStageWords);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_prompts) return;
   const int bs = BS > 0 ? BS : block_size_rt;
@@ -108,11 +131,18 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
     fold(h, 0x83u);                                 // array(3)
     fold_head64(h, 0x00u, parent);                  // parent: unsigned int
     fold_head64(h, 0x80u, (uint64_t)bs);            // chunk: array(bs)
-    if (BS > 0) {
+    if (BS > 0 && BS <= kStageTokens) {
+      int n = 0;
 #pragma unroll
-      for (int j = 0; j < BS; ++j) fold_token(h, cur[j]);
+      for (int j = 0; j < BS; ++j) n = stage_token(buf, n, cur[j]);
+      fold_staged(h, buf, n);
     } else {
-      for (int j = 0; j < bs; ++j) fold_token(h, __ldg(tk + i * bs + j));
+      for (int j0 = 0; j0 < bs; j0 += kStageTokens) {
+        const int m = min(kStageTokens, bs - j0);
+        int n = 0;
+        for (int j = 0; j < m; ++j) n = stage_token(buf, n, __ldg(tk + i * bs + j0 + j));
+        fold_staged(h, buf, n);
+      }
     }
     bool text = true;
     if (extra_off != nullptr) {                     // pre-encoded X(extra_i), host-built (extra_keys.go)
@@ -129,6 +159,84 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
 #pragma unroll
       for (int j = 0; j < BS; ++j) cur[j] = nxt[j];
     }
+  }
+}
+
+// Two-warp variant for block sizes <= 16 (the vLLM default is 16): 32 chains per CTA, warp 0 STAGES block i+1 of
+// every chain (pass 1) while warp 1 FOLDS block i (pass 2), double-buffered strips, one CTA barrier per block.
+// The two warps sit on different SM sub-partitions, so the encode work leaves the serial chain's issue stream:
+// measured on B200 the one-warp kernel is issue-bound (1048 instructions per block at 3.1 cycles per instruction
+// for a lone warp, profiles/r01_ncu_hash_*.txt).
+template <int BS>
+__global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __restrict__ tokens,
+                                                           const int64_t* __restrict__ prompt_off,
+                                                           const uint64_t* __restrict__ parents, int32_t n_prompts,
+                                                           const uint8_t* __restrict__ extra,
+                                                           const int64_t* __restrict__ extra_off,
+                                                           uint64_t* __restrict__ out_keys,
+                                                           const int64_t* __restrict__ key_off) {
+  static_assert(BS > 0 && BS <= kStageTokens, "two-warp kernel stages one whole block per strip");
+  __shared__ uint32_t strips[2][32 * kStageWords];
+  __shared__ int nbytes[2][32];
+  const int lane = threadIdx.x & 31;
+  const bool stager = threadIdx.x < 32;
+  const int p = blockIdx.x * 32 + lane;
+  const bool live = p < n_prompts;
+  int64_t t0 = 0, nblk = 0, k0 = 0;
+  if (live) {
+    t0 = prompt_off[p];
+    nblk = (prompt_off[p + 1] - t0) / BS;
+    k0 = key_off[p];
+  }
+  // both warps must run the same number of barriers: longest chain in this CTA
+  int64_t nmax = nblk;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  const uint32_t* tk = tokens + t0;
+  uint64_t parent = (!stager && live) ? parents[p] : 0;
+
+  uint32_t cur[BS];  // stager: tokens of the next block to stage, loaded one barrier interval ahead
+  auto load_block = [&](int64_t i) {
+    if (i < nblk) {
+#pragma unroll
+      for (int j = 0; j < BS; ++j) cur[j] = __ldg(tk + i * BS + j);
+    }
+  };
+  auto stage_block = [&](int64_t i) {  // stages `cur` as block i, then starts loading block i+1
+    uint8_t* buf = reinterpret_cast<uint8_t*>(strips[i & 1] + lane * kStageWords);
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) n = stage_token(buf, n, cur[j]);
+    nbytes[i & 1][lane] = n;
+    load_block(i + 1);
+  };
+  if (stager) {
+    load_block(0);
+    if (nblk > 0) stage_block(0);
+  }
+  __syncthreads();
+  for (int64_t i = 0; i < nmax; ++i) {
+    if (stager) {
+      if (i + 1 < nblk) stage_block(i + 1);
+    } else if (i < nblk) {
+      Fnv h = fnv_init();
+      fold(h, 0x83u);
+      fold_head64(h, 0x00u, parent);
+      fold_head64(h, 0x80u, (uint64_t)BS);
+      fold_staged(h, reinterpret_cast<const uint8_t*>(strips[i & 1] + lane * kStageWords), nbytes[i & 1][lane]);
+      bool text = true;
+      if (extra_off != nullptr) {
+        const int64_t e0 = extra_off[k0 + i], e1 = extra_off[k0 + i + 1];
+        if (e1 > e0) {
+          text = false;
+          for (int64_t e = e0; e < e1; ++e) fold(h, extra[e]);
+        }
+      }
+      if (text) fold(h, 0xf6u);
+      parent = fnv_value(h);
+      out_keys[k0 + i] = parent;
+    }
+    __syncthreads();
   }
 }
 
@@ -152,15 +260,28 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   // small batches: 32-thread CTAs so the chains spread over the SMs; large: 128
   const int threads = n_prompts >= 148 * 128 ? 128 : 32;
   const int grid = (n_prompts + threads - 1) / threads;
-  switch (block_size) {
+  static const bool one_warp = std::getenv("KVB_HASH_ONE_WARP") != nullptr;  // A/B switch for profiling
+  const int grid2 = (n_prompts + 31) / 32;
+  switch (one_warp ? -1 : block_size) {
     case 16:
-      hash_chain_kernel<16><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
-                                                     extra_off, out_keys, key_off);
+      hash_chain_kernel_2w<16><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
+                                                    key_off);
+      break;
+    case 8:
+      hash_chain_kernel_2w<8><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
+                                                   key_off);
       break;
     case 4:
-      hash_chain_kernel<4><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
-                                                    extra_off, out_keys, key_off);
+      hash_chain_kernel_2w<4><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
+                                                   key_off);
       break;
+    case -1:
+      if (block_size == 16) {
+        hash_chain_kernel<16><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
+                                                       extra_off, out_keys, key_off);
+        break;
+      }
+      [[fallthrough]];
     default:
       hash_chain_kernel<0><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
                                                     extra_off, out_keys, key_off);
