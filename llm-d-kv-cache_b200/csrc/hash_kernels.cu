@@ -32,9 +32,13 @@ struct Fnv {
 };
 __device__ __forceinline__ void fold(Fnv& h, uint32_t byte) {
   const uint32_t x = h.lo ^ byte;
-  const uint32_t carry = __umulhi(x, 0x1b3u) + (x << 8);
-  h.hi = h.hi * 0x1b3u + carry;
-  h.lo = x * 0x1b3u;
+  // one IMAD.WIDE gives both halves of x * 0x1b3 with a ZERO addend: written as PTX so the compiler cannot fold the
+  // high-half accumulation into the wide multiply's addend, which would chain lo' behind the hi update
+  // (LOP3 -> SHL -> IMAD -> IMAD.WIDE per byte instead of LOP3 -> IMAD.WIDE; measured 33 vs ~11 cycles per byte)
+  uint32_t lo2, carry;
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, 435;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo2), "=r"(carry) : "r"(x));
+  h.hi = h.hi * 0x1b3u + (carry + (x << 8));
+  h.lo = lo2;
 }
 __device__ __forceinline__ Fnv fnv_init() { return Fnv{(uint32_t)kFnvOffset, (uint32_t)(kFnvOffset >> 32)}; }
 __device__ __forceinline__ uint64_t fnv_value(const Fnv& h) { return ((uint64_t)h.hi << 32) | h.lo; }
