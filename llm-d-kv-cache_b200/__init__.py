@@ -13,6 +13,6 @@ from . import _lib
 
 lib = _lib.load()  # fail loudly if the CUDA library is absent
 
-from . import pool, engine, file_mapper, mediums, worker, kvblock, indexer, migrate, partition  # noqa: E402,F401
+from . import pool, engine, file_mapper, mediums, worker, kvblock, indexer, migrate, partition, kvevents, manager, spec  # noqa: E402,F401
 
-__all__ = ["lib", "pool", "engine", "file_mapper", "mediums", "worker", "kvblock", "indexer", "migrate", "partition"]
+__all__ = ["lib", "pool", "engine", "file_mapper", "mediums", "worker", "kvblock", "indexer", "migrate", "partition", "kvevents", "manager", "spec"]

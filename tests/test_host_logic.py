@@ -141,3 +141,34 @@ def test_offload_oracle_layout_properties():
     oo.unpack_blocks(back, [7, 7, 0], p)
     for b, t in zip(back, tensors):
         assert np.array_equal(b[7], t[7]) and np.array_equal(b[0], t[0])
+
+
+def test_manager_and_spec(kvb, tmp_path):
+    """manager.py:43-102 and spec.py:38-157 behaviours with plain config objects (no vLLM import)."""
+    from types import SimpleNamespace as NS
+    cfg = NS(cache_config=NS(block_size=16, cache_dtype="torch.float16"),
+             parallel_config=NS(tensor_parallel_size=2, pipeline_parallel_size=1, prefill_context_parallel_size=1,
+                                world_size=2, rank=0),
+             model_config=NS(model="meta-llama/Llama-3-8B"),
+             kv_transfer_config=NS(kv_connector_extra_config={"shared_storage_path": str(tmp_path), "block_size": 64,
+                                                              "threads_per_gpu": 3}))
+    spec = kvb.spec.SharedStorageOffloadingSpec(cfg)
+    assert spec.gpu_blocks_per_file == 4 and spec.threads_per_gpu == 3
+    assert spec.file_mapper.base_path == oo.base_path(str(tmp_path), "meta-llama/Llama-3-8B", 16, 4, 2, 1, 1, 0, "float16")
+    mgr = spec.get_manager()
+    hashes = [11, 22, 33]
+    assert mgr.lookup(hashes) == 0
+    import os
+    for h in hashes[:2]:
+        p = spec.file_mapper.get_file_name(h)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        open(p, "wb").close()
+    assert mgr.lookup(hashes) == 2 and mgr.lookup([33, 11]) == 0           # consecutive hits from the start only
+    out = mgr.prepare_store(iter(hashes))
+    assert out.block_hashes_to_store == hashes and out.block_hashes_evicted == [] and out.store_spec.block_hashes == hashes
+    assert mgr.prepare_load(hashes).medium() == "SHARED_STORAGE"
+    with pytest.raises(AssertionError):
+        kvb.spec.SharedStorageOffloadingSpec(cfg, extra_config={"block_size": 40})   # not a multiple of gpu block size
+    cfg.parallel_config.rank = 1
+    with pytest.raises(AssertionError):
+        kvb.spec.SharedStorageOffloadingSpec(cfg).get_manager()               # scheduler rank must be 0
