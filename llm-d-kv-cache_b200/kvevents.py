@@ -139,6 +139,9 @@ def realign_extra_features(engine_features, canonical_block_count: int):
     n = len(engine_features)
     if n == canonical_block_count:
         return engine_features
+    if n == 0 or canonical_block_count == 0:
+        # the Go code indexes an empty slice here (panic); no canonical block can come out of it either way
+        return [None] * canonical_block_count
     if n < canonical_block_count:
         return [engine_features[i * n // canonical_block_count] for i in range(canonical_block_count)]
     merged = [None] * canonical_block_count

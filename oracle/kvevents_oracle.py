@@ -129,6 +129,8 @@ def realign_extra_features(engine_features, canonical_count: int):
     n = len(engine_features)
     if n == canonical_count:
         return engine_features
+    if n == 0 or canonical_count == 0:  # Go would panic on the empty slice; nothing can be produced anyway
+        return [None] * canonical_count
     out = [None] * canonical_count
     if n < canonical_count:
         for i in range(canonical_count):
