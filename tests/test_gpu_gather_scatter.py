@@ -175,3 +175,30 @@ def test_baseline_config2_full_size(kvb, torch_cuda):
     torch.cuda.synchronize()
     assert torch.equal(w.sum(dim=(1, 2)), per_tensor)           # checksum of checksums restored
     assert int(w[:, rest_dev].sum().item()) == sum_rest and int(w[:, ids_dev].sum().item()) == sum_listed
+
+
+def test_block_stride_larger_than_fragment(kvb, torch_cuda):
+    """Pools whose rows are wider than the fragment (K-only view of a (N, 2, page) layout): only the first
+    frag_bytes of every row move; the rest of the row is never touched."""
+    torch = torch_cuda
+    T, N, frag, stride = 3, 40, 4096, 8192
+    g = torch.Generator(device="cuda").manual_seed(5)
+    backing = [torch.randint(0, 256, (N, stride), dtype=torch.uint8, device="cuda", generator=g) for _ in range(T)]
+    pool = kvb.pool.KVPool(None, 0, ptrs=[b.data_ptr() for b in backing], num_blocks=N, frag_bytes=frag, stride_bytes=stride)
+    ids = np.array([39, 0, 17, 5], dtype=np.int64)
+    packed = torch.zeros(ids.size * T * frag, dtype=torch.uint8, device="cuda")
+    for variant in (LDG, BULK):
+        packed.zero_()
+        pool.gather(ids, packed, flags=variant)
+        torch.cuda.synchronize()
+        want = oo.pack_blocks([b[:, :frag].cpu().numpy() for b in backing], ids)
+        assert np.array_equal(packed.cpu().numpy(), want)
+        before = [b.clone() for b in backing]
+        newp = torch.randint(0, 256, packed.shape, dtype=torch.uint8, device="cuda", generator=g)
+        pool.scatter(ids, newp, flags=variant)
+        torch.cuda.synchronize()
+        for t, (b, old) in enumerate(zip(backing, before)):
+            assert torch.equal(b[:, frag:], old[:, frag:])                       # the V half of every row untouched
+            exp = old[:, :frag].cpu().numpy().copy()
+            exp[ids] = newp.cpu().numpy().reshape(ids.size, T, frag)[:, t]
+            assert np.array_equal(b[:, :frag].cpu().numpy(), exp)
