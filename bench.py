@@ -45,6 +45,18 @@ BLOCKS_PER_FILE = 16                           # reference default: 256-token fi
 REF_SAMPLE_BLOCKS = min(2048, N_BLOCKS)        # bounded sample for the reference arm (4.3 GB each way)
 
 
+_JSON_FD = None
+
+
+def emit_json(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def env_int(name, d):
     v = os.environ.get(name)
     return int(v) if v else d
@@ -271,7 +283,7 @@ def run_reference(args):
                          "host_cores": cores, **({"note": why} if why else {})},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     reference_step.engines.clear()
     if dist is not None:
         dist.destroy_process_group()
@@ -392,6 +404,23 @@ def run_ours(args):
         assert torch.equal(t[check_ids], r), "pipelined save+load did not restore the pool bit-exact"
     eng.shutdown()
 
+    # ---- PCIe ceiling probe: plain pinned cudaMemcpy of one contiguous 2 GiB buffer, all ranks at once
+    probe_n = 2 << 30
+    hbuf = torch.empty(probe_n, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(probe_n, dtype=torch.uint8, device="cuda")
+    probe = {}
+    for name, (dst_t, src_t) in (("d2h_gbs", (hbuf, dbuf)), ("h2d_gbs", (dbuf, hbuf))):
+        dst_t.copy_(src_t, non_blocking=True)
+        barrier_sync(dist)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            dst_t.copy_(src_t, non_blocking=True)
+        b.record()
+        barrier_sync(dist)
+        probe[name] = world * 3 * probe_n / (max_over_ranks(dist, a.elapsed_time(b)) / 1e3) / 1e9
+    del hbuf, dbuf
+
     # ---- cross-GPU migration over NVLink (only where there is a peer)
     migration = None
     if world > 1 and not args.no_migration:
@@ -427,6 +456,8 @@ def run_ours(args):
                     "blocks_per_s": world * 2 * N_BLOCKS * args.steps / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
                     "store_gbs": world * payload * args.steps / store_s / 1e9,
                     "load_gbs": world * payload * args.steps / max(e2e_s - store_s, 1e-9) / 1e9,
+                    "pcie_probe": {**probe, "what": "contiguous 2 GiB pinned cudaMemcpy, all ranks at once (aggregate GB/s)"},
+                    "frac_of_pcie_probe": e2e_gbs / (2 * probe["d2h_gbs"] * probe["h2d_gbs"] / (probe["d2h_gbs"] + probe["h2d_gbs"])),
                     "pipelined_jobs_gbs": world * 2 * payload / t_pipe / 1e9,
                     "pipelined_note": "extra, not the headline: 25-file jobs, each group loaded back as soon as it is stored, so D2H and H2D overlap",
                     "api": "StorageOffloadEngine.async_store_gpu_blocks/async_load_gpu_blocks/get_finished, tier=host_arena (pinned)"},
@@ -444,7 +475,7 @@ def run_ours(args):
             line["migration"] = migration
         if file_tier is not None:
             line["e2e_file_tier"] = file_tier
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -627,10 +658,12 @@ def run_cpu_baseline(tensors):
 
 
 def main():
-    # NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (the image's default under torchrun);
-    # stdout must carry exactly one JSON line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner on
+    # fd 1).  Keep the real stdout aside for the JSON line and point fd 1 at stderr for everything else.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
