@@ -9,6 +9,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Iterable, Optional, Sequence
 
@@ -196,18 +197,25 @@ class PodEntry:
 
 
 class _Interner:
+    """name <-> dense id; safe to call from several threads (Index operations are, index.go:119)."""
+
     def __init__(self, limit: int, what: str):
         self.ids: dict = {}
         self.names: list = []
         self.limit, self.what = limit, what
+        self._lock = threading.Lock()
 
     def get(self, name: str) -> int:
         i = self.ids.get(name)
         if i is None:
-            if len(self.names) >= self.limit:
-                raise OverflowError(f"too many distinct {self.what} (limit {self.limit})")
-            i = self.ids[name] = len(self.names)
-            self.names.append(name)
+            with self._lock:
+                i = self.ids.get(name)
+                if i is None:
+                    if len(self.names) >= self.limit:
+                        raise OverflowError(f"too many distinct {self.what} (limit {self.limit})")
+                    i = len(self.names)
+                    self.names.append(name)
+                    self.ids[name] = i
         return i
 
 
@@ -225,6 +233,7 @@ class Index:
         self._h = h
         self.pods = _Interner(65536, "pod identifiers")
         self.tiers = _Interner(256, "device tiers")
+        self._tier_lock = threading.Lock()
         self._weights: dict = {}
         self.set_medium_weights({"gpu": 1.0, "cpu": 0.8} if medium_weights is None else medium_weights)  # backend.go:26-31
 
@@ -251,10 +260,16 @@ class Index:
         check(_lib.load().kvb_index_set_tier_weight(self._h, tid, float(self._weights.get(name, 1.0)), int(known)))
 
     def _tier_id(self, name: str) -> int:
-        new = name not in self.tiers.ids
-        tid = self.tiers.get(name)
-        if new:
-            self._push_weight(name, tid)
+        tid = self.tiers.ids.get(name)
+        if tid is None:
+            with self._tier_lock:
+                tid = self.tiers.ids.get(name)
+                if tid is None:
+                    # register the weight BEFORE the id becomes visible to other threads
+                    nxt = len(self.tiers.names)
+                    known = name in self._weights
+                    check(_lib.load().kvb_index_set_tier_weight(self._h, nxt, float(self._weights.get(name, 1.0)), int(known)))
+                    tid = self.tiers.get(name)
         return tid
 
     def _entries(self, entries: Sequence[PodEntry]):

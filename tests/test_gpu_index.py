@@ -200,3 +200,48 @@ def test_table_growth_and_tombstones(kvb, torch_cuda):
     oidx.add(None, keys[:2500], oe)
     got = idx.lookup(keys)
     assert set(got) == set(oidx.lookup(keys)) and len(got) == 17500
+
+
+def test_concurrent_stress(kvb, torch_cuda):
+    """The reference's contract suite hammers every backend from many goroutines (index_test.go:267-585).  Same idea
+    with threads: adders, evictors, lookers and scorers run concurrently; the index must stay consistent —
+    keys only ever touched by adders end up with exactly the expected entries."""
+    import threading
+    K = kvb.kvblock
+    idx = K.Index(expected_keys=1 << 14)
+    n_threads, per = 8, 300
+    stable = {t: [int(x) for x in np.random.default_rng(100 + t).integers(1, 1 << 62, per)] for t in range(n_threads)}
+    churn = [int(x) for x in np.random.default_rng(7).integers(1, 1 << 62, 500)]
+    errors = []
+
+    def worker(t):
+        try:
+            rng = np.random.default_rng(t)
+            ent = [K.PodEntry("pod-%d" % t, "gpu")]
+            for i in range(per):
+                idx.add([stable[t][i] ^ 0x5555], [stable[t][i]], ent)
+                k = churn[int(rng.integers(0, len(churn)))]
+                op = rng.random()
+                if op < 0.4:
+                    idx.add(None, [k], [K.PodEntry("pod-%d" % int(rng.integers(0, 4)), "cpu")])
+                elif op < 0.6:
+                    idx.evict(k, K.REQUEST_KEY, [K.PodEntry("pod-%d" % int(rng.integers(0, 4)), "cpu")])
+                elif op < 0.8:
+                    got = idx.lookup([k, stable[t][i]])
+                    assert stable[t][i] in got
+                else:
+                    kvb.indexer.LongestPrefixScorer(idx).score([stable[t][i], k])
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
+    for t in range(n_threads):
+        got = idx.lookup(stable[t])
+        assert len(got) == per
+        assert all(v == [K.PodEntry("pod-%d" % t, "gpu")] for v in got.values())
+        assert idx.get_request_key(stable[t][0] ^ 0x5555) == stable[t][0]
