@@ -31,25 +31,31 @@ class SharedStorageOffloadingSpec:
         self.gpu_block_size = list(gpu_block_size) if isinstance(gpu_block_size, (list, tuple)) else [gpu_block_size]
         self._manager = None
         self._handlers = None
-        cfg = self.extra_config
-        self.threads_per_gpu = int(cfg.get("threads_per_gpu", DEFAULT_THREADS_PER_GPU))
-        shared_storage_path = cfg.get("shared_storage_path", "/tmp/shared-kv")
-        self.max_staging_memory_gb = int(cfg.get("max_staging_memory_gb", DEFAULT_MAX_STAGING_MEMORY_GB))
-        self.offloaded_block_size = int(cfg.get("block_size", DEFAULT_STORAGE_BLOCK_SIZE))
-        assert len(self.gpu_block_size) == 1, f"Expected exactly one KV cache group, got {len(self.gpu_block_size)}"
-        assert self.offloaded_block_size % self.gpu_block_size[0] == 0, \
-            "offloaded_block_size must be a multiple of gpu_block_size"
-        self.gpu_blocks_per_file = self.offloaded_block_size // self.gpu_block_size[0]
-        self.read_preferring_ratio = float(cfg.get("read_preferring_ratio", DEFAULT_READ_PREFERRING_WORKERS_RATIO))
-        self.max_write_queued_seconds = float(cfg.get("max_write_queued_seconds", DEFAULT_MAX_WRITE_QUEUED_SECONDS))
-        pc = vllm_config.parallel_config
-        tp, pp = pc.tensor_parallel_size, pc.pipeline_parallel_size
-        pcp = getattr(pc, "prefill_context_parallel_size", 1)
-        assert pc.world_size == tp * pp * pcp
-        dtype = str(vllm_config.cache_config.cache_dtype).replace("torch.", "")
-        self.file_mapper = FileMapper(root_dir=shared_storage_path, model_name=vllm_config.model_config.model,
-                                      gpu_block_size=self.gpu_block_size[0], gpu_blocks_per_file=self.gpu_blocks_per_file,
-                                      tp_size=tp, pp_size=pp, pcp_size=pcp, rank=pc.rank, dtype=dtype)
+        # kv_connector_extra_config keys and defaults (reference README.md:107-118, spec.py:50-85)
+        knobs = (("threads_per_gpu", int, DEFAULT_THREADS_PER_GPU),
+                 ("max_staging_memory_gb", int, DEFAULT_MAX_STAGING_MEMORY_GB),
+                 ("read_preferring_ratio", float, DEFAULT_READ_PREFERRING_WORKERS_RATIO),
+                 ("max_write_queued_seconds", float, DEFAULT_MAX_WRITE_QUEUED_SECONDS))
+        for key, cast, default in knobs:
+            setattr(self, key, cast(self.extra_config.get(key, default)))
+        self.offloaded_block_size = int(self.extra_config.get("block_size", DEFAULT_STORAGE_BLOCK_SIZE))
+        if len(self.gpu_block_size) != 1:
+            raise AssertionError(f"Expected exactly one KV cache group, got {len(self.gpu_block_size)}")
+        gbs = self.gpu_block_size[0]
+        if self.offloaded_block_size % gbs:
+            raise AssertionError("offloaded_block_size must be a multiple of gpu_block_size")
+        self.gpu_blocks_per_file = self.offloaded_block_size // gbs
+
+        par = vllm_config.parallel_config
+        sizes = {"tp_size": par.tensor_parallel_size, "pp_size": par.pipeline_parallel_size,
+                 "pcp_size": getattr(par, "prefill_context_parallel_size", 1)}
+        if par.world_size != sizes["tp_size"] * sizes["pp_size"] * sizes["pcp_size"]:
+            raise AssertionError("world_size != tp * pp * pcp")
+        self.file_mapper = FileMapper(
+            root_dir=self.extra_config.get("shared_storage_path", "/tmp/shared-kv"),
+            model_name=vllm_config.model_config.model, gpu_block_size=gbs,
+            gpu_blocks_per_file=self.gpu_blocks_per_file, rank=par.rank,
+            dtype=str(vllm_config.cache_config.cache_dtype).replace("torch.", ""), **sizes)
 
     def get_manager(self) -> SharedStorageOffloadingManager:
         assert self.vllm_config.parallel_config.rank == 0, "Scheduler rank should be 0"
