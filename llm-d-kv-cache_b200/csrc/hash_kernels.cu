@@ -40,6 +40,44 @@ __device__ __forceinline__ void fold(Fnv& h, uint32_t byte) {
   h.hi = h.hi * 0x1b3u + (carry + (x << 8));
   h.lo = lo2;
 }
+// Four bytes (one little-endian word of the byte stream).  The low half is the serial chain (LOP3 -> IMAD.WIDE per
+// byte).  The high half is  hi' = hi*M^4 + c0*M^3 + c1*M^2 + c2*M + c3  with c_j = carry_j + (x_j << 8): evaluated
+// as (hi*M^2 + (c0*M + c1))*M^2 + (c2*M + c3), i.e. only TWO multiply-adds depend on the previous hi instead of four
+// — an in-order lone warp otherwise stalls ~20 cycles per word on that tail (tools/micro/hash_phase_profile.cu).
+__device__ __forceinline__ void fold4(Fnv& h, uint32_t word) {
+  constexpr uint32_t M = 0x1b3u, M2 = M * M;
+  uint32_t lo = h.lo, c[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t x = lo ^ ((word >> (8 * j)) & 0xffu);
+    uint32_t carry;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, 435;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(carry) : "r"(x));
+    c[j] = carry + (x << 8);
+  }
+  h.hi = (h.hi * M2 + (c[0] * M + c[1])) * M2 + (c[2] * M + c[3]);
+  h.lo = lo;
+}
+__device__ __forceinline__ Fnv fnv_init();
+__device__ __forceinline__ void fold_head64(Fnv& h, uint32_t major, uint64_t n);
+__device__ __forceinline__ void fold(Fnv& h, uint32_t byte);
+
+// Block prefix  0x83 | U(parent) | array-head(bs)  for the common shape (parent >= 2^32 so U(parent) is the 9-byte
+// form, bs < 24 so the array head is one byte): 11 bytes packed into words and folded with fold4.
+__device__ __forceinline__ void fold_prefix(Fnv& h, uint64_t parent, uint32_t bs) {
+  if (parent >= 0x100000000ull && bs < 24u) {
+    const uint32_t ph = (uint32_t)(parent >> 32), pl = (uint32_t)parent;
+    // stream: 83 1b P7 P6 | P5 P4 P3 P2 | P1 P0 (80+bs)          (P7 = most significant byte of parent)
+    fold4(h, 0x83u | (0x1bu << 8) | ((ph >> 24) << 16) | (((ph >> 16) & 0xffu) << 24));
+    fold4(h, ((ph >> 8) & 0xffu) | ((ph & 0xffu) << 8) | ((pl >> 24) << 16) | (((pl >> 16) & 0xffu) << 24));
+    fold(h, (pl >> 8) & 0xffu);
+    fold(h, pl & 0xffu);
+    fold(h, 0x80u | bs);
+  } else {
+    fold(h, 0x83u);
+    fold_head64(h, 0x00u, parent);
+    fold_head64(h, 0x80u, (uint64_t)bs);
+  }
+}
 __device__ __forceinline__ Fnv fnv_init() { return Fnv{(uint32_t)kFnvOffset, (uint32_t)(kFnvOffset >> 32)}; }
 __device__ __forceinline__ uint64_t fnv_value(const Fnv& h) { return ((uint64_t)h.hi << 32) | h.lo; }
 
@@ -71,8 +109,11 @@ __device__ __forceinline__ void fold_head64(Fnv& h, uint32_t major, uint64_t n) 
 //           written to the lane's private strip of shared memory with five unconditional byte stores — bytes past
 //           the encoding's length are overwritten by the next token, so there is no branch on the token width;
 //   pass 2 (the serial chain): the strip is read back a word at a time and folded byte by byte.
+#ifdef KVB_HASH_PROFILE
+__device__ long long g_hash_prof[16];
+#endif
 constexpr int kStageTokens = 16;  // tokens staged per pass
-constexpr int kStageWords = 23;   // 92 B strip: 16 x 5 B + 4 B of slack; odd word count => lanes hit distinct banks
+constexpr int kStageWords = 28;   // 112 B strip (16 x 5 B + slack), 16 B aligned so it is read back with 128-bit loads
 
 __device__ __forceinline__ int stage_token(uint8_t* buf, int n, uint32_t t) {
   const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
@@ -87,18 +128,45 @@ __device__ __forceinline__ int stage_token(uint8_t* buf, int n, uint32_t t) {
   return n + (ge64k ? 5 : (ge256 ? 3 : (ge24 ? 2 : 1)));
 }
 
+template <bool BRANCH_FREE>
 __device__ __forceinline__ void fold_staged(Fnv& h, const uint8_t* buf, int n) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(buf);
-  int k = 0;
-#pragma unroll 2
-  for (; k + 4 <= n; k += 4) {
-    const uint32_t v = w[k >> 2];
-    fold(h, v & 0xffu);
-    fold(h, (v >> 8) & 0xffu);
-    fold(h, (v >> 16) & 0xffu);
-    fold(h, v >> 24);
+  // Pull the whole strip into registers first (five 128-bit LDS, one shared-memory latency in total), then fold
+  // from registers: folding out of shared memory word by word exposes the LDS latency on every word to the in-order
+  // issue of a lone warp (29 vs 14 cycles/byte, tools/micro/hash_micro.cu).  asm volatile pins the loads up front.
+  constexpr int kWords = (kStageTokens * 5 + 3) / 4;  // 20
+  uint32_t v[kWords];
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(buf);
+#pragma unroll
+  for (int q = 0; q < kWords / 4; ++q)
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[4 * q]), "=r"(v[4 * q + 1]), "=r"(v[4 * q + 2]), "=r"(v[4 * q + 3])
+                 : "r"(saddr + 16 * q));  // words past n hold stale bytes and are never folded
+  // Whole words, branch-free: every lane runs the same straight-line code (a branch per word costs a lone warp
+  // ~4 cycles/byte, tools/micro/hash_micro.cu) and keeps the folded state only for the words it really has.
+  // The first 12 words (48 B = 16 three-byte tokens, the minimum for real vocabularies) are usually all present.
+  // Large batches have many warps per scheduler: there the issue slots, not the latency, are scarce, and skipping
+  // absent words (a branch per word) wins — BRANCH_FREE = false.
+  const int nwords = n >> 2;
+#pragma unroll
+  for (int i = 0; i < kWords; ++i) {
+    if (BRANCH_FREE) {
+      Fnv t = h;
+      fold4(t, v[i]);
+      const bool take = i < nwords;
+      h.lo = take ? t.lo : h.lo;
+      h.hi = take ? t.hi : h.hi;
+    } else {
+      if (i >= nwords) break;
+      fold4(h, v[i]);
+    }
   }
-  for (; k < n; ++k) fold(h, buf[k]);
+  const int tail = n & 3;  // 0..3 trailing bytes live in word n/4 (dynamic index: re-read it from the strip)
+  if (tail) {
+    const uint32_t tw = reinterpret_cast<const uint32_t*>(buf)[n >> 2];
+    fold(h, tw & 0xffu);
+    if (tail > 1) fold(h, (tw >> 8) & 0xffu);
+    if (tail > 2) fold(h, (tw >> 16) & 0xffu);
+  }
 }
 
 template <int BS>
@@ -109,7 +177,7 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
                                                          const int64_t* __restrict__ extra_off,
                                                          uint64_t* __restrict__ out_keys,
                                                          const int64_t* __restrict__ key_off) {
-  __shared__ uint32_t strips[128 * kStageWords];
+  __shared__ __align__(16) uint32_t strips[128 * kStageWords];
   uint8_t* buf = reinterpret_cast<uint8_t*>(strips + threadIdx.x * kStageWords);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_prompts) return;
@@ -132,20 +200,18 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
       for (int j = 0; j < BS; ++j) nxt[j] = __ldg(tk + (i + 1) * BS + j);
     }
     Fnv h = fnv_init();
-    fold(h, 0x83u);                                 // array(3)
-    fold_head64(h, 0x00u, parent);                  // parent: unsigned int
-    fold_head64(h, 0x80u, (uint64_t)bs);            // chunk: array(bs)
+    fold_prefix(h, parent, (uint32_t)bs);           // array(3) | parent | array(bs)
     if (BS > 0 && BS <= kStageTokens) {
       int n = 0;
 #pragma unroll
       for (int j = 0; j < BS; ++j) n = stage_token(buf, n, cur[j]);
-      fold_staged(h, buf, n);
+      fold_staged<true>(h, buf, n);
     } else {
       for (int j0 = 0; j0 < bs; j0 += kStageTokens) {
         const int m = min(kStageTokens, bs - j0);
         int n = 0;
         for (int j = 0; j < m; ++j) n = stage_token(buf, n, __ldg(tk + i * bs + j0 + j));
-        fold_staged(h, buf, n);
+        fold_staged<true>(h, buf, n);
       }
     }
     bool text = true;
@@ -171,7 +237,7 @@ __global__ void __launch_bounds__(128) hash_chain_kernel(const uint32_t* __restr
 // The two warps sit on different SM sub-partitions, so the encode work leaves the serial chain's issue stream:
 // measured on B200 the one-warp kernel is issue-bound (1048 instructions per block at 3.1 cycles per instruction
 // for a lone warp, profiles/r01_ncu_hash_*.txt).
-template <int BS>
+template <int BS, bool BRANCH_FREE>
 __global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __restrict__ tokens,
                                                            const int64_t* __restrict__ prompt_off,
                                                            const uint64_t* __restrict__ parents, int32_t n_prompts,
@@ -180,7 +246,7 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __res
                                                            uint64_t* __restrict__ out_keys,
                                                            const int64_t* __restrict__ key_off) {
   static_assert(BS > 0 && BS <= kStageTokens, "two-warp kernel stages one whole block per strip");
-  __shared__ uint32_t strips[2][32 * kStageWords];
+  __shared__ __align__(16) uint32_t strips[2][32 * kStageWords];
   __shared__ int nbytes[2][32];
   const int lane = threadIdx.x & 31;
   const bool stager = threadIdx.x < 32;
@@ -219,15 +285,31 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __res
     if (nblk > 0) stage_block(0);
   }
   __syncthreads();
+#ifdef KVB_HASH_PROFILE
+  long long pc[5] = {0, 0, 0, 0, 0};  // stager work, folder prefix, folder staged, folder rest, barrier wait
+#define PROF(slot, t_begin) pc[slot] += clock64() - (t_begin)
+#else
+#define PROF(slot, t_begin)
+#endif
   for (int64_t i = 0; i < nmax; ++i) {
+#ifdef KVB_HASH_PROFILE
+    long long tb = clock64();
+#endif
     if (stager) {
       if (i + 1 < nblk) stage_block(i + 1);
+      PROF(0, tb);
     } else if (i < nblk) {
       Fnv h = fnv_init();
-      fold(h, 0x83u);
-      fold_head64(h, 0x00u, parent);
-      fold_head64(h, 0x80u, (uint64_t)BS);
-      fold_staged(h, reinterpret_cast<const uint8_t*>(strips[i & 1] + lane * kStageWords), nbytes[i & 1][lane]);
+      fold_prefix(h, parent, (uint32_t)BS);
+      PROF(1, tb);
+#ifdef KVB_HASH_PROFILE
+      long long ts = clock64();
+#endif
+      fold_staged<BRANCH_FREE>(h, reinterpret_cast<const uint8_t*>(strips[i & 1] + lane * kStageWords), nbytes[i & 1][lane]);
+      PROF(2, ts);
+#ifdef KVB_HASH_PROFILE
+      long long tr = clock64();
+#endif
       bool text = true;
       if (extra_off != nullptr) {
         const int64_t e0 = extra_off[k0 + i], e1 = extra_off[k0 + i + 1];
@@ -239,9 +321,21 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __res
       if (text) fold(h, 0xf6u);
       parent = fnv_value(h);
       out_keys[k0 + i] = parent;
+      PROF(3, tr);
     }
+#ifdef KVB_HASH_PROFILE
+    long long tw = clock64();
+#endif
     __syncthreads();
+    PROF(4, tw);
   }
+#ifdef KVB_HASH_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    long long* dst = g_hash_prof + (stager ? 0 : 5);
+    for (int q = 0; q < 5; ++q) dst[q] = pc[q];
+    g_hash_prof[10] = nmax;
+  }
+#endif
 }
 
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
@@ -266,19 +360,28 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   const int grid = (n_prompts + threads - 1) / threads;
   static const bool one_warp = std::getenv("KVB_HASH_ONE_WARP") != nullptr;  // A/B switch for profiling
   const int grid2 = (n_prompts + 31) / 32;
+  // fewer CTAs than ~2 per SM sub-partition: every warp is alone on its scheduler -> optimise latency, else issue slots
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool latency_bound = grid2 <= 4 * sm_count(dev);
   switch (one_warp ? -1 : block_size) {
+#define KVB_LAUNCH_2W(BSV)                                                                                          \
+  if (latency_bound)                                                                                                \
+    hash_chain_kernel_2w<BSV, true><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off,  \
+                                                         out_keys, key_off);                                        \
+  else                                                                                                              \
+    hash_chain_kernel_2w<BSV, false><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, \
+                                                          out_keys, key_off)
     case 16:
-      hash_chain_kernel_2w<16><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
-                                                    key_off);
+      KVB_LAUNCH_2W(16);
       break;
     case 8:
-      hash_chain_kernel_2w<8><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
-                                                   key_off);
+      KVB_LAUNCH_2W(8);
       break;
     case 4:
-      hash_chain_kernel_2w<4><<<grid2, 64, 0, s>>>(tokens, prompt_off, parents, n_prompts, extra, extra_off, out_keys,
-                                                   key_off);
+      KVB_LAUNCH_2W(4);
       break;
+#undef KVB_LAUNCH_2W
     case -1:
       if (block_size == 16) {
         hash_chain_kernel<16><<<grid, threads, 0, s>>>(tokens, prompt_off, parents, n_prompts, block_size, extra,
