@@ -4,14 +4,15 @@
 // (pkg/kvcache/kvblock/token_processor.go:123-205):
 //     key_i = FNV64a( 0x83 | U(parent) | ARR(chunk_i) | X(extra_i) ),  parent = key_{i-1}
 // with U/ARR the RFC 8949 shortest-form heads the reference gets from fxamacker/cbor v2.7.0
-// CanonicalEncOptions (token_processor.go:97).  The payload is never materialised: every
-// CBOR byte is folded into the FNV state as it is produced.
+// CanonicalEncOptions (token_processor.go:97).  The payload never reaches global memory: token bytes
+// are staged in a per-lane strip of shared memory and folded from registers.
 //
-// Parallelism: FNV-1a is a serial byte chain and keys chain across blocks, so one prompt is
-// one serial chain.  One THREAD per prompt (32 chains per warp); per token the 1..5 CBOR bytes
-// are folded under per-token predicates so lanes holding 1/2/3/5-byte tokens do not diverge.
-// Latency/ALU-bound (two dependent 32-bit ops per payload byte per chain), not HBM-bound: the only
-// memory traffic is 4 B/token in and 8 B/key out.
+// Parallelism: FNV-1a is a serial byte chain and keys chain across blocks, so one prompt is one serial
+// chain: one LANE per prompt (32 chains per warp), parallel only across prompts.
+//   hash_chain_kernel_2w<BS<=16>  two warps per 32 chains: warp 0 encodes block i+1, warp 1 folds block i
+//   hash_chain_kernel<BS>         one warp does both (any block size; A/B switch KVB_HASH_ONE_WARP)
+// Bound: issue/latency of a lone warp (xor -> wide multiply, >= 10-12 cycles per payload byte on B200,
+// tools/micro/hash_micro.cu), NOT HBM: the only memory traffic is 4 B/token in and 8 B/key out.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
