@@ -198,6 +198,12 @@ def pipelined_save_load(eng, files, groups, files_per_job=25, first_job=1000):
     return time.perf_counter() - t0
 
 
+def pool_checksum(big) -> int:
+    """64-bit wrap-around sum of every 8-byte word of the pool (order independent)."""
+    import torch
+    return int(big.view(torch.int64).sum().item())
+
+
 def dist_setup(n_gpus):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -346,6 +352,13 @@ def run_ours(args):
     launches_dev = lib.kvb_launch_count() - launches0
     gather_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev_sets]))
     scatter_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev_sets]))
+    # untimed proof that the load leg really restores: save, ZERO every saved page, load, compare
+    sum0 = pool_checksum(big)
+    pool.gather_dev(ids_dev, packed)
+    big[:, ids_dev] = 0
+    assert pool_checksum(big) != sum0
+    pool.scatter_dev(ids_dev, packed)
+    assert pool_checksum(big) == sum0, "device-resident save+load did not restore the pool bit-exact"
     for t, r in zip(tensors[::8], check_ref):
         assert torch.equal(t[check_ids], r), "device-resident save+load did not restore the pool bit-exact"
     value = world * 2 * payload * args.steps / (dev_ms / 1e3) / 1e9
@@ -388,6 +401,17 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches_e2e = lib.kvb_launch_count() - launches1
     stats1 = eng.stats()
+    # untimed proof through the engine: store, ZERO every saved page, load, whole-pool checksum + samples
+    vfiles = [f"verify/{i:06d}" for i in range(n_files)]
+    job[0] += 1
+    assert eng.async_store_gpu_blocks(job[0], vfiles, groups)
+    _drain(eng, job[0])
+    big[:, ids_dev] = 0
+    job[0] += 1
+    assert eng.async_load_gpu_blocks(job[0], vfiles, groups)
+    _drain(eng, job[0])
+    eng.arena_clear()
+    assert pool_checksum(big) == sum0, "engine save+load did not restore the pool bit-exact"
     for t, r in zip(tensors[::8], check_ref):
         assert torch.equal(t[check_ids], r), "engine save+load did not restore the pool bit-exact"
     e2e_gbs = world * 2 * payload * args.steps / e2e_s / 1e9
@@ -505,9 +529,18 @@ def run_file_tier(kvb, tensors, root="/dev/shm/kvb_file_bench"):
             assert eng.async_store_gpu_blocks(1, files, groups)
             _drain(eng, 1)
             t1 = time.perf_counter()
+            if tag == "warm":   # the warm-up pass doubles as the proof: zero the saved pages before loading them back
+                import torch
+                ids_dev = torch.from_numpy(ids).to(tensors[0].device)
+                keep = [t[ids_dev[:32]].clone() for t in tensors[::16]]
+                for t in tensors:
+                    t[ids_dev] = 0
             assert eng.async_load_gpu_blocks(2, files, groups)
             _drain(eng, 2)
             t2 = time.perf_counter()
+            if tag == "warm":
+                for t, k in zip(tensors[::16], keep):
+                    assert torch.equal(t[ids_dev[:32]], k), "file-tier load did not restore zeroed pages"
             shutil.rmtree(f"{root}/{tag}", ignore_errors=True)
             res = {"value": 2 * payload / (t2 - t0) / 1e9, "unit": "GB/s", "store_gbs": payload / (t1 - t0) / 1e9,
                    "load_gbs": payload / (t2 - t1) / 1e9, "io_threads": threads,
