@@ -474,22 +474,29 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
   if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);  // KV produced on the caller's stream
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !opts.direct_host_io) {
     ok = launch_gather(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
     kernels++;
   }
   if (e == cudaSuccess && ok) {
-    // D2H: merge destinations that are contiguous on the host into one copy
+    // merge destinations that are contiguous on the host into one run
     size_t i = 0;
-    while (i < dests.size() && e == cudaSuccess) {
+    while (i < dests.size() && e == cudaSuccess && ok) {
       size_t j = i;
       int64_t bytes = (int64_t)dests[i].f->ids.size() * block_bytes;
       while (j + 1 < dests.size() && dests[j + 1].host == dests[i].host + bytes) {
         ++j;
         bytes += (int64_t)dests[j].f->ids.size() * block_bytes;
       }
-      e = cudaMemcpyAsync(dests[i].host, w.d_packed + dests[i].first_block * block_bytes, (size_t)bytes,
-                          cudaMemcpyDeviceToHost, w.stream);
+      if (opts.direct_host_io) {
+        // fused gather + D2H: the kernel's bulk stores land in the pinned host run (UVA), no HBM staging, no memcpy
+        ok = launch_gather(pool, w.d_ids + dests[i].first_block, bytes / block_bytes, dests[i].host, w.stream,
+                           opts.copy_flags) == KVB_OK;
+        kernels++;
+      } else {
+        e = cudaMemcpyAsync(dests[i].host, w.d_packed + dests[i].first_block * block_bytes, (size_t)bytes,
+                            cudaMemcpyDeviceToHost, w.stream);
+      }
       d2h += bytes;
       i = j + 1;
     }
@@ -565,12 +572,19 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
         ++j;
         bytes += (int64_t)srcs[j].f->ids.size() * block_bytes;
       }
-      e = cudaMemcpyAsync(w.d_packed + srcs[i].first_block * block_bytes, srcs[i].host, (size_t)bytes,
-                          cudaMemcpyHostToDevice, w.stream);
+      if (opts.direct_host_io) {
+        // fused H2D + scatter: the kernel's bulk loads read the pinned host run directly
+        ok = ok && launch_scatter(pool, w.d_ids + srcs[i].first_block, bytes / block_bytes, srcs[i].host, w.stream,
+                                  opts.copy_flags) == KVB_OK;
+        kernels++;
+      } else {
+        e = cudaMemcpyAsync(w.d_packed + srcs[i].first_block * block_bytes, srcs[i].host, (size_t)bytes,
+                            cudaMemcpyHostToDevice, w.stream);
+      }
       h2d += bytes;
       i = j + 1;
     }
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && !opts.direct_host_io) {
       ok = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
       kernels++;
     }
@@ -725,7 +739,7 @@ void kvb_engine_default_opts(kvb_engine_opts_t* o) {
   o->copy_flags = KVB_COPY_DEFAULT;
   o->host_arena_bytes = 0;
   o->chunk_bytes = 64ll << 20;
-  o->num_slots = 0;
+  o->direct_host_io = 0;
   o->strict_load_errors = 0;
 }
 

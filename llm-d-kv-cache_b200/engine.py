@@ -25,7 +25,7 @@ class StorageOffloadEngine:
     def __init__(self, io_threads: int, gpu_blocks_per_file: int, tensors: Sequence, read_preferring_workers: int,
                  gds_mode: str = "disabled", max_write_queued_seconds: float = 10.0, *, tier: str = "file",
                  host_arena_bytes: int = 0, chunk_bytes: int = 0, copy_variant: int = 0,
-                 strict_load_errors: bool = False):
+                 strict_load_errors: bool = False, direct_host_io: bool = False):
         if gds_mode != "disabled":
             # GDS file tier is SURVEY §8(f) "next"; the reference itself falls back to the CPU
             # staging path when GDS is unavailable (storage_offload.cpp:129-134).
@@ -44,6 +44,7 @@ class StorageOffloadEngine:
         if chunk_bytes:
             opts.chunk_bytes = int(chunk_bytes)
         opts.strict_load_errors = 1 if strict_load_errors else 0
+        opts.direct_host_io = 1 if direct_host_io else 0
         h = C.c_void_p()
         check(lib.kvb_engine_create(self.pool.handle, C.byref(opts), C.byref(h)))
         self._h = h

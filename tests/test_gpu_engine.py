@@ -339,3 +339,40 @@ def test_reads_overtake_queued_writes(kvb, torch_cuda):
     assert order.index(99) < 4, order               # the read did not wait behind every queued write
     assert all(torch.equal(t[127], t[0]) for t in tensors)
     eng.shutdown()
+
+
+@pytest.mark.parametrize("tier", ["file", "host_arena"])
+def test_direct_host_io_roundtrip(kvb, torch_cuda, tier):
+    """direct_host_io: the gather kernel's bulk stores land in pinned host memory (fused gather+D2H) and the scatter
+    kernel reads it back (fused H2D+scatter); same files / arena entries, same bytes as the staged path."""
+    torch = torch_cuda
+    T, N, frag, bpf = 16, 96, 16384, 4
+    g = torch.Generator(device="cuda").manual_seed(21)
+    tensors = [torch.randint(0, 256, (N, frag), dtype=torch.uint8, device="cuda", generator=g) for _ in range(T)]
+    ref = [t.clone() for t in tensors]
+    ids = np.random.default_rng(2).permutation(N)[:70]
+    groups = [ids[:2].tolist()] + [ids[2 + 4 * i: 6 + 4 * i].tolist() for i in range(17)]
+    files = [f"{TMP_DIR}/direct/{tier}/{i}.bin" for i in range(len(groups))]
+    eng = kvb.engine.StorageOffloadEngine(3, bpf, tensors, 2, "disabled", 0.0, tier=tier, host_arena_bytes=1 << 28,
+                                          chunk_bytes=1 << 20, direct_host_io=True)
+    assert eng.async_store_gpu_blocks(1, files, groups)
+    while not eng.get_finished():
+        time.sleep(0.001)
+    if tier == "file":
+        np_t = [t.cpu().numpy() for t in ref]
+        for f, grp in zip(files, groups):
+            assert np.array_equal(np.fromfile(f, dtype=np.uint8), oo.file_image(np_t, grp, bpf))
+    for t in tensors:
+        t.zero_()
+    assert eng.async_load_gpu_blocks(2, files, groups)
+    while not eng.get_finished():
+        time.sleep(0.001)
+    idt = torch.from_numpy(ids).cuda()
+    for t, r in zip(tensors, ref):
+        assert torch.equal(t[idt], r[idt])
+        mask = torch.ones(N, dtype=torch.bool, device="cuda")
+        mask[idt] = False
+        assert int(t[mask].sum()) == 0
+    st = eng.stats()
+    assert st["bytes_stored"] == st["bytes_loaded"] == 70 * T * frag
+    eng.shutdown()
