@@ -664,6 +664,47 @@ def run_migration(kvb, dist, rank, world, local, tensors, pool, steps, warmup):
                     r.close()
     barrier_sync(dist)
     remote.close()
+
+    # status quo for the same hand-off with the reference: no cross-GPU path exists, a block reaches another GPU by
+    # being stored by the source worker and loaded by the destination worker through the shared tier (here /dev/shm)
+    mod, _why = load_reference_engine()
+    if mod is not None:
+        ref_dir = "/dev/shm/kvb_ref_migrate"
+        nf = n // BLOCKS_PER_FILE
+        files = [f"{ref_dir}/{i:06d}.bin" for i in range(nf)]
+        sid = np.random.default_rng(10).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64)   # rank 0's source pages
+        did = (POOL_BLOCKS // 2 + np.random.default_rng(21).permutation(POOL_BLOCKS // 2)[:n]).astype(np.int64)
+        grp = lambda ids: [[int(x) for x in ids[i * BLOCKS_PER_FILE:(i + 1) * BLOCKS_PER_FILE]] for i in range(nf)]
+        t_store = t_load = 0.0
+        try:
+            eng = None
+            if rank in (0, 1):
+                eng = mod.StorageOffloadEngine(min(64, os.cpu_count() or 1), BLOCKS_PER_FILE,
+                                               [t.view(torch.int8) for t in tensors], 48, "disabled", 0.0)
+            barrier_sync(dist)
+            if rank == 0:
+                shutil.rmtree(ref_dir, ignore_errors=True)
+                t0 = time.perf_counter()
+                eng.async_store_gpu_blocks(1, files, grp(sid))
+                _drain(eng, 1)
+                t_store = time.perf_counter() - t0
+            barrier_sync(dist)
+            if rank == 1:
+                t0 = time.perf_counter()
+                eng.async_load_gpu_blocks(2, files, grp(did))
+                _drain(eng, 2)
+                t_load = time.perf_counter() - t0
+            barrier_sync(dist)
+            t_store, t_load = max_over_ranks(dist, t_store), max_over_ranks(dist, t_load)
+            out["via_host_reference_engine"] = {
+                "gbs": payload / (t_store + t_load) / 1e9, "store_s": t_store, "load_s": t_load,
+                "note": "GPU0 -> /dev/shm -> GPU1 with the unmodified reference engine (store on rank 0, then load on rank 1)"}
+            del eng
+        except Exception as e:  # never let the comparison take the bench down
+            out["via_host_reference_engine"] = {"error": repr(e)}
+        if rank == 0:
+            shutil.rmtree(ref_dir, ignore_errors=True)
+        barrier_sync(dist)
     return out
 
 
