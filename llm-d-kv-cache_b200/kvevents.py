@@ -132,6 +132,11 @@ class VLLMAdapter:
         return pod, model, EventBatch(float(raw[0]), [self.decode_event(list(e)) for e in raw[1]])
 
 
+class SGLangAdapter(VLLMAdapter):
+    """SGLang publishes the same positional msgpack encoding and may omit trailing optional fields
+    (engineadapter/sglang_adapter.go:40-239, padFields); the decoder above already treats absent trailing fields as nil."""
+
+
 # ------------------------------------------------------------------------------------------ event processing
 def realign_extra_features(engine_features, canonical_block_count: int):
     """Per-engine-block features -> per-canonical-block (pool.go:206-249): replicate when the engine block is
