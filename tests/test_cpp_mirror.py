@@ -40,3 +40,23 @@ def test_cpp_mirror_parity(kvb, torch_cuda, golden, tmp_path):
     r = subprocess.run([exe, gold], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK ")
+
+
+def test_engine_header_compiles(kvb, tmp_path):
+    r = subprocess.run([CXX, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", "/usr/local/cuda/include", "-c", os.path.join(ROOT, "tests", "cpp", "test_engine.cpp"),
+                        "-o", str(tmp_path / "e.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_engine_roundtrip(kvb, torch_cuda, tmp_path):
+    exe = str(tmp_path / "test_engine")
+    r = subprocess.run([CXX, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(ROOT, "tests", "cpp", "test_engine.cpp"), "-o", exe, "-L", PKG, "-lkvb",
+                        "-Wl,-rpath," + PKG, "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,/usr/local/cuda/lib64",
+                        "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, str(tmp_path / "files")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK engine round trips" in r.stdout
