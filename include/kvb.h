@@ -98,7 +98,8 @@ typedef struct kvb_engine_opts {
   int32_t tier;                    /* KVB_TIER_* */
   int32_t copy_flags;              /* KVB_COPY_* */
   int64_t host_arena_bytes;        /* KVB_TIER_HOST_ARENA capacity */
-  int64_t chunk_bytes;             /* packed HBM staging per pipeline slot (0 = default 64 MiB) */
+  int64_t chunk_bytes;             /* bytes gathered per kernel launch = packed HBM staging per worker (0 = 64 MiB);
+                                      a chunk always holds whole files */
   int32_t direct_host_io;          /* 1 = the gather/scatter kernels read/write the pinned host buffers directly
                                       (fused gather+D2H / H2D+scatter, no HBM staging, no cudaMemcpy); 0 = staged */
   int32_t strict_load_errors;      /* 0 = reference behaviour: a failed load still reports ok (storage_offload.cpp:378-383);
