@@ -241,3 +241,47 @@ def test_raw_messages_end_to_end(kvb, torch_cuda):
     assert set(idx.lookup(keys)) == {keys[0], keys[2]}
     proc.process_raw_message(ad, "kv@p@m", b"garbage")          # logged and dropped
     assert proc.skipped == 1
+
+
+def test_adapter_known_answers(kvb):
+    """common_test.go:28-91 and vllm_adapter_test.go:29-440 (values transcribed), for the product adapter and the oracle."""
+    E = kvb.kvevents
+    ad = E.VLLMAdapter()
+    for parse in (ad.parse_topic, eo.parse_topic):
+        assert parse("kv@pod-123@llama-2-7b") == ("pod-123", "llama-2-7b")
+        assert parse("pod-123@llama-2-7b") == ("pod-123@llama-2-7b", "")
+        assert parse("fallback") == ("fallback", "")
+    for h in (E._hash_u64, eo.hash_as_u64):
+        assert h(42) == 42 and h((12345).to_bytes(8, "big")) == 12345
+        assert h(b"\x01" * 24 + (7).to_bytes(8, "big")) == 7 and h(b"\x01\x02") == 0x0102   # last 8 bytes / left-padded
+        assert h(-1) == (1 << 64) - 1                                                          # int64 reinterpretation
+        for bad in (b"", "not a hash"):
+            with pytest.raises(ValueError):
+                h(bad)
+    stored = ["BlockStored", [100, 101], 99, [1, 2, 3], 16, None, "gpu", None, None]
+    pod, model, batch = ad.parse_message("kv@pod-1@llama-2-7b", msgpack.packb([1234567890.0, [stored], None]))
+    assert (pod, model, batch.timestamp, len(batch.events)) == ("pod-1", "llama-2-7b", 1234567890.0, 1)
+    ev = batch.events[0]
+    assert ev.block_hashes == [100, 101] and ev.parent_hash == 99 and ev.tokens == [1, 2, 3] and ev.device_tier == "gpu"
+    # forward compatibility: unknown trailing fields are ignored, present ones parsed
+    ev = ad.decode_event(["BlockStored", [400, 401], 399, [10, 11, 12], 16, None, "gpu", "my-lora", [["extra", "keys"]],
+                          "completely-unknown-field"])
+    assert (ev.lora_id, ev.lora_name, ev.extra_keys) == (None, "my-lora", [["extra", "keys"]])
+    # backward compatibility: missing trailing fields
+    for fields, want in ((["BlockStored", [1], None, [5], 16, 7, "cpu"], (7, "cpu", None)),
+                         (["BlockStored", [1], None, [5], 16, 7], (7, "", None)),
+                         (["BlockStored", [1], None, [5], 16], (None, "", None))):
+        ev = ad.decode_event(fields)
+        assert (ev.lora_id, ev.device_tier, ev.lora_name) == want and ev.parent_hash == 0 and ev.extra_keys is None
+    rm = ad.decode_event(["BlockRemoved", [5, 6], "cpu", "future-field"])
+    assert rm.block_hashes == [5, 6] and rm.device_tier == "cpu"
+    assert ad.decode_event(["BlockRemoved", [5]]).device_tier == ""
+    assert isinstance(ad.decode_event(["AllBlocksCleared"]), E.AllBlocksClearedEvent)
+    for bad in (["BlockStored", [1], None, [5], 16, None, None, None, ["not-a-list"]],   # invalid extra_keys entry
+                ["Unknown"], [], [17]):
+        with pytest.raises(ValueError):
+            ad.decode_event(bad)
+    for payload in (b"", b"\x93\x01"):                                                    # empty / malformed
+        with pytest.raises(ValueError):
+            ad.parse_message("kv@p@m", payload)
+    assert isinstance(E.SGLangAdapter().decode_event(["BlockStored", [1], None, [5], 16]), E.BlockStoredEvent)
