@@ -160,7 +160,7 @@ def reference_step(mod, tensors, ids, step_tag, io_threads, root="/dev/shm/kvb_r
 reference_step.engines = {}
 
 
-def _drain(eng, job_id, timeout=600.0):
+def _drain(eng, job_id, timeout=600.0, sleep=0.0005):
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < timeout:
         for jid, ok in eng.get_finished():
@@ -168,7 +168,8 @@ def _drain(eng, job_id, timeout=600.0):
                 if not ok:
                     raise RuntimeError(f"job {job_id} failed")
                 return
-        time.sleep(0.0005)
+        if sleep:
+            time.sleep(sleep)
     raise TimeoutError(f"job {job_id}")
 
 
@@ -196,6 +197,30 @@ def pipelined_save_load(eng, files, groups, files_per_job=25, first_job=1000):
     if pending_loads:
         raise TimeoutError("pipelined save+load")
     return time.perf_counter() - t0
+
+
+def single_file_job_latency(eng, ids, root, jobs=40, first_job=500000, cleanup=None):
+    """Median wall time of ONE-file jobs (16 blocks = 32 MiB) issued one at a time: store latency and load latency.
+    Small jobs are what a serving engine issues per request; works for any engine with the reference's surface."""
+    bpf = BLOCKS_PER_FILE
+    st, ld = [], []
+    for j in range(jobs):
+        grp = [[int(x) for x in ids[(j * bpf) % (len(ids) - bpf):(j * bpf) % (len(ids) - bpf) + bpf]]]
+        f = [f"{root}/lat_{j:04d}.bin"]
+        t0 = time.perf_counter()
+        assert eng.async_store_gpu_blocks(first_job + 2 * j, f, grp)
+        _drain(eng, first_job + 2 * j, sleep=0)
+        t1 = time.perf_counter()
+        assert eng.async_load_gpu_blocks(first_job + 2 * j + 1, f, grp)
+        _drain(eng, first_job + 2 * j + 1, sleep=0)
+        t2 = time.perf_counter()
+        if j >= 5:  # first jobs warm the workers
+            st.append(t1 - t0)
+            ld.append(t2 - t1)
+    if cleanup:
+        cleanup()
+    return {"store_ms_median": float(np.median(st)) * 1e3, "load_ms_median": float(np.median(ld)) * 1e3,
+            "blocks_per_job": bpf, "bytes_per_job": bpf * BLOCK_BYTES, "jobs": len(st)}
 
 
 def pool_checksum(big) -> int:
@@ -426,6 +451,8 @@ def run_ours(args):
     t_pipe = max_over_ranks(dist, t_pipe)
     for t, r in zip(tensors[::8], check_ref):
         assert torch.equal(t[check_ids], r), "pipelined save+load did not restore the pool bit-exact"
+    eng.arena_clear()
+    job_latency = single_file_job_latency(eng, ids_np, "lat") if rank == 0 else None
     eng.shutdown()
     # extra: fused variant — the gather / scatter kernels address the pinned arena directly (no staging, no memcpy)
     eng_d = kvb.engine.StorageOffloadEngine(env_int("KVB_BENCH_IO_THREADS", 4), bpf, tensors, 3, "disabled", 0.0,
@@ -503,6 +530,7 @@ def run_ours(args):
                     "pcie_probe": {**probe, "what": "contiguous 2 GiB pinned cudaMemcpy, all ranks at once (aggregate GB/s)"},
                     "frac_of_pcie_probe": e2e_gbs / (2 * probe["d2h_gbs"] * probe["h2d_gbs"] / (probe["d2h_gbs"] + probe["h2d_gbs"])),
                     "pipelined_jobs_gbs": world * 2 * payload / t_pipe / 1e9,
+                    "single_file_job_latency": job_latency,
                     "direct_host_io_gbs": world * 2 * payload / t_direct / 1e9,
                     "direct_host_io_note": "extra: fused gather+D2H / H2D+scatter kernels addressing the pinned arena (no HBM staging, no cudaMemcpy)",
                     "pipelined_note": "extra, not the headline: 25-file jobs, each group loaded back as soon as it is stored, so D2H and H2D overlap",
@@ -568,6 +596,7 @@ def run_file_tier(kvb, tensors, root="/dev/shm/kvb_file_bench"):
                    "load_gbs": payload / (t2 - t1) / 1e9, "io_threads": threads,
                    "sample": f"{REF_SAMPLE_BLOCKS} blocks, {bpf} blocks/file, reference .bin format on /dev/shm "
                              "(same sample and grouping as cpu_baseline)"}
+        res["single_file_job_latency"] = single_file_job_latency(eng, ids, f"{root}/lat")
     finally:
         eng.shutdown()
         shutil.rmtree(root, ignore_errors=True)
@@ -734,8 +763,14 @@ def run_cpu_baseline(tensors):
                 t_pipe = None
                 print(f"[bench] reference pipelined pattern failed: {e}", file=sys.stderr)
             shutil.rmtree(root, ignore_errors=True)
+            try:
+                lat = single_file_job_latency(ref_eng, ids, "/dev/shm/kvb_ref_bench/lat",
+                                              cleanup=lambda: shutil.rmtree("/dev/shm/kvb_ref_bench/lat", ignore_errors=True))
+            except Exception as e:
+                lat = {"error": repr(e)}
             reference_step.engines.clear()
             return {"value": 2 * payload / (a + b) / 1e9, "unit": "GB/s", "cores": io_threads, "kind": "reference",
+                    "single_file_job_latency": lat,
                     "pipelined_jobs_gbs": (2 * payload / t_pipe / 1e9) if t_pipe else None,
                     "sample": sample + ", default cudaMemcpyAsync path, io_threads=min(64,nproc)",
                     "store_gbs": payload / a / 1e9, "load_gbs": payload / b / 1e9, "host_cores": cores}
