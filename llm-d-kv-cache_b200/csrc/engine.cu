@@ -63,6 +63,7 @@ struct ChunkTask {
   bool is_store = false;
   std::vector<FilePart> files;  // whole files, total blocks <= blocks_per_chunk
   int64_t n_blocks = 0;
+  int io_parts = 1;             // >1: nothing else was queued when the task started -> split file I/O for latency
   cudaEvent_t ready = nullptr;  // caller-stream event (shared by the job's chunks, owned by last user)
   std::shared_ptr<void> ready_owner;
 };
@@ -314,6 +315,26 @@ static bool read_all(int fd, uint8_t* p, int64_t n, int64_t off) {
   return true;
 }
 
+// One file's payload through the page cache.  With parts > 1 the byte range is split over short-lived helper threads
+// (pread with explicit offsets is thread-safe on one descriptor): a lone 32 MiB load drops from 7.5 to 4.0 ms on tmpfs.
+// Only reads are split — writes to ONE file serialise on the inode lock (measured: no gain) — and only when no other
+// task is queued, so the throughput regime keeps one I/O thread per worker.
+static bool file_rw(int fd, uint8_t* p, int64_t n, int64_t off, bool is_write, int parts) {
+  if (parts <= 1 || n < (8ll << 20)) return is_write ? write_all(fd, p, n, off) : read_all(fd, p, n, off);
+  const int64_t chunk = ((n + parts - 1) / parts + 4095) & ~4095ll;
+  std::atomic<bool> ok{true};
+  std::vector<std::thread> th;
+  for (int k = 0; k < parts; ++k) {
+    const int64_t lo = (int64_t)k * chunk, len = std::min(chunk, n - lo);
+    if (len <= 0) break;
+    th.emplace_back([=, &ok] {
+      if (!(is_write ? write_all(fd, p + lo, len, off + lo) : read_all(fd, p + lo, len, off + lo))) ok = false;
+    });
+  }
+  for (auto& t : th) t.join();
+  return ok.load();
+}
+
 }  // namespace kvb
 
 using namespace kvb;
@@ -382,8 +403,8 @@ struct kvb_engine {
   void worker_loop(Worker* w);
   bool run_store(Worker& w, ChunkTask& t);
   bool run_load(Worker& w, ChunkTask& t);
-  bool write_file(const FilePart& f, const uint8_t* payload);
-  bool read_file(const FilePart& f, uint8_t* payload);
+  bool write_file(const FilePart& f, const uint8_t* payload, int parts);
+  bool read_file(const FilePart& f, uint8_t* payload, int parts);
   int submit(int64_t job_id, int32_t n_files, const char* const* files, const int64_t* ids, const int64_t* off,
              void* caller_stream, bool is_store);
 };
@@ -403,7 +424,7 @@ bool kvb_engine::worker_init(Worker& w) {
 }
 
 // reference on-disk format, CPU path: full-size file, payload tail-aligned inside the bpf slots
-bool kvb_engine::write_file(const FilePart& f, const uint8_t* payload) {
+bool kvb_engine::write_file(const FilePart& f, const uint8_t* payload, int parts) {
   const std::string& target = f.path;
   size_t pos = target.find_last_of('/');
   if (pos != std::string::npos && !mkdirs(target.substr(0, pos))) return false;
@@ -412,19 +433,21 @@ bool kvb_engine::write_file(const FilePart& f, const uint8_t* payload) {
   if (fd < 0) return false;
   const int64_t n = (int64_t)f.ids.size();
   const int64_t off = ((int64_t)opts.gpu_blocks_per_file - n) * block_bytes;
-  bool ok = ::ftruncate(fd, file_bytes) == 0 && write_all(fd, payload, n * block_bytes, off);
+  bool ok = ::ftruncate(fd, file_bytes) == 0 &&
+            file_rw(fd, const_cast<uint8_t*>(payload), n * block_bytes, off, true, 1);
+  (void)parts;
   ok = (::close(fd) == 0) && ok;
   if (ok && ::rename(tmp.c_str(), target.c_str()) != 0) ok = false;
   if (!ok) ::unlink(tmp.c_str());
   return ok;
 }
 
-bool kvb_engine::read_file(const FilePart& f, uint8_t* payload) {
+bool kvb_engine::read_file(const FilePart& f, uint8_t* payload, int parts) {
   int fd = ::open(f.path.c_str(), O_RDONLY);
   if (fd < 0) return false;
   const int64_t n = (int64_t)f.ids.size();
   const int64_t off = ((int64_t)opts.gpu_blocks_per_file - n) * block_bytes;
-  bool ok = read_all(fd, payload, n * block_bytes, off);
+  bool ok = file_rw(fd, payload, n * block_bytes, off, false, parts);
   ::close(fd);
   return ok;
 }
@@ -512,7 +535,7 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
   } else if (ok) {
     for (auto& d : dests) {
       if (t.job->cancelled.load()) break;  // in-flight cancelled job skips the file write (storage_offload.cpp:228-229)
-      if (!write_file(*d.f, d.host)) {
+      if (!write_file(*d.f, d.host, t.io_parts)) {
         set_error("store: writing %s failed: %s", d.f->path.c_str(), std::strerror(errno));
         ok = false;
       }
@@ -549,7 +572,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       srcs.push_back({&f, src, n});
     } else {
       uint8_t* dst = w.h_stage + n * block_bytes;
-      if (!read_file(f, dst)) {
+      if (!read_file(f, dst, t.io_parts)) {
         set_error("load: reading %s failed", f.path.c_str());
         ok = false;
         break;
@@ -620,6 +643,7 @@ void kvb_engine::worker_loop(Worker* w) {
       auto& q = !first.empty() ? first : second;
       task = std::move(q.front());
       q.pop_front();
+      if (q_high.empty() && q_normal.empty() && opts.tier == KVB_TIER_FILE) task->io_parts = 4;
     }
     if (!inited) {
       inited = worker_init(*w);
