@@ -565,9 +565,10 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
     if (opts.tier == KVB_TIER_HOST_ARENA) {
       const uint8_t* src = arena.pin_read(f.path, nb, block_bytes);
       if (!src) {
+        // the reference runs one task per file: a missing file fails alone, the others still load
         set_error("load: %s not in host arena (or holds fewer than %lld blocks)", f.path.c_str(), (long long)nb);
         ok = false;
-        break;
+        continue;
       }
       srcs.push_back({&f, src, n});
     } else {
@@ -575,7 +576,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       if (!read_file(f, dst, t.io_parts)) {
         set_error("load: reading %s failed", f.path.c_str());
         ok = false;
-        break;
+        continue;
       }
       srcs.push_back({&f, dst, n});
     }
@@ -583,7 +584,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
     n += nb;
   }
   cudaError_t e = cudaSuccess;
-  if (ok && n > 0) {
+  if (n > 0) {
     if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
@@ -597,8 +598,9 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       }
       if (opts.direct_host_io) {
         // fused H2D + scatter: the kernel's bulk loads read the pinned host run directly
-        ok = ok && launch_scatter(pool, w.d_ids + srcs[i].first_block, bytes / block_bytes, srcs[i].host, w.stream,
-                                  opts.copy_flags) == KVB_OK;
+        if (launch_scatter(pool, w.d_ids + srcs[i].first_block, bytes / block_bytes, srcs[i].host, w.stream,
+                           opts.copy_flags) != KVB_OK)
+          ok = false;
         kernels++;
       } else {
         e = cudaMemcpyAsync(w.d_packed + srcs[i].first_block * block_bytes, srcs[i].host, (size_t)bytes,
@@ -607,25 +609,27 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       h2d += bytes;
       i = j + 1;
     }
+    bool moved = true;
     if (e == cudaSuccess && !opts.direct_host_io) {
-      ok = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
+      moved = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
       kernels++;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
     if (e != cudaSuccess) {
       set_error("load chunk: %s", cudaGetErrorString(e));
       cudaGetLastError();
+      moved = false;
+    }
+    if (moved) {  // the files that were found did load, whatever happened to the missing ones
+      bytes_loaded += n * block_bytes;
+      files_loaded += (int64_t)srcs.size();
+    } else {
       ok = false;
     }
   }
   if (opts.tier == KVB_TIER_HOST_ARENA)
     for (auto& s : srcs) arena.unpin(s.f->path);
-  if (ok) {
-    bytes_loaded += n * block_bytes;
-    files_loaded += (int64_t)srcs.size();
-  } else {
-    load_failures++;
-  }
+  if (!ok) load_failures++;
   return ok;
 }
 

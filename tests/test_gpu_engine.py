@@ -376,3 +376,32 @@ def test_direct_host_io_roundtrip(kvb, torch_cuda, tier):
     st = eng.stats()
     assert st["bytes_stored"] == st["bytes_loaded"] == 70 * T * frag
     eng.shutdown()
+
+
+@pytest.mark.parametrize("tier", ["file", "host_arena"])
+def test_missing_file_does_not_block_other_files(kvb, torch_cuda, tier):
+    """The reference runs one task per file (storage_offload.cpp:373-419): a missing file fails alone, the other files
+    of the same job are still loaded.  Same here although several files share one GPU chunk."""
+    torch = torch_cuda
+    tensors = [torch.randint(1, 256, (16, 4096), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    ref = [t.clone() for t in tensors]
+    eng = kvb.engine.StorageOffloadEngine(2, 2, tensors, 1, "disabled", 0.0, tier=tier, host_arena_bytes=1 << 24,
+                                          strict_load_errors=True)
+    files = [f"{TMP_DIR}/partial/{tier}/{i}.bin" for i in range(3)]
+    groups = [[0, 1], [2, 3], [4, 5]]
+    assert eng.async_store_gpu_blocks(1, [files[0], files[2]], [groups[0], groups[2]])      # file 1 never stored
+    while not eng.get_finished():
+        time.sleep(0.001)
+    for t in tensors:
+        t.zero_()
+    assert eng.async_load_gpu_blocks(2, files, groups)
+    res = []
+    while not res:
+        res = eng.get_finished()
+    assert res == [(2, False)]                                   # strict mode reports the failure ...
+    for t, r in zip(tensors, ref):
+        assert torch.equal(t[[0, 1, 4, 5]], r[[0, 1, 4, 5]])     # ... but the files that exist were loaded
+        assert int(t[[2, 3]].sum()) == 0
+    st = eng.stats()
+    assert st["files_loaded"] == 2 and st["load_failures"] == 1
+    eng.shutdown()
