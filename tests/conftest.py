@@ -17,7 +17,10 @@ def pytest_configure(config):
 def kvb():
     """The product package (llm-d-kv-cache_b200); builds libkvb.so first if nvcc is present and it is stale."""
     try:
-        build = importlib.import_module("llm-d-kv-cache_b200.build")
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("kvb_build", os.path.join(ROOT, "llm-d-kv-cache_b200", "build.py"))
+        build = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(build)
         build.build()
     except Exception as e:  # no nvcc on this box: use the prebuilt library that travelled with the repo
         print(f"[conftest] not rebuilding libkvb.so: {e}")
