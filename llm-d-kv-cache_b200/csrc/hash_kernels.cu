@@ -7,12 +7,17 @@
 // CanonicalEncOptions (token_processor.go:97).  The payload never reaches global memory: token bytes
 // are staged in a per-lane strip of shared memory and folded from registers.
 //
-// Parallelism: FNV-1a is a serial byte chain and keys chain across blocks, so one prompt is one serial
-// chain: one LANE per prompt (32 chains per warp), parallel only across prompts.
-//   hash_chain_kernel_2w<BS<=16>  two warps per 32 chains: warp 0 encodes block i+1, warp 1 folds block i
-//   hash_chain_kernel<BS>         one warp does both (any block size; A/B switch KVB_HASH_ONE_WARP)
-// Bound: issue/latency of a lone warp (xor -> wide multiply, >= 10-12 cycles per payload byte on B200,
-// tools/micro/hash_micro.cu), NOT HBM: the only memory traffic is 4 B/token in and 8 B/key out.
+// Parallelism: keys chain across blocks, so one prompt is one serial chain of blocks.  Two kernel families:
+//   lane per prompt (32 chains per warp; the byte chain xor -> multiply runs serially in each lane)
+//     hash_chain_kernel_2w<BS<=16>  two warps per 32 chains: warp 0 encodes block i+1, warp 1 folds block i
+//     hash_chain_kernel<BS>         one warp does both (any block size; A/B switch KVB_HASH_ONE_WARP)
+//   warp per prompt, batches <= kWpcMaxPrompts and block size 4/8/16 (KVB_HASH_KERNEL=lanes disables it)
+//     hash_chain_kernel_wpc<BS>     the 32 lanes resolve one block's byte stream together: FNV-1a is a T-function,
+//                                   so its low byte is 8 prefix-XOR rounds (warp votes) and the 64-bit state a dot
+//                                   product with powers of P^-1 (see the comment above the kernel)
+// Bound: issue/latency of dependent warp instructions (xor -> wide multiply >= 10-12 cycles per payload byte for the
+// lane kernels, ~75 cycles per vote round for the warp kernel; tools/micro/), NOT HBM: the only memory traffic is
+// 4 B/token in and 8 B/key out.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -339,6 +344,299 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_2w(const uint32_t* __res
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-chain kernel for small batches (one CTA per prompt): the 32 lanes of a warp fold ONE block's byte stream
+// together, so the serial cost per block is ~8 warp votes instead of ~75 dependent xor->multiply steps.
+//
+// FNV-1a is a T-function: bit k of (h ^ b) * P depends only on bits <= k of h and b.  With l_i = low byte of the
+// state before stream byte b_i and z_i = l_i ^ b_i:
+//   (1) l_{i+1} = low8(z_i * 0xb3)               (0xb3 = low byte of P): an 8-bit chain, and for every bit k
+//       l_{i+1,k} = l_{i,k} ^ b_{i,k} ^ c_{i,k},  c_{i,k} = bit k of ((z_i mod 2^k) * 0xb3)
+//       — linear in bit k once the lower bits are known, so bit k of EVERY position is one prefix-XOR over the stream:
+//       a warp vote + popc per bit, 8 rounds per block, each lane owning 3 consecutive stream positions;
+//   (2) h ^ b = h + e with e_i = z_i - l_i in [-255, 255], so  h_m = P^m * (h_0 + sum_i e_i * Q^i),  Q = P^-1 mod 2^64:
+//       once the l_i are known the 64-bit state is a dot product with per-position constants, summed over the warp
+//       in four 16-bit limbs (redux.sync.add).
+// Stream of one block (block sizes < 24, parent >= 2^32):  83 1b P7..P0 (80+BS) | token bytes | f6   (<= 92 bytes).
+// Warp 0 of the CTA stages blocks two ahead (token widths -> exclusive scan -> byte scatter -> per-lane 3-byte words),
+// warp 1 runs the rounds; the rare block whose parent is < 2^32 (a caller-supplied root) and multimodal extras fall back
+// to the byte-serial fold.  Measured against the lane-per-prompt kernels in DESIGN.md section 4.
+constexpr uint64_t inv_mod_2_64(uint64_t a) {  // Newton: the correct low bits double every step (a * a == 1 mod 8)
+  uint64_t x = a;
+  for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+  return x;
+}
+constexpr uint64_t kFnvPrimeInv = inv_mod_2_64(kFnvPrime);
+static_assert(kFnvPrimeInv * kFnvPrime == 1ull, "P^-1 mod 2^64");
+constexpr int kWpcPositions = 96;  // 32 lanes x 3 stream positions
+constexpr int kWpcPrefix = 11;     // 83 1b P7..P0 (80+BS)
+constexpr int kWpcMaxPrompts = 1536;  // beyond ~2000 prompts the lane-per-prompt kernels (flat ~66 us to 19k) win
+
+__device__ __forceinline__ uint64_t pow_u64(uint64_t base, uint32_t e) {  // e < 128
+  uint64_t r = 1;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    if (e & 1u) r *= base;
+    base *= base;
+    e >>= 1;
+  }
+  return r;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(64) hash_chain_kernel_wpc(const uint32_t* __restrict__ tokens,
+                                                            const int64_t* __restrict__ prompt_off,
+                                                            const uint64_t* __restrict__ parents,
+                                                            const uint8_t* __restrict__ extra,
+                                                            const int64_t* __restrict__ extra_off,
+                                                            uint64_t* __restrict__ out_keys,
+                                                            const int64_t* __restrict__ key_off) {
+  static_assert(BS > 0 && BS < 24 && kWpcPrefix + 5 * BS + 1 <= kWpcPositions, "stream must fit 96 positions");
+  constexpr uint32_t kFull = 0xffffffffu;
+  __shared__ uint32_t bw[3][32];                          // per lane: its 3 stream bytes (parent bytes left zero)
+  __shared__ uint8_t raw[3][kWpcPositions];               // token bytes (+ f6); the byte-serial fallback reads it too
+  // per staged block, one 16 B load: .x/.y = P^(stream length), .z = bytes after the prefix, .w = 1 if nil extra (f6 in)
+  __shared__ uint4 meta[3];
+  __shared__ uint32_t tring[4][BS];                       // token ring (cp.async landing buffer)
+  __shared__ uint64_t pw[kWpcPositions];                  // P^m
+  __shared__ uint32_t slot_id[2];
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x;
+  const int64_t t0 = prompt_off[p];
+  const int nblk = (int)((prompt_off[p + 1] - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
+  if (nblk == 0) return;
+  const int64_t k0 = key_off[p];
+  for (int t = threadIdx.x; t < kWpcPositions; t += 64) pw[t] = pow_u64(kFnvPrime, (uint32_t)t);
+  // Which warp folds: a warp's scheduler (SM sub-partition) is its hardware slot % 4 and a CTA's two warps take
+  // consecutive slots, so "warp 1 folds" would put every folder of an SM on sub-partitions 1 and 3.  Pick by slot so
+  // that successive CTAs' folders land on 0, 2, 1, 3, ...; fall back to warp 1 if the slots are not an aligned pair.
+  if (lane == 0) {
+    uint32_t wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    slot_id[threadIdx.x >> 5] = wid;
+  }
+  __syncthreads();  // also publishes pw[]
+  const uint32_t sa = slot_id[0], sb = slot_id[1];
+  const bool fa = ((sa >> 2) & 1u) == (sa & 1u), fb = ((sb >> 2) & 1u) == (sb & 1u);
+  const int folder_warp = (fa != fb) ? (fa ? 0 : 1) : 1;
+  const bool stager = (int)(threadIdx.x >> 5) != folder_warp;
+
+  // ---- stager: tokens land in a 4-slot shared-memory ring by cp.async, three blocks ahead of their use (an L2/HBM
+  // round trip is longer than one block interval; a register destination would stall the warp on the rotation moves)
+  const uint32_t lt = (1u << lane) - 1u;
+  auto fetch_tokens = [&](int i) {  // one commit group per block, empty past the end so the group count stays uniform
+    if (lane < BS && i < nblk) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[i & 3][lane]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(tokens + t0 + (int64_t)i * BS + lane));
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  int sbuf = 0;              // buffer of the next block to stage (i % 3 without the division)
+  auto stage = [&](int i) {  // block i -> buffer i % 3
+    const int buf = sbuf;
+    sbuf = sbuf == 2 ? 0 : sbuf + 1;
+    fetch_tokens(i + 3);
+    asm volatile("cp.async.wait_group 3;" ::: "memory");  // all but the three newest groups: block i has landed
+    const uint32_t t = lane < BS ? tring[i & 3][lane] : 0u;  // each lane reads back its own copy
+    const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
+    const uint32_t head = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
+    const uint32_t pay = ge64k ? t : (ge256 ? (t << 16) : (t << 24));  // payload, left-aligned big-endian
+    // width = 1 + [>=24] + [>=256] + 2*[>=65536]: the exclusive scan over the block is three votes and popcounts
+    // (lanes >= BS hold token 0 and vote false everywhere)
+    const uint32_t v24 = __ballot_sync(kFull, ge24), v256 = __ballot_sync(kFull, ge256),
+                   v64k = __ballot_sync(kFull, ge64k);
+    const int w = 1 + (ge24 ? 1 : 0) + (ge256 ? 1 : 0) + (ge64k ? 2 : 0);
+    const int off = lane + __popc(v24 & lt) + __popc(v256 & lt) + 2 * __popc(v64k & lt);
+    const int n_tok = BS + __popc(v24) + __popc(v256) + 2 * __popc(v64k);
+    bool text = true;
+    if (extra_off != nullptr) text = extra_off[k0 + i + 1] <= extra_off[k0 + i];
+    {  // exactly w bytes per token (neighbouring lanes' ranges must not overlap); lane BS appends f6 for a nil extra;
+       // predicated stores, no divergent branches
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(raw[buf]) + (lane < BS ? off : n_tok);
+      const uint32_t first = lane < BS ? head : 0xf6u;
+      const int nst = lane < BS ? w : ((lane == BS && text) ? 1 : 0);
+      asm volatile(
+          "{\n\t.reg .pred p1, p2, p3, p4;\n\t"
+          "setp.gt.s32 p1, %2, 0;\n\tsetp.gt.s32 p2, %2, 1;\n\tsetp.gt.s32 p3, %2, 2;\n\tsetp.gt.s32 p4, %2, 3;\n\t"
+          "@p1 st.shared.u8 [%0], %1;\n\t@p2 st.shared.u8 [%0+1], %3;\n\t@p3 st.shared.u8 [%0+2], %4;\n\t"
+          "@p4 st.shared.u8 [%0+3], %5;\n\t@p4 st.shared.u8 [%0+4], %6;\n\t}"
+          :
+          : "r"(d), "r"(first), "r"(nst), "r"(pay >> 24), "r"((pay >> 16) & 0xffu), "r"((pay >> 8) & 0xffu), "r"(pay & 0xffu)
+          : "memory");
+    }
+    __syncwarp();
+    const int n_tot = n_tok + (text ? 1 : 0);
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // unconditional loads from a clamped index, then selects
+      const int pos = 3 * lane + j, idx = pos - kWpcPrefix;
+      const uint32_t ld = raw[buf][idx < 0 ? 0 : idx];
+      const uint32_t fixed = pos == 0 ? 0x83u : (pos == 1 ? 0x1bu : (pos == kWpcPrefix - 1 ? (0x80u | BS) : 0u));
+      const uint32_t byte = (idx >= 0 && idx < n_tot) ? ld : fixed;
+      word |= byte << (8 * j);
+    }
+    bw[buf][lane] = word;
+    if (lane == 0) {
+      const uint64_t pm = pw[kWpcPrefix + n_tot];
+      meta[buf] = make_uint4((uint32_t)pm, (uint32_t)(pm >> 32), (uint32_t)n_tot, text ? 1u : 0u);
+    }
+  };
+
+  // ---- folder constants: where the parent's bytes land in this lane's word, and Q^(3*lane + j)
+  uint32_t psel = 0, pmask = 0;
+  int32_t qlo[3];
+  uint32_t qhi[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int pos = 3 * lane + j;
+    if (pos >= 2 && pos <= 9) {  // stream position 2 + k carries parent byte 7 - k
+      psel |= (uint32_t)(9 - pos) << (4 * j);
+      pmask |= 0xffu << (8 * j);
+    }
+    const uint64_t q = pow_u64(kFnvPrimeInv, (uint32_t)pos);
+    qlo[j] = (int32_t)(uint32_t)q;  // q = (qhi + [qlo < 0]) * 2^32 + (signed) qlo
+    qhi[j] = (uint32_t)(q >> 32) + (qlo[j] < 0 ? 1u : 0u);
+  }
+
+  if (stager) {
+    fetch_tokens(0);
+    fetch_tokens(1);
+    fetch_tokens(2);
+  }
+  if (stager) {
+    stage(0);
+    if (nblk > 1) stage(1);
+  }
+  __syncthreads();
+
+  uint64_t parent = parents[p];
+  uint32_t w_cur = 0;
+  int n_cur = 0, text_cur = 1, cbuf = 0, nbuf = 1;  // buffers of block i and i + 1 (i % 3 without the division)
+  uint64_t pw_cur = 0;
+  if (!stager) {
+    w_cur = bw[0][lane];
+    const uint4 m = meta[0];
+    pw_cur = ((uint64_t)m.y << 32) | m.x;
+    n_cur = (int)m.z;
+    text_cur = (int)m.w;
+  }
+#ifdef KVB_HASH_PROFILE
+  long long wp[5] = {0, 0, 0, 0, 0};  // stager: work | folder: rounds, reduce+combine, rest | both: barrier wait
+#define WPROF(slot, t_begin) wp[slot] += clock64() - (t_begin)
+#else
+#define WPROF(slot, t_begin)
+#endif
+  for (int i = 0; i < nblk; ++i) {
+#ifdef KVB_HASH_PROFILE
+    long long tb = clock64();
+#endif
+    if (stager) {
+      if (i + 2 < nblk) stage(i + 2);
+      WPROF(0, tb);
+    } else {
+      uint32_t w_nxt = 0;
+      int n_nxt = 0, text_nxt = 1;
+      uint64_t pw_nxt = 0;
+      if (i + 1 < nblk) {  // staged during the previous interval, published by its barrier
+        const int nb = nbuf;
+        w_nxt = bw[nb][lane];
+        const uint4 m = meta[nb];
+        pw_nxt = ((uint64_t)m.y << 32) | m.x;
+        n_nxt = (int)m.z;
+        text_nxt = (int)m.w;
+      }
+      uint64_t key;
+      if (parent >= 0x100000000ull) {
+        const uint32_t w = w_cur | (__byte_perm((uint32_t)parent, (uint32_t)(parent >> 32), psel) & pmask);
+        const uint32_t b0 = __byte_perm(w, 0u, 0x4440u), b1 = __byte_perm(w, 0u, 0x4441u), b2 = __byte_perm(w, 0u, 0x4442u);
+        // z_j starts as b_j: bit k of z_j * 0xb3 is then exactly b_{j,k} ^ c_{j,k}; resolved l bits are xor-ed in.
+        // Serial part of a round: IMAD -> LOP3 (xor3) -> LOP3.P -> VOTE -> LOP3 -> POPC -> SHL -> LOP3, ~61 cycles
+        // (tools/micro/warp_chain_latency.cu); everything else is prepared while the vote is in flight.
+        uint32_t z0 = b0, z1 = b1, z2 = b2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          constexpr uint32_t kL0 = (uint32_t)(kFnvOffset & 0xffu);
+          const uint32_t mask = 1u << k;
+          const uint32_t p0 = z0 * 0xb3u, p1 = z1 * 0xb3u, p2 = z2 * 0xb3u;
+          uint32_t votes;
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t.reg .b32 g;\n\tlop3.b32 g, %1, %2, %3, 0x96;\n\tand.b32 g, g, %4;\n\t"
+              "setp.ne.u32 q, g, 0;\n\tvote.sync.ballot.b32 %0, q, 0xffffffff;\n\t}"
+              : "=r"(votes)
+              : "r"(p0), "r"(p1), "r"(p2), "r"(mask));
+          // l bit k at the lane's positions = l0 bit ^ parity(earlier lanes) ^ {0, t0, t0 ^ t1}: the local part now
+          const uint32_t m0 = (kL0 & mask) ? mask : 0u;
+          uint32_t zc0 = z0 ^ m0, zc1 = z1 ^ m0 ^ (p0 & mask), zc2 = z2 ^ m0 ^ ((p0 ^ p1) & mask);
+          asm volatile("" : "+r"(zc0), "+r"(zc1), "+r"(zc2));  // keep them off the vote -> popc chain (no re-association)
+          const uint32_t sh = (uint32_t)__popc(votes & lt) << k;  // parity of all earlier positions' toggles -> bit k
+          // z = zc ^ (sh & mask) as ONE LOP3 each (the compiler would share sh & mask and add a level to the chain)
+          asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z0) : "r"(zc0), "r"(sh), "r"(mask));
+          asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z1) : "r"(zc1), "r"(sh), "r"(mask));
+          asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z2) : "r"(zc2), "r"(sh), "r"(mask));
+        }
+        WPROF(1, tb);
+#ifdef KVB_HASH_PROFILE
+        tb = clock64();
+#endif
+        // e = z - l with l = z ^ b
+        const int32_t e0 = (int32_t)z0 - (int32_t)(z0 ^ b0), e1 = (int32_t)z1 - (int32_t)(z1 ^ b1),
+                      e2 = (int32_t)z2 - (int32_t)(z2 ^ b2);
+        int64_t acc;  // three signed IMAD.WIDE (plain C++ widens both operands and emulates the 64-bit product)
+        asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %1, %2;\n\tmad.wide.s32 t, %3, %4, t;\n\tmad.wide.s32 %0, %5, %6, t;\n\t}"
+            : "=l"(acc)
+            : "r"(e0), "r"(qlo[0]), "r"(e1), "r"(qlo[1]), "r"(e2), "r"(qlo[2]));
+        const uint32_t hi = (uint32_t)e0 * qhi[0] + (uint32_t)e1 * qhi[1] + (uint32_t)e2 * qhi[2];
+        // lane 0 carries the FNV offset basis into the sum
+        const uint64_t tl = (uint64_t)acc + ((uint64_t)hi << 32) + (lane == 0 ? kFnvOffset : 0ull);
+        const uint32_t tlo = (uint32_t)tl, thi = (uint32_t)(tl >> 32);
+        const uint64_t s0 = __reduce_add_sync(kFull, tlo & 0xffffu), s1 = __reduce_add_sync(kFull, tlo >> 16),
+                       s2 = __reduce_add_sync(kFull, thi & 0xffffu), s3 = __reduce_add_sync(kFull, thi >> 16);
+        key = pw_cur * (s0 + (s1 << 16) + (s2 << 32) + (s3 << 48));
+#ifdef KVB_HASH_PROFILE
+        if (key == 0x1234u) wp[3] = 1;  // keep `key` live up to the clock read
+#endif
+        WPROF(2, tb);
+#ifdef KVB_HASH_PROFILE
+        tb = clock64();
+#endif
+      } else {  // short parent head: byte-serial fold, every lane the same
+        Fnv h = fnv_init();
+        fold_prefix(h, parent, (uint32_t)BS);
+        const uint8_t* src = raw[cbuf];
+        for (int k = 0; k < n_cur; ++k) fold(h, src[k]);
+        key = fnv_value(h);
+      }
+      if (!text_cur) {  // pre-encoded X(extra_i) follows the tokens (extra_keys.go)
+        Fnv h{(uint32_t)key, (uint32_t)(key >> 32)};
+        for (int64_t e = extra_off[k0 + i]; e < extra_off[k0 + i + 1]; ++e) fold(h, extra[e]);
+        key = fnv_value(h);
+      }
+      if (lane == 0) out_keys[k0 + i] = key;
+      parent = key;
+      w_cur = w_nxt;
+      n_cur = n_nxt;
+      text_cur = text_nxt;
+      pw_cur = pw_nxt;
+      cbuf = nbuf;
+      nbuf = nbuf == 2 ? 0 : nbuf + 1;
+      WPROF(3, tb);
+    }
+#ifdef KVB_HASH_PROFILE
+    long long tw = clock64();
+#endif
+    __syncthreads();
+    WPROF(4, tw);
+  }
+#ifdef KVB_HASH_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    long long* dst = g_hash_prof + (stager ? 0 : 5);
+    for (int q = 0; q < 5; ++q) dst[q] = wp[q];
+    g_hash_prof[10] = nblk;
+  }
+#endif
+#undef WPROF
+}
+
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
 __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__ name, uint32_t len,
                                  uint64_t* __restrict__ out) {
@@ -360,6 +658,24 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   const int threads = n_prompts >= 148 * 128 ? 128 : 32;
   const int grid = (n_prompts + threads - 1) / threads;
   static const bool one_warp = std::getenv("KVB_HASH_ONE_WARP") != nullptr;  // A/B switch for profiling
+  // KVB_HASH_KERNEL=lanes forces the lane-per-prompt kernels (A/B and parity tests of both families); read per call
+  const char* force = std::getenv("KVB_HASH_KERNEL");
+  const bool lanes_only = force != nullptr && std::strcmp(force, "lanes") == 0;
+  if (!one_warp && !lanes_only && n_prompts <= kWpcMaxPrompts && (block_size == 16 || block_size == 8 || block_size == 4)) {
+    if (block_size == 16)
+      hash_chain_kernel_wpc<16><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    else if (block_size == 8)
+      hash_chain_kernel_wpc<8><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    else
+      hash_chain_kernel_wpc<4><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("hash kernel launch failed: %s", cudaGetErrorString(e));
+      return KVB_ERR_CUDA;
+    }
+    count_launch();
+    return KVB_OK;
+  }
   const int grid2 = (n_prompts + 31) / 32;
   // fewer CTAs than ~2 per SM sub-partition: every warp is alone on its scheduler -> optimise latency, else issue slots
   int dev = 0;

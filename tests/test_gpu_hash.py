@@ -7,6 +7,17 @@ from oracle import kvblock_oracle as o
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "lanes"])
+def hash_kernel_family(request, monkeypatch):
+    """Every test runs twice: default dispatch (warp-per-chain kernel for small batches of block size 4/8/16) and with
+    the lane-per-prompt kernels forced (KVB_HASH_KERNEL is read on every launch)."""
+    if request.param == "lanes":
+        monkeypatch.setenv("KVB_HASH_KERNEL", "lanes")
+    else:
+        monkeypatch.delenv("KVB_HASH_KERNEL", raising=False)
+    return request.param
+
+
 def _oracle_features(kvb_feats):
     return None if kvb_feats is None else [
         None if f is None else o.BlockExtraFeatures([o.MMHash(m.hash) for m in f.mm_hashes]) for f in kvb_feats]
@@ -92,3 +103,26 @@ def test_long_context_chain_property(kvb, torch_cuda):
     assert tail == full[1000:]
     sample = o.TokenProcessor(16, "").tokens_to_kv_block_keys(0, [int(x) for x in toks[:1600]], "meta-llama/Llama-3-8B")
     assert sample == full[:100]
+
+
+@pytest.mark.parametrize("n_prompts", [1, 31, 1536, 1537, 5000])
+def test_dispatch_boundary_batches_match_c_oracle(kvb, torch_cuda, n_prompts):
+    """Batch sizes either side of the warp-per-chain / lane-per-prompt dispatch threshold, ragged lengths, mixed token
+    widths and short parents, against the oracle's C restatement."""
+    from oracle import kvblock_oracle_c as oc
+    rng = np.random.default_rng(n_prompts)
+    lens = rng.integers(0, 200, n_prompts)
+    off = np.zeros(n_prompts + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    width = rng.choice([5, 8, 16, 17, 32], int(off[-1]))
+    tokens = (rng.integers(0, 1 << 32, int(off[-1]), dtype=np.uint64) & ((np.uint64(1) << width.astype(np.uint64)) - np.uint64(1))).astype(np.uint32)
+    parents = rng.integers(0, 1 << 63, n_prompts, dtype=np.int64).astype(np.uint64)
+    parents[::7] = rng.integers(0, 70000, parents[::7].size).astype(np.uint64)     # short CBOR heads for the parent
+    for bs in (4, 8, 16):
+        want, woff = oc.hash_batch(tokens, off, parents, bs)
+        tp = kvb.kvblock.ChunkedTokenDatabase(bs, "")
+        got = np.empty(int(woff[-1]), np.uint64)
+        goff = np.empty(n_prompts + 1, np.int64)
+        kvb._lib.check(kvb.lib.kvb_hash_token_blocks(0, tokens.ctypes.data, off.ctypes.data, parents.ctypes.data, n_prompts,
+                                                     bs, None, None, got.ctypes.data, goff.ctypes.data, None))
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), bs

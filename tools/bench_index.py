@@ -117,6 +117,35 @@ def main():
     t_hash_gpu = med(lambda: kvb._lib.check(kvb.lib.kvb_hash_token_blocks(
         0, tokens.ctypes.data, off.ctypes.data, parents.ctypes.data, N_PROMPTS, BS, None, None, keys_g.ctypes.data,
         koff_g.ctypes.data, None)))
+    # kernel alone: everything resident in HBM, CUDA events on the launching stream
+    d_tok, d_off, d_par = (torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int64)).cuda()
+                           for a in (tokens, off, parents))
+    d_koff = torch.from_numpy(koff_g).cuda()
+    d_keys = torch.empty(int(koff_g[-1]), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream()
+
+    def hash_dev():
+        kvb._lib.check(kvb.lib.kvb_hash_token_blocks_dev(0, d_tok.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), N_PROMPTS, BS,
+                                                         None, None, d_keys.data_ptr(), d_koff.data_ptr(), st.cuda_stream))
+    for _ in range(5):
+        hash_dev()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record(st)
+        hash_dev()
+        b.record(st)
+    torch.cuda.synchronize()
+    t_hash_kernel = float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
+    assert np.array_equal(d_keys.cpu().numpy().view(np.uint64), keys_c), "device-resident hash differs from the oracle"
+    # latency floor of the serial chain: every CBOR byte of a prompt's chain is one dependent
+    # xor -> 64-bit multiply, 12.3 cycles per byte on a lone in-order warp (profiles/r01_hash_phase_profile.txt); all
+    # chains run concurrently, so the floor is the LONGEST chain's byte count * 12.3 / f_sm
+    full = tokens.reshape(N_PROMPTS, N_TOK)[:, : (N_TOK // BS) * BS]
+    width = np.where(full < 24, 1, np.where(full < 256, 2, np.where(full < 65536, 3, 5)))
+    chain_bytes = width.sum(axis=1) + (N_TOK // BS) * (1 + 9 + 1 + 1)        # 0x83, uint64 parent, array head, null extra
+    sm_hz = 1.965e9
+    chain_floor = float(chain_bytes.max()) * 12.3 / sm_hz
     cores = os.cpu_count() or 1
     # CPU baseline = the BEST thread count for each phase (OpenMP team start-up dominates a 0.1 ms job at 128 threads)
     sweep = [t for t in (1, 4, 8, 16, 32, 64, 128, 256) if t <= cores]
@@ -133,6 +162,11 @@ def main():
         "gpu_fused_tokens_to_scores_ms": t_fused * 1e3, "gpu_prompts_per_s": N_PROMPTS / t_fused,
         "gpu_keys_per_s": total_keys / t_fused, "gpu_kernels_per_call": int(launches),
         "gpu_hash_only_host_to_host_ms": t_hash_gpu * 1e3,
+        "hash_kernel": {"device_resident_us": t_hash_kernel * 1e6, "keys_per_s": total_keys / t_hash_kernel,
+                        "bound": "latency (serial FNV chain, one lane per prompt)",
+                        "longest_chain_cbor_bytes": int(chain_bytes.max()), "cycles_per_byte_floor": 12.3, "sm_hz": sm_hz,
+                        "floor_us": chain_floor * 1e6, "frac_of_floor": chain_floor / t_hash_kernel,
+                        "hbm_bytes": int(tokens.nbytes + total_keys * 8)},
         "gpu_fused_pinned_tokens_ms": t_fused_pinned * 1e3, "gpu_prompts_per_s_pinned": N_PROMPTS / t_fused_pinned,
         "gpu_fused_8192_prompts_pinned_ms": t_fused8 * 1e3, "gpu_prompts_per_s_8192": N_PROMPTS * reps / t_fused8,
         "gpu_keys_per_s_8192": total_keys * reps / t_fused8,
