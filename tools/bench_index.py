@@ -138,14 +138,18 @@ def main():
     torch.cuda.synchronize()
     t_hash_kernel = float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e-3
     assert np.array_equal(d_keys.cpu().numpy().view(np.uint64), keys_c), "device-resident hash differs from the oracle"
-    # latency floor of the serial chain: every CBOR byte of a prompt's chain is one dependent
-    # xor -> 64-bit multiply, 12.3 cycles per byte on a lone in-order warp (profiles/r01_hash_phase_profile.txt); all
-    # chains run concurrently, so the floor is the LONGEST chain's byte count * 12.3 / f_sm
+    # latency floors, all chains concurrent so the LONGEST chain bounds the launch:
+    #  - byte-serial formulation (lane per prompt): one dependent xor -> 64-bit multiply per CBOR byte, 12.3 cycles per
+    #    byte on a lone in-order warp (profiles/r01_hash_phase_profile.txt)
+    #  - vote-round formulation (warp per prompt, the kernel used for <= 1536 prompts): per block 8 rounds of
+    #    IMAD -> LOP3 -> LOP3.P -> VOTE -> LOP3 -> POPC -> SHL -> LOP3 (61 cycles) + 4x REDUX and recombine (80) + the
+    #    64-bit multiply (15)  (profiles/r01_warp_chain_latency.txt)
     full = tokens.reshape(N_PROMPTS, N_TOK)[:, : (N_TOK // BS) * BS]
     width = np.where(full < 24, 1, np.where(full < 256, 2, np.where(full < 65536, 3, 5)))
     chain_bytes = width.sum(axis=1) + (N_TOK // BS) * (1 + 9 + 1 + 1)        # 0x83, uint64 parent, array head, null extra
     sm_hz = 1.965e9
-    chain_floor = float(chain_bytes.max()) * 12.3 / sm_hz
+    byte_floor = float(chain_bytes.max()) * 12.3 / sm_hz
+    vote_floor = (N_TOK // BS) * (8 * 61 + 80 + 15) / sm_hz
     cores = os.cpu_count() or 1
     # CPU baseline = the BEST thread count for each phase (OpenMP team start-up dominates a 0.1 ms job at 128 threads)
     sweep = [t for t in (1, 4, 8, 16, 32, 64, 128, 256) if t <= cores]
@@ -163,9 +167,13 @@ def main():
         "gpu_keys_per_s": total_keys / t_fused, "gpu_kernels_per_call": int(launches),
         "gpu_hash_only_host_to_host_ms": t_hash_gpu * 1e3,
         "hash_kernel": {"device_resident_us": t_hash_kernel * 1e6, "keys_per_s": total_keys / t_hash_kernel,
-                        "bound": "latency (serial FNV chain, one lane per prompt)",
-                        "longest_chain_cbor_bytes": int(chain_bytes.max()), "cycles_per_byte_floor": 12.3, "sm_hz": sm_hz,
-                        "floor_us": chain_floor * 1e6, "frac_of_floor": chain_floor / t_hash_kernel,
+                        "kernel": "hash_chain_kernel_wpc (warp per prompt)" if N_PROMPTS <= 1536 and not os.environ.get("KVB_HASH_KERNEL")
+                        else "hash_chain_kernel_2w (lane per prompt)",
+                        "bound": "latency of dependent warp instructions, not HBM", "sm_hz": sm_hz,
+                        "longest_chain_cbor_bytes": int(chain_bytes.max()),
+                        "floor_us": {"byte_serial_12.3_cycles_per_byte": byte_floor * 1e6,
+                                     "vote_rounds_583_cycles_per_block": vote_floor * 1e6},
+                        "frac_of_vote_round_floor": vote_floor / t_hash_kernel,
                         "hbm_bytes": int(tokens.nbytes + total_keys * 8)},
         "gpu_fused_pinned_tokens_ms": t_fused_pinned * 1e3, "gpu_prompts_per_s_pinned": N_PROMPTS / t_fused_pinned,
         "gpu_fused_8192_prompts_pinned_ms": t_fused8 * 1e3, "gpu_prompts_per_s_8192": N_PROMPTS * reps / t_fused8,
