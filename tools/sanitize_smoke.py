@@ -48,13 +48,18 @@ while not eng.get_finished():
     pass
 eng.shutdown()
 rng = np.random.default_rng(0)
-for bs in (4, 16, 17, 64):
+for family, bs in [(f, b) for f in ("", "lanes") for b in (4, 16, 17, 64)]:  # warp-per-prompt and lane-per-prompt kernels
+    if family:
+        os.environ["KVB_HASH_KERNEL"] = family
+    else:
+        os.environ.pop("KVB_HASH_KERNEL", None)
     tp, otp = K.ChunkedTokenDatabase(bs, "s"), ko.TokenProcessor(bs, "s")
     prompts = [rng.integers(0, 1 << int(rng.choice([5, 8, 16, 17, 32])), int(rng.integers(0, 5 * bs + 3)), dtype=np.uint64).astype(np.uint32)
                for _ in range(70)]
     keys, off = tp.tokens_to_kv_block_keys_batch(prompts, "m")
     for i, p in enumerate(prompts):
         assert [int(k) for k in keys[off[i]:off[i + 1]]] == (otp.tokens_to_kv_block_keys(0, [int(x) for x in p], "m") or [])
+os.environ.pop("KVB_HASH_KERNEL", None)
 idx = K.Index(expected_keys=64)
 tp, otp = K.ChunkedTokenDatabase(16, ""), ko.TokenProcessor(16, "")
 prompts = [rng.integers(0, 128256, int(rng.integers(0, 700))).astype(np.uint32) for _ in range(40)]
