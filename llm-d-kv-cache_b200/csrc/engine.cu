@@ -105,12 +105,12 @@ class Arena {
     auto it = entries.find(k);
     return it != entries.end() && it->second.valid;
   }
-  void clear() {
+  void clear() {  // drops every entry that is not pinned by an in-flight store or load
     std::lock_guard<std::mutex> lk(mu);
-    entries.clear();
-    lru.clear();
-    free_.clear();
-    free_[0] = cap;
+    for (auto it = entries.begin(); it != entries.end();) {
+      auto cur = it++;
+      if (cur->second.pins == 0) erase_locked(cur);
+    }
   }
   // reserve space for a new entry (pinned for writing); evicts unpinned LRU entries when full.
   // returns nullptr if the key exists already (*existed=true) or no space can be made.
@@ -246,7 +246,8 @@ static std::vector<int> cpus_of_node(int node) {
   char buf[4096] = {0};
   if (!fgets(buf, sizeof(buf), f)) buf[0] = 0;
   fclose(f);
-  for (char* tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+  char* save = nullptr;
+  for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-31,64-95"
     int a = 0, b = 0;
     if (sscanf(tok, "%d-%d", &a, &b) == 2) {
       for (int c = a; c <= b; ++c) cpus.push_back(c);
@@ -400,6 +401,7 @@ struct kvb_engine {
   }
 
   bool worker_init(Worker& w);
+  void worker_release(Worker& w);
   void worker_loop(Worker* w);
   bool run_store(Worker& w, ChunkTask& t);
   bool run_load(Worker& w, ChunkTask& t);
@@ -635,7 +637,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
 
 void kvb_engine::worker_loop(Worker* w) {
   bind_this_thread(local_cpus);
-  bool inited = false;
+  bool inited = false, init_failed = false;
   for (;;) {
     std::unique_ptr<ChunkTask> task;
     {
@@ -649,10 +651,14 @@ void kvb_engine::worker_loop(Worker* w) {
       q.pop_front();
       if (q_high.empty() && q_normal.empty() && opts.tier == KVB_TIER_FILE) task->io_parts = 4;
     }
-    if (!inited) {
+    if (!inited && !init_failed) {
       inited = worker_init(*w);
-      if (!inited) set_error("engine worker: CUDA resource allocation failed");
+      if (!inited) {  // one attempt: release what was allocated, every task of this worker fails from now on
+        init_failed = true;
+        worker_release(*w);
+      }
     }
+    if (init_failed) set_error("engine worker: CUDA resource allocation failed");
     bool ok = false;
     if (inited) {
       try {
@@ -674,15 +680,21 @@ void kvb_engine::worker_loop(Worker* w) {
     }
     task_done(task->job, ok);
   }
-  if (w->stream) {
-    cudaSetDevice(device);
-    cudaStreamSynchronize(w->stream);
-    if (w->d_packed) cudaFree(w->d_packed);
-    if (w->d_ids) cudaFree(w->d_ids);
-    if (w->h_ids) cudaFreeHost(w->h_ids);
-    if (w->h_stage) cudaFreeHost(w->h_stage);
-    cudaStreamDestroy(w->stream);
-  }
+  worker_release(*w);
+}
+
+void kvb_engine::worker_release(Worker& w) {
+  cudaSetDevice(device);
+  if (w.stream) cudaStreamSynchronize(w.stream);
+  if (w.d_packed) cudaFree(w.d_packed);
+  if (w.d_ids) cudaFree(w.d_ids);
+  if (w.h_ids) cudaFreeHost(w.h_ids);
+  if (w.h_stage) cudaFreeHost(w.h_stage);
+  if (w.stream) cudaStreamDestroy(w.stream);
+  w.d_packed = w.h_stage = nullptr;
+  w.d_ids = w.h_ids = nullptr;
+  w.stream = nullptr;
+  cudaGetLastError();
 }
 
 int kvb_engine::submit(int64_t job_id, int32_t n_files, const char* const* files, const int64_t* ids,
@@ -706,8 +718,8 @@ int kvb_engine::submit(int64_t job_id, int32_t n_files, const char* const* files
   {
     DeviceGuard g(device);
     KVB_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    KVB_CUDA_TRY(cudaEventRecord(ev, static_cast<cudaStream_t>(caller_stream)));
     ev_owner = std::shared_ptr<void>(ev, [](void* e) { cudaEventDestroy(static_cast<cudaEvent_t>(e)); });
+    KVB_CUDA_TRY(cudaEventRecord(ev, static_cast<cudaStream_t>(caller_stream)));
   }
 
   std::vector<std::unique_ptr<ChunkTask>> tasks;
@@ -772,57 +784,59 @@ void kvb_engine_default_opts(kvb_engine_opts_t* o) {
 }
 
 int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engine_t** out) {
-  KVB_REQUIRE(out != nullptr, "out is NULL");
-  *out = nullptr;
-  KVB_REQUIRE(pool != nullptr && opts != nullptr, "NULL argument");
-  KVB_REQUIRE(opts->gpu_blocks_per_file > 0, "gpu_blocks_per_file must be > 0");  // tensor_copier.cu:35-36
-  KVB_REQUIRE(opts->io_threads > 0 && opts->io_threads <= 256, "io_threads out of range");
-  KVB_REQUIRE(opts->tier == KVB_TIER_FILE || opts->tier == KVB_TIER_HOST_ARENA, "unknown tier %d", opts->tier);
-  std::unique_ptr<kvb_engine> e(new kvb_engine());
-  e->pool = pool;
-  e->opts = *opts;
-  e->device = pool->device;
-  e->block_bytes = pool->frag_bytes * pool->num_tensors;
-  int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : (64ll << 20);
-  int64_t bpc = chunk / e->block_bytes;
-  if (bpc < opts->gpu_blocks_per_file) bpc = opts->gpu_blocks_per_file;  // a chunk always holds whole files
-  e->blocks_per_chunk = bpc;
-  e->file_bytes = std::max<int64_t>((int64_t)opts->gpu_blocks_per_file * e->block_bytes, kMinFileBytes);
-  e->tmp_suffix = "_" + std::to_string((long long)::getpid()) + "_" +
-                  std::to_string((unsigned long long)(uintptr_t)e.get() & 0xffffff) + ".tmp";
-  DeviceGuard g(e->device);
-  if (!g.ok) {
-    set_error("cannot select CUDA device %d", e->device);
-    return KVB_ERR_CUDA;
-  }
-  if (!std::getenv("KVB_NO_NUMA_BIND")) e->local_cpus = cpus_of_node(gpu_numa_node(e->device));
-  if (opts->tier == KVB_TIER_HOST_ARENA) {
-    KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
-    // allocate (and thereby first-touch / pin) the arena from a thread bound to the GPU-local node, without
-    // disturbing the caller's own affinity
-    int rc = KVB_OK;
-    std::string err;
-    std::thread t([&] {
-      bind_this_thread(e->local_cpus);
-      cudaSetDevice(e->device);
-      rc = e->arena.init(opts->host_arena_bytes);
-      if (rc) err = get_error();
-    });
-    t.join();
-    if (rc) {
-      set_error("%s", err.c_str());
-      return rc;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    KVB_REQUIRE(pool != nullptr && opts != nullptr, "NULL argument");
+    KVB_REQUIRE(opts->gpu_blocks_per_file > 0, "gpu_blocks_per_file must be > 0");  // tensor_copier.cu:35-36
+    KVB_REQUIRE(opts->io_threads > 0 && opts->io_threads <= 256, "io_threads out of range");
+    KVB_REQUIRE(opts->tier == KVB_TIER_FILE || opts->tier == KVB_TIER_HOST_ARENA, "unknown tier %d", opts->tier);
+    std::unique_ptr<kvb_engine> e(new kvb_engine());
+    e->pool = pool;
+    e->opts = *opts;
+    e->device = pool->device;
+    e->block_bytes = pool->frag_bytes * pool->num_tensors;
+    int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : (64ll << 20);
+    int64_t bpc = chunk / e->block_bytes;
+    if (bpc < opts->gpu_blocks_per_file) bpc = opts->gpu_blocks_per_file;  // a chunk always holds whole files
+    e->blocks_per_chunk = bpc;
+    e->file_bytes = std::max<int64_t>((int64_t)opts->gpu_blocks_per_file * e->block_bytes, kMinFileBytes);
+    e->tmp_suffix = "_" + std::to_string((long long)::getpid()) + "_" +
+                    std::to_string((unsigned long long)(uintptr_t)e.get() & 0xffffff) + ".tmp";
+    DeviceGuard g(e->device);
+    if (!g.ok) {
+      set_error("cannot select CUDA device %d", e->device);
+      return KVB_ERR_CUDA;
     }
-  }
-  const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);
-  for (int i = 0; i < opts->io_threads; ++i) {
-    auto w = std::make_unique<kvb_engine::Worker>();
-    w->high_first = i < n_high;  // thread_pool.cpp:52-57
-    e->workers.push_back(std::move(w));
-  }
-  for (auto& w : e->workers) w->th = std::thread([eng = e.get(), wp = w.get()] { eng->worker_loop(wp); });
-  *out = e.release();
-  return KVB_OK;
+    if (!std::getenv("KVB_NO_NUMA_BIND")) e->local_cpus = cpus_of_node(gpu_numa_node(e->device));
+    if (opts->tier == KVB_TIER_HOST_ARENA) {
+      KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
+      // allocate (and thereby first-touch / pin) the arena from a thread bound to the GPU-local node, without
+      // disturbing the caller's own affinity
+      int rc = KVB_OK;
+      std::string err;
+      std::thread t([&] {
+        bind_this_thread(e->local_cpus);
+        cudaSetDevice(e->device);
+        rc = e->arena.init(opts->host_arena_bytes);
+        if (rc) err = get_error();
+      });
+      t.join();
+      if (rc) {
+        set_error("%s", err.c_str());
+        return rc;
+      }
+    }
+    const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);
+    for (int i = 0; i < opts->io_threads; ++i) {
+      auto w = std::make_unique<kvb_engine::Worker>();
+      w->high_first = i < n_high;  // thread_pool.cpp:52-57
+      e->workers.push_back(std::move(w));
+    }
+    for (auto& w : e->workers) w->th = std::thread([eng = e.get(), wp = w.get()] { eng->worker_loop(wp); });
+    *out = e.release();
+    return KVB_OK;
+  });
 }
 
 void kvb_engine_destroy(kvb_engine_t* e) {
@@ -840,73 +854,87 @@ void kvb_engine_destroy(kvb_engine_t* e) {
 
 int kvb_engine_store(kvb_engine_t* e, int64_t job_id, int32_t n_files, const char* const* files,
                      const int64_t* block_ids, const int64_t* file_off, void* caller_stream) {
-  KVB_REQUIRE(e != nullptr, "engine is NULL");
-  return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, true);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e != nullptr, "engine is NULL");
+    return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, true);
+  });
 }
 int kvb_engine_load(kvb_engine_t* e, int64_t job_id, int32_t n_files, const char* const* files,
                     const int64_t* block_ids, const int64_t* file_off, void* caller_stream) {
-  KVB_REQUIRE(e != nullptr, "engine is NULL");
-  return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, false);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e != nullptr, "engine is NULL");
+    return e->submit(job_id, n_files, files, block_ids, file_off, caller_stream, false);
+  });
 }
 
 int kvb_engine_poll(kvb_engine_t* e, int64_t* job_ids, int32_t* ok, int32_t cap) {
-  KVB_REQUIRE(e != nullptr, "engine is NULL");
-  KVB_REQUIRE(cap >= 0 && (cap == 0 || (job_ids && ok)), "bad output buffers");
-  std::lock_guard<std::mutex> lk(e->jmu);
-  int n = 0;
-  for (auto it = e->jobs.begin(); it != e->jobs.end() && n < cap;) {
-    if (it->second->completed.load() == it->second->total) {  // storage_offload.cpp:196-201
-      job_ids[n] = it->first;
-      ok[n] = it->second->ok.load() ? 1 : 0;
-      ++n;
-      it = e->jobs.erase(it);
-    } else {
-      ++it;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e != nullptr, "engine is NULL");
+    KVB_REQUIRE(cap >= 0 && (cap == 0 || (job_ids && ok)), "bad output buffers");
+    std::lock_guard<std::mutex> lk(e->jmu);
+    int n = 0;
+    for (auto it = e->jobs.begin(); it != e->jobs.end() && n < cap;) {
+      if (it->second->completed.load() == it->second->total) {  // storage_offload.cpp:196-201
+        job_ids[n] = it->first;
+        ok[n] = it->second->ok.load() ? 1 : 0;
+        ++n;
+        it = e->jobs.erase(it);
+      } else {
+        ++it;
+      }
     }
-  }
-  return n;
+    return n;
+  });
 }
 
 int kvb_engine_wait(kvb_engine_t* e, int64_t job_id) {
-  KVB_REQUIRE(e != nullptr, "engine is NULL");
-  std::shared_ptr<JobState> job;
-  {
-    std::lock_guard<std::mutex> lk(e->jmu);
-    auto it = e->jobs.find(job_id);
-    if (it == e->jobs.end()) return KVB_OK;  // storage_offload.cpp:221: unknown job returns
-    job = it->second;
-  }
-  job->cancelled = true;  // queued tasks bail early (storage_offload.cpp:226-229)
-  std::unique_lock<std::mutex> lk(e->jmu);
-  e->jcv.wait(lk, [&] { return job->completed.load() == job->total; });
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e != nullptr, "engine is NULL");
+    std::shared_ptr<JobState> job;
+    {
+      std::lock_guard<std::mutex> lk(e->jmu);
+      auto it = e->jobs.find(job_id);
+      if (it == e->jobs.end()) return KVB_OK;  // storage_offload.cpp:221: unknown job returns
+      job = it->second;
+    }
+    job->cancelled = true;  // queued tasks bail early (storage_offload.cpp:226-229)
+    std::unique_lock<std::mutex> lk(e->jmu);
+    e->jcv.wait(lk, [&] { return job->completed.load() == job->total; });
+    return KVB_OK;
+  });
 }
 
 int kvb_engine_exists(kvb_engine_t* e, const char* file) {
-  if (!e || !file) return 0;
-  if (e->opts.tier == KVB_TIER_HOST_ARENA) return e->arena.exists(file) ? 1 : 0;
-  return file_exists(file) ? 1 : 0;
+  return kvb::guarded([&]() -> int {
+    if (!e || !file) return 0;
+    if (e->opts.tier == KVB_TIER_HOST_ARENA) return e->arena.exists(file) ? 1 : 0;
+    return file_exists(file) ? 1 : 0;
+  });
 }
 
 int kvb_engine_arena_clear(kvb_engine_t* e) {
-  KVB_REQUIRE(e != nullptr, "engine is NULL");
-  if (e->opts.tier == KVB_TIER_HOST_ARENA) e->arena.clear();
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e != nullptr, "engine is NULL");
+    if (e->opts.tier == KVB_TIER_HOST_ARENA) e->arena.clear();
+    return KVB_OK;
+  });
 }
 
 int kvb_engine_get_stats(kvb_engine_t* e, kvb_engine_stats_t* s) {
-  KVB_REQUIRE(e && s, "NULL argument");
-  s->bytes_stored = e->bytes_stored;
-  s->bytes_loaded = e->bytes_loaded;
-  s->files_stored = e->files_stored;
-  s->files_loaded = e->files_loaded;
-  s->files_skipped_existing = e->files_skipped;
-  s->writes_dropped = e->writes_dropped;
-  s->load_failures = e->load_failures;
-  s->kernels_launched = e->kernels;
-  s->h2d_bytes = e->h2d;
-  s->d2h_bytes = e->d2h;
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e && s, "NULL argument");
+    s->bytes_stored = e->bytes_stored;
+    s->bytes_loaded = e->bytes_loaded;
+    s->files_stored = e->files_stored;
+    s->files_loaded = e->files_loaded;
+    s->files_skipped_existing = e->files_skipped;
+    s->writes_dropped = e->writes_dropped;
+    s->load_failures = e->load_failures;
+    s->kernels_launched = e->kernels;
+    s->h2d_bytes = e->h2d;
+    s->d2h_bytes = e->d2h;
+    return KVB_OK;
+  });
 }
 
 }  // extern "C"

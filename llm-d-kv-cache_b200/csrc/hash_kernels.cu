@@ -734,106 +734,112 @@ uint64_t kvb_fnv64a(const void* data, size_t len) {
 }
 
 int kvb_init_hash(int device, uint64_t seed_hash, const char* model_name, size_t model_len, uint64_t* out) {
-  KVB_REQUIRE(out != nullptr, "out is NULL");
-  KVB_REQUIRE(model_name != nullptr || model_len == 0, "model_name is NULL");
-  KVB_REQUIRE(model_len < (1u << 31), "model name too long");
-  DeviceGuard g(device);
-  if (!g.ok) {
-    set_error("cannot select CUDA device %d", device);
-    return KVB_ERR_CUDA;
-  }
-  uint8_t* d = nullptr;
-  KVB_CUDA_TRY(cudaMalloc(&d, model_len + 8 + 8));
-  uint64_t* d_out = reinterpret_cast<uint64_t*>(d);
-  uint8_t* d_name = d + 8;
-  cudaError_t e = cudaSuccess;
-  if (model_len) e = cudaMemcpy(d_name, model_name, model_len, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    init_hash_kernel<<<1, 32>>>(seed_hash, d_name, (uint32_t)model_len, d_out);
-    count_launch();
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 8, cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  KVB_CUDA_TRY(e);
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(out != nullptr, "out is NULL");
+    KVB_REQUIRE(model_name != nullptr || model_len == 0, "model_name is NULL");
+    KVB_REQUIRE(model_len < (1u << 31), "model name too long");
+    DeviceGuard g(device);
+    if (!g.ok) {
+      set_error("cannot select CUDA device %d", device);
+      return KVB_ERR_CUDA;
+    }
+    uint8_t* d = nullptr;
+    KVB_CUDA_TRY(cudaMalloc(&d, model_len + 8 + 8));
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(d);
+    uint8_t* d_name = d + 8;
+    cudaError_t e = cudaSuccess;
+    if (model_len) e = cudaMemcpy(d_name, model_name, model_len, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      init_hash_kernel<<<1, 32>>>(seed_hash, d_name, (uint32_t)model_len, d_out);
+      count_launch();
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    KVB_CUDA_TRY(e);
+    return KVB_OK;
+  });
 }
 
 int kvb_hash_token_blocks_dev(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
                               int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
                               uint64_t* out_keys, const int64_t* key_off, void* stream) {
-  KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);  // token_processor.go:86-88
-  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
-  if (n_prompts == 0) return KVB_OK;
-  KVB_REQUIRE(tokens && prompt_off && parents && out_keys && key_off, "NULL argument");
-  DeviceGuard g(device);
-  return launch_hash_blocks(tokens, prompt_off, parents, n_prompts, block_size, extra, extra_off, out_keys, key_off,
-                            static_cast<cudaStream_t>(stream));
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);  // token_processor.go:86-88
+    KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+    if (n_prompts == 0) return KVB_OK;
+    KVB_REQUIRE(tokens && prompt_off && parents && out_keys && key_off, "NULL argument");
+    DeviceGuard g(device);
+    return launch_hash_blocks(tokens, prompt_off, parents, n_prompts, block_size, extra, extra_off, out_keys, key_off,
+                              static_cast<cudaStream_t>(stream));
+  });
 }
 
 int kvb_hash_token_blocks(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
                           int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
                           uint64_t* out_keys, int64_t* out_key_off, void* stream) {
-  KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
-  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
-  KVB_REQUIRE(out_key_off != nullptr, "out_key_off is NULL");
-  out_key_off[0] = 0;
-  if (n_prompts == 0) return KVB_OK;
-  KVB_REQUIRE(prompt_off && parents, "NULL argument");
-  for (int32_t p = 0; p < n_prompts; ++p) {
-    KVB_REQUIRE(prompt_off[p + 1] >= prompt_off[p], "prompt_off not monotonic at %d", p);
-    out_key_off[p + 1] = out_key_off[p] + (prompt_off[p + 1] - prompt_off[p]) / block_size;
-  }
-  const int64_t total_keys = out_key_off[n_prompts];
-  const int64_t total_tok = prompt_off[n_prompts] - prompt_off[0];
-  if (total_keys == 0) return KVB_OK;
-  KVB_REQUIRE(tokens && out_keys, "NULL argument");
-  DeviceGuard g(device);
-  if (!g.ok) {
-    set_error("cannot select CUDA device %d", device);
-    return KVB_ERR_CUDA;
-  }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t extra_bytes = extra_off ? extra_off[total_keys] : 0;
-  // one device scratch: [tokens | prompt_off | key_off | parents | keys | extra_off | extra]
-  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  const size_t o_tok = 0;
-  const size_t o_poff = o_tok + al(total_tok * 4);
-  const size_t o_koff = o_poff + al((n_prompts + 1) * 8);
-  const size_t o_par = o_koff + al((n_prompts + 1) * 8);
-  const size_t o_keys = o_par + al(n_prompts * 8);
-  const size_t o_eoff = o_keys + al(total_keys * 8);
-  const size_t o_ext = o_eoff + (extra_off ? al((total_keys + 1) * 8) : 0);
-  const size_t total = o_ext + (extra_off ? al(extra_bytes) : 0) + 256;
-  uint8_t* d = nullptr;
-  KVB_CUDA_TRY(cudaMallocAsync(&d, total, s));
-  std::vector<int64_t> poff_rel(n_prompts + 1);
-  for (int32_t p = 0; p <= n_prompts; ++p) poff_rel[p] = prompt_off[p] - prompt_off[0];
-  cudaError_t e = cudaMemcpyAsync(d + o_tok, tokens + prompt_off[0], total_tok * 4, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(d + o_poff, poff_rel.data(), (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_koff, out_key_off, (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_par, parents, n_prompts * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess && extra_off) {
-    e = cudaMemcpyAsync(d + o_eoff, extra_off, (total_keys + 1) * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && extra_bytes)
-      e = cudaMemcpyAsync(d + o_ext, extra, extra_bytes, cudaMemcpyHostToDevice, s);
-  }
-  int rc = KVB_OK;
-  if (e == cudaSuccess) {
-    rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(d + o_tok), reinterpret_cast<int64_t*>(d + o_poff),
-                            reinterpret_cast<uint64_t*>(d + o_par), n_prompts, block_size,
-                            extra_off ? d + o_ext : nullptr,
-                            extra_off ? reinterpret_cast<int64_t*>(d + o_eoff) : nullptr,
-                            reinterpret_cast<uint64_t*>(d + o_keys), reinterpret_cast<int64_t*>(d + o_koff), s);
-    if (rc == KVB_OK) e = cudaMemcpyAsync(out_keys, d + o_keys, total_keys * 8, cudaMemcpyDeviceToHost, s);
-  }
-  cudaError_t e2 = cudaStreamSynchronize(s);  // poff_rel and the caller's buffers must outlive the copies
-  cudaFreeAsync(d, s);
-  if (rc != KVB_OK) return rc;
-  KVB_CUDA_TRY(e);
-  KVB_CUDA_TRY(e2);
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
+    KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+    KVB_REQUIRE(out_key_off != nullptr, "out_key_off is NULL");
+    out_key_off[0] = 0;
+    if (n_prompts == 0) return KVB_OK;
+    KVB_REQUIRE(prompt_off && parents, "NULL argument");
+    for (int32_t p = 0; p < n_prompts; ++p) {
+      KVB_REQUIRE(prompt_off[p + 1] >= prompt_off[p], "prompt_off not monotonic at %d", p);
+      out_key_off[p + 1] = out_key_off[p] + (prompt_off[p + 1] - prompt_off[p]) / block_size;
+    }
+    const int64_t total_keys = out_key_off[n_prompts];
+    const int64_t total_tok = prompt_off[n_prompts] - prompt_off[0];
+    if (total_keys == 0) return KVB_OK;
+    KVB_REQUIRE(tokens && out_keys, "NULL argument");
+    DeviceGuard g(device);
+    if (!g.ok) {
+      set_error("cannot select CUDA device %d", device);
+      return KVB_ERR_CUDA;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t extra_bytes = extra_off ? extra_off[total_keys] : 0;
+    // one device scratch: [tokens | prompt_off | key_off | parents | keys | extra_off | extra]
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_tok = 0;
+    const size_t o_poff = o_tok + al(total_tok * 4);
+    const size_t o_koff = o_poff + al((n_prompts + 1) * 8);
+    const size_t o_par = o_koff + al((n_prompts + 1) * 8);
+    const size_t o_keys = o_par + al(n_prompts * 8);
+    const size_t o_eoff = o_keys + al(total_keys * 8);
+    const size_t o_ext = o_eoff + (extra_off ? al((total_keys + 1) * 8) : 0);
+    const size_t total = o_ext + (extra_off ? al(extra_bytes) : 0) + 256;
+    uint8_t* d = nullptr;
+    KVB_CUDA_TRY(cudaMallocAsync(&d, total, s));
+    std::vector<int64_t> poff_rel(n_prompts + 1);
+    for (int32_t p = 0; p <= n_prompts; ++p) poff_rel[p] = prompt_off[p] - prompt_off[0];
+    cudaError_t e = cudaMemcpyAsync(d + o_tok, tokens + prompt_off[0], total_tok * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d + o_poff, poff_rel.data(), (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_koff, out_key_off, (n_prompts + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_par, parents, n_prompts * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && extra_off) {
+      e = cudaMemcpyAsync(d + o_eoff, extra_off, (total_keys + 1) * 8, cudaMemcpyHostToDevice, s);
+      if (e == cudaSuccess && extra_bytes)
+        e = cudaMemcpyAsync(d + o_ext, extra, extra_bytes, cudaMemcpyHostToDevice, s);
+    }
+    int rc = KVB_OK;
+    if (e == cudaSuccess) {
+      rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(d + o_tok), reinterpret_cast<int64_t*>(d + o_poff),
+                              reinterpret_cast<uint64_t*>(d + o_par), n_prompts, block_size,
+                              extra_off ? d + o_ext : nullptr,
+                              extra_off ? reinterpret_cast<int64_t*>(d + o_eoff) : nullptr,
+                              reinterpret_cast<uint64_t*>(d + o_keys), reinterpret_cast<int64_t*>(d + o_koff), s);
+      if (rc == KVB_OK) e = cudaMemcpyAsync(out_keys, d + o_keys, total_keys * 8, cudaMemcpyDeviceToHost, s);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s);  // poff_rel and the caller's buffers must outlive the copies
+    cudaFreeAsync(d, s);
+    if (rc != KVB_OK) return rc;
+    KVB_CUDA_TRY(e);
+    KVB_CUDA_TRY(e2);
+    return KVB_OK;
+  });
 }
 
 }  // extern "C"

@@ -288,6 +288,7 @@ struct kvb_index {
   Bucket* table = nullptr;
   uint64_t slots = 0;
   int64_t dev_live = 0, dev_tomb = 0;
+  bool stale_mirror = false;  // the device table misses host entries (a rebuild failed after the swap)
   double tier_w_host[256];
   double* tier_w = nullptr;
   cudaStream_t stream = nullptr;
@@ -302,6 +303,7 @@ struct kvb_index {
     if (dev_bytes > d_scratch_cap) {
       if (d_scratch) cudaFree(d_scratch);
       d_scratch = nullptr;
+      d_scratch_cap = 0;  // a failed allocation below must not leave a stale capacity behind
       size_t cap = std::max<size_t>(dev_bytes, 1 << 20);
       cap = (cap * 3 / 2 + 255) & ~size_t(255);
       KVB_CUDA_TRY(cudaMalloc(&d_scratch, cap));
@@ -310,6 +312,7 @@ struct kvb_index {
     if (host_bytes > h_scratch_cap) {
       if (h_scratch) cudaFreeHost(h_scratch);
       h_scratch = nullptr;
+      h_scratch_cap = 0;
       size_t cap = std::max<size_t>(host_bytes, 1 << 20);
       cap = (cap * 3 / 2 + 255) & ~size_t(255);
       KVB_CUDA_TRY(cudaHostAlloc(&h_scratch, cap, cudaHostAllocDefault));
@@ -394,13 +397,23 @@ static int apply_ops(kvb_index* idx, const std::vector<Op>& ops) {
 }
 
 int kvb_index::rebuild(uint64_t new_slots) {
+  // the new table is allocated BEFORE the old one goes: a failed allocation leaves the mirror as it was (stale but
+  // consistent; dirty keys stay queued), a failure while refilling leaves stale_mirror set so the next flush retries
+  Bucket* fresh = nullptr;
+  KVB_CUDA_TRY(cudaMalloc(&fresh, new_slots * sizeof(Bucket)));
+  cudaError_t e = cudaMemsetAsync(fresh, 0, new_slots * sizeof(Bucket), stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) {
+    cudaFree(fresh);
+    set_error("index rebuild: %s", cudaGetErrorString(e));
+    return KVB_ERR_CUDA;
+  }
   if (table) cudaFree(table);
-  table = nullptr;
-  KVB_CUDA_TRY(cudaMalloc(&table, new_slots * sizeof(Bucket)));
-  KVB_CUDA_TRY(cudaMemsetAsync(table, 0, new_slots * sizeof(Bucket), stream));
+  table = fresh;
   slots = new_slots;
   dev_live = 0;
   dev_tomb = 0;
+  stale_mirror = true;
   std::vector<Op> ops;
   const size_t batch = 1 << 20;
   ops.reserve(std::min(batch, data.size()));
@@ -418,10 +431,12 @@ int kvb_index::rebuild(uint64_t new_slots) {
   if (rc) return rc;
   dev_live = (int64_t)data.size();
   dirty.clear();
+  stale_mirror = false;
   return KVB_OK;
 }
 
 int kvb_index::flush_locked() {
+  if (stale_mirror) return rebuild(slots);  // an earlier rebuild stopped half-way
   if (dirty.empty()) return KVB_OK;
   std::sort(dirty.begin(), dirty.end());
   dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
@@ -459,37 +474,40 @@ int kvb_index::flush_locked() {
 extern "C" {
 
 int kvb_index_create(int device, int64_t max_keys, int32_t pods_per_key, int64_t expected_keys, kvb_index_t** out) {
-  KVB_REQUIRE(out != nullptr, "out is NULL");
-  *out = nullptr;
-  KVB_REQUIRE(max_keys > 0, "must provide a positive size");  // golang-lru New()
-  KVB_REQUIRE(pods_per_key > 0, "must provide a positive size");
-  if (pods_per_key > kMaxEnt) {
-    set_error("podCacheSize %d exceeds the %d entries of a device bucket", pods_per_key, kMaxEnt);
-    return KVB_ERR_UNSUPPORTED;
-  }
-  DeviceGuard g(device);
-  if (!g.ok) {
-    set_error("cannot select CUDA device %d", device);
-    return KVB_ERR_CUDA;
-  }
-  std::unique_ptr<kvb_index> idx(new kvb_index());
-  idx->device = device;
-  idx->max_keys = max_keys;
-  idx->pods_per_key = pods_per_key;
-  for (int i = 0; i < 256; ++i) idx->tier_w_host[i] = 1.0;  // unknown tier -> 1.0 (kvblock_scorer.go:93-98)
-  KVB_CUDA_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
-  KVB_CUDA_TRY(cudaMalloc(&idx->tier_w, 256 * sizeof(double)));
-  KVB_CUDA_TRY(cudaMemcpy(idx->tier_w, idx->tier_w_host, 256 * sizeof(double), cudaMemcpyHostToDevice));
-  int64_t exp_keys = std::max<int64_t>(expected_keys, 1024);
-  exp_keys = std::min<int64_t>(exp_keys, max_keys);
-  uint64_t slots = 2048;
-  while (slots * 3 < (uint64_t)exp_keys * 10) slots <<= 1;  // load <= 0.3 at expected size
-  idx->slots = slots;
-  KVB_CUDA_TRY(cudaMalloc(&idx->table, slots * sizeof(Bucket)));
-  KVB_CUDA_TRY(cudaMemset(idx->table, 0, slots * sizeof(Bucket)));
-  if (expected_keys > 0) idx->data.reserve((size_t)std::min<int64_t>(expected_keys, max_keys));
-  *out = idx.release();
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    KVB_REQUIRE(max_keys > 0, "must provide a positive size");  // golang-lru New()
+    KVB_REQUIRE(pods_per_key > 0, "must provide a positive size");
+    if (pods_per_key > kMaxEnt) {
+      set_error("podCacheSize %d exceeds the %d entries of a device bucket", pods_per_key, kMaxEnt);
+      return KVB_ERR_UNSUPPORTED;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) {
+      set_error("cannot select CUDA device %d", device);
+      return KVB_ERR_CUDA;
+    }
+    // kvb_index_destroy releases whatever CUDA resources exist if a later step fails
+    std::unique_ptr<kvb_index, void (*)(kvb_index*)> idx(new kvb_index(), kvb_index_destroy);
+    idx->device = device;
+    idx->max_keys = max_keys;
+    idx->pods_per_key = pods_per_key;
+    for (int i = 0; i < 256; ++i) idx->tier_w_host[i] = 1.0;  // unknown tier -> 1.0 (kvblock_scorer.go:93-98)
+    KVB_CUDA_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+    KVB_CUDA_TRY(cudaMalloc(&idx->tier_w, 256 * sizeof(double)));
+    KVB_CUDA_TRY(cudaMemcpy(idx->tier_w, idx->tier_w_host, 256 * sizeof(double), cudaMemcpyHostToDevice));
+    int64_t exp_keys = std::max<int64_t>(expected_keys, 1024);
+    exp_keys = std::min<int64_t>(exp_keys, max_keys);
+    uint64_t slots = 2048;
+    while (slots * 3 < (uint64_t)exp_keys * 10) slots <<= 1;  // load <= 0.3 at expected size
+    idx->slots = slots;
+    KVB_CUDA_TRY(cudaMalloc(&idx->table, slots * sizeof(Bucket)));
+    KVB_CUDA_TRY(cudaMemset(idx->table, 0, slots * sizeof(Bucket)));
+    if (expected_keys > 0) idx->data.reserve((size_t)std::min<int64_t>(expected_keys, max_keys));
+    *out = idx.release();
+    return KVB_OK;
+  });
 }
 
 void kvb_index_destroy(kvb_index_t* idx) {
@@ -506,79 +524,83 @@ void kvb_index_destroy(kvb_index_t* idx) {
 }
 
 int kvb_index_set_tier_weight(kvb_index_t* idx, uint8_t tier, double weight, int known) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  std::lock_guard<std::mutex> lk(idx->mu);
-  DeviceGuard g(idx->device);
-  idx->tier_w_host[tier] = known ? weight : 1.0;
-  KVB_CUDA_TRY(cudaMemcpy(idx->tier_w + tier, &idx->tier_w_host[tier], sizeof(double), cudaMemcpyHostToDevice));
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    idx->tier_w_host[tier] = known ? weight : 1.0;
+    KVB_CUDA_TRY(cudaMemcpy(idx->tier_w + tier, &idx->tier_w_host[tier], sizeof(double), cudaMemcpyHostToDevice));
+    return KVB_OK;
+  });
 }
 
 int kvb_index_add(kvb_index_t* idx, const uint64_t* engine_keys, int64_t n_engine, int has_engine_keys,
                   const uint64_t* request_keys, int64_t n_request, const kvb_pod_entry_t* entries, int32_t n_entries) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  // in_memory.go:155-157
-  KVB_REQUIRE(n_request > 0 && n_entries > 0 && request_keys && entries,
-              "no keys or entries provided for adding to index");
-  KVB_REQUIRE(!has_engine_keys || n_engine > 0, "engineKeys is non-nil but empty");
-  std::lock_guard<std::mutex> lk(idx->mu);
-  if (has_engine_keys) {  // in_memory.go:166-177
-    const int64_t n = std::max(n_engine, n_request);
-    std::vector<uint64_t> order;
-    std::unordered_map<uint64_t, std::vector<uint64_t>> m;
-    for (int64_t i = 0; i < n; ++i) {
-      const uint64_t ek = engine_keys[i * n_engine / n];
-      const uint64_t rk = request_keys[i * n_request / n];
-      auto it = m.find(ek);
-      if (it == m.end()) {
-        order.push_back(ek);
-        m[ek].push_back(rk);
-      } else {
-        it->second.push_back(rk);
-      }
-    }
-    for (uint64_t ek : order) idx->eng_add(ek, std::move(m[ek]));
-  }
-  for (int64_t i = 0; i < n_request; ++i) {  // in_memory.go:180-221
-    const uint64_t rk = request_keys[i];
-    auto it = idx->data.find(rk);
-    if (it != idx->data.end()) {
-      idx->touch(it);
-    } else {
-      KeyNode n;
-      idx->data_lru.push_back(rk);
-      n.lru = std::prev(idx->data_lru.end());
-      it = idx->data.emplace(rk, n).first;
-      if ((int64_t)idx->data.size() > idx->max_keys) {  // outer LRU evicts the oldest key
-        const uint64_t old = idx->data_lru.front();
-        auto oit = idx->data.find(old);
-        if (oit != idx->data.end()) idx->erase_key(oit);
-      }
-    }
-    KeyNode& node = it->second;
-    for (int32_t e = 0; e < n_entries; ++e) {  // inner lru.Add
-      int at = -1;
-      for (int k = 0; k < node.count; ++k)
-        if (same_entry(node.e[k], entries[e])) {
-          at = k;
-          break;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    // in_memory.go:155-157
+    KVB_REQUIRE(n_request > 0 && n_entries > 0 && request_keys && entries,
+                "no keys or entries provided for adding to index");
+    KVB_REQUIRE(!has_engine_keys || n_engine > 0, "engineKeys is non-nil but empty");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (has_engine_keys) {  // in_memory.go:166-177
+      const int64_t n = std::max(n_engine, n_request);
+      std::vector<uint64_t> order;
+      std::unordered_map<uint64_t, std::vector<uint64_t>> m;
+      for (int64_t i = 0; i < n; ++i) {
+        const uint64_t ek = engine_keys[i * n_engine / n];
+        const uint64_t rk = request_keys[i * n_request / n];
+        auto it = m.find(ek);
+        if (it == m.end()) {
+          order.push_back(ek);
+          m[ek].push_back(rk);
+        } else {
+          it->second.push_back(rk);
         }
-      kvb_pod_entry_t v = entries[e];
-      v.speculative = v.speculative ? 1 : 0;
-      if (at >= 0) {  // move to newest
-        for (int k = at; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
-        node.e[node.count - 1] = v;
-      } else {
-        if (node.count == idx->pods_per_key) {  // evict oldest pod entry
-          for (int k = 0; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
-          node.count--;
-        }
-        node.e[node.count++] = v;
       }
+      for (uint64_t ek : order) idx->eng_add(ek, std::move(m[ek]));
     }
-    idx->dirty.push_back(rk);
-  }
-  return KVB_OK;
+    for (int64_t i = 0; i < n_request; ++i) {  // in_memory.go:180-221
+      const uint64_t rk = request_keys[i];
+      auto it = idx->data.find(rk);
+      if (it != idx->data.end()) {
+        idx->touch(it);
+      } else {
+        KeyNode n;
+        idx->data_lru.push_back(rk);
+        n.lru = std::prev(idx->data_lru.end());
+        it = idx->data.emplace(rk, n).first;
+        if ((int64_t)idx->data.size() > idx->max_keys) {  // outer LRU evicts the oldest key
+          const uint64_t old = idx->data_lru.front();
+          auto oit = idx->data.find(old);
+          if (oit != idx->data.end()) idx->erase_key(oit);
+        }
+      }
+      KeyNode& node = it->second;
+      for (int32_t e = 0; e < n_entries; ++e) {  // inner lru.Add
+        int at = -1;
+        for (int k = 0; k < node.count; ++k)
+          if (same_entry(node.e[k], entries[e])) {
+            at = k;
+            break;
+          }
+        kvb_pod_entry_t v = entries[e];
+        v.speculative = v.speculative ? 1 : 0;
+        if (at >= 0) {  // move to newest
+          for (int k = at; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
+          node.e[node.count - 1] = v;
+        } else {
+          if (node.count == idx->pods_per_key) {  // evict oldest pod entry
+            for (int k = 0; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
+            node.count--;
+          }
+          node.e[node.count++] = v;
+        }
+      }
+      idx->dirty.push_back(rk);
+    }
+    return KVB_OK;
+  });
 }
 
 static void evict_from_request_key(kvb_index* idx, uint64_t rk, const kvb_pod_entry_t* entries, int32_t n) {
@@ -602,41 +624,45 @@ static void evict_from_request_key(kvb_index* idx, uint64_t rk, const kvb_pod_en
 }
 
 int kvb_index_evict(kvb_index_t* idx, uint64_t key, int key_type, const kvb_pod_entry_t* entries, int32_t n_entries) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  KVB_REQUIRE(n_entries > 0 && entries, "no entries provided for eviction from index");  // in_memory.go:230-232
-  std::lock_guard<std::mutex> lk(idx->mu);
-  if (key_type == KVB_KEY_ENGINE) {
-    auto it = idx->eng.find(key);
-    if (it == idx->eng.end()) return KVB_OK;  // nothing to evict (in_memory.go:238-242)
-    std::vector<uint64_t> rks = it->second.rks;
-    for (uint64_t rk : rks) evict_from_request_key(idx, rk, entries, n_entries);
-    it = idx->eng.find(key);
-    if (it != idx->eng.end()) {
-      idx->eng_lru.erase(it->second.lru);
-      idx->eng.erase(it);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    KVB_REQUIRE(n_entries > 0 && entries, "no entries provided for eviction from index");  // in_memory.go:230-232
+    std::lock_guard<std::mutex> lk(idx->mu);
+    if (key_type == KVB_KEY_ENGINE) {
+      auto it = idx->eng.find(key);
+      if (it == idx->eng.end()) return KVB_OK;  // nothing to evict (in_memory.go:238-242)
+      std::vector<uint64_t> rks = it->second.rks;
+      for (uint64_t rk : rks) evict_from_request_key(idx, rk, entries, n_entries);
+      it = idx->eng.find(key);
+      if (it != idx->eng.end()) {
+        idx->eng_lru.erase(it->second.lru);
+        idx->eng.erase(it);
+      }
+      return KVB_OK;
     }
-    return KVB_OK;
-  }
-  if (key_type == KVB_KEY_REQUEST) {
-    evict_from_request_key(idx, key, entries, n_entries);
-    return KVB_OK;
-  }
-  set_error("unknown key type: %d", key_type);  // in_memory.go:252-254
-  return KVB_ERR_INVALID;
+    if (key_type == KVB_KEY_REQUEST) {
+      evict_from_request_key(idx, key, entries, n_entries);
+      return KVB_OK;
+    }
+    set_error("unknown key type: %d", key_type);  // in_memory.go:252-254
+    return KVB_ERR_INVALID;
+  });
 }
 
 int kvb_index_get_request_key(kvb_index_t* idx, uint64_t engine_key, uint64_t* out) {
-  KVB_REQUIRE(idx && out, "NULL argument");
-  std::lock_guard<std::mutex> lk(idx->mu);
-  auto it = idx->eng.find(engine_key);
-  if (it == idx->eng.end() || it->second.rks.empty()) {  // in_memory.go:299-302
-    set_error("engine key not found: %llu", (unsigned long long)engine_key);
-    *out = 0;
-    return KVB_ERR_NOTFOUND;
-  }
-  idx->touch_eng(it);
-  *out = it->second.rks.back();
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx && out, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    auto it = idx->eng.find(engine_key);
+    if (it == idx->eng.end() || it->second.rks.empty()) {  // in_memory.go:299-302
+      set_error("engine key not found: %llu", (unsigned long long)engine_key);
+      *out = 0;
+      return KVB_ERR_NOTFOUND;
+    }
+    idx->touch_eng(it);
+    *out = it->second.rks.back();
+    return KVB_OK;
+  });
 }
 
 int64_t kvb_index_num_keys(kvb_index_t* idx) {
@@ -646,80 +672,86 @@ int64_t kvb_index_num_keys(kvb_index_t* idx) {
 }
 
 int kvb_index_host_peek(kvb_index_t* idx, uint64_t request_key, kvb_pod_entry_t* out_entries, int32_t cap) {
-  if (!idx) return -1;
-  std::lock_guard<std::mutex> lk(idx->mu);
-  auto it = idx->data.find(request_key);
-  if (it == idx->data.end()) return -1;
-  const int n = std::min<int>(it->second.count, cap);
-  for (int i = 0; i < n; ++i) out_entries[i] = it->second.e[i];
-  return it->second.count;
+  return kvb::guarded([&]() -> int {
+    if (!idx) return -1;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    auto it = idx->data.find(request_key);
+    if (it == idx->data.end()) return -1;
+    const int n = std::min<int>(it->second.count, cap);
+    for (int i = 0; i < n; ++i) out_entries[i] = it->second.e[i];
+    return it->second.count;
+  });
 }
 
 int kvb_index_flush(kvb_index_t* idx, void* stream) {
-  (void)stream;
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  std::lock_guard<std::mutex> lk(idx->mu);
-  DeviceGuard g(idx->device);
-  return idx->flush_locked();
+  return kvb::guarded([&]() -> int {
+    (void)stream;
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    return idx->flush_locked();
+  });
 }
 
 int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const uint16_t* pod_filter, int32_t n_filter,
                      int32_t* out_counts, kvb_pod_entry_t* out_entries, int64_t* out_cut) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  KVB_REQUIRE(n > 0 && keys, "no requestKeys provided for lookup");  // in_memory.go:110-112
-  KVB_REQUIRE(out_counts && out_entries && out_cut, "NULL output");
-  std::lock_guard<std::mutex> lk(idx->mu);
-  DeviceGuard g(idx->device);
-  int rc = idx->flush_locked();
-  if (rc) return rc;
-  const uint32_t* filt = nullptr;
-  rc = idx->set_filter(pod_filter, n_filter, &filt);
-  if (rc) return rc;
-  const size_t o_keys = 0, o_cnt = (size_t)n * 8, o_ent = o_cnt + (((size_t)n * 4 + 255) & ~size_t(255));
-  const size_t total = o_ent + (size_t)n * kMaxEnt * 4;
-  rc = idx->ensure_scratch(total, total);
-  if (rc) return rc;
-  std::memcpy(idx->h_scratch, keys, (size_t)n * 8);
-  cudaStream_t s = idx->stream;
-  KVB_CUDA_TRY(cudaMemcpyAsync(idx->d_scratch + o_keys, idx->h_scratch, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-  const int threads = 128;
-  index_lookup_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(
-      idx->table, idx->slots - 1, reinterpret_cast<const uint64_t*>(idx->d_scratch + o_keys), n, filt,
-      reinterpret_cast<int32_t*>(idx->d_scratch + o_cnt), reinterpret_cast<uint32_t*>(idx->d_scratch + o_ent));
-  KVB_CUDA_TRY(cudaGetLastError());
-  count_launch();
-  KVB_CUDA_TRY(cudaMemcpyAsync(idx->h_scratch + o_cnt, idx->d_scratch + o_cnt, total - o_cnt, cudaMemcpyDeviceToHost, s));
-  KVB_CUDA_TRY(cudaStreamSynchronize(s));
-  const int32_t* cnt = reinterpret_cast<const int32_t*>(idx->h_scratch + o_cnt);
-  const uint32_t* ent = reinterpret_cast<const uint32_t*>(idx->h_scratch + o_ent);
-  int64_t cut = n;
-  for (int64_t i = 0; i < n; ++i) {
-    if (cut < n) {  // after the cut nothing is looked at (in_memory.go:121-124 returns)
-      out_counts[i] = -1;
-      continue;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    KVB_REQUIRE(n > 0 && keys, "no requestKeys provided for lookup");  // in_memory.go:110-112
+    KVB_REQUIRE(out_counts && out_entries && out_cut, "NULL output");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    int rc = idx->flush_locked();
+    if (rc) return rc;
+    const uint32_t* filt = nullptr;
+    rc = idx->set_filter(pod_filter, n_filter, &filt);
+    if (rc) return rc;
+    const size_t o_keys = 0, o_cnt = (size_t)n * 8, o_ent = o_cnt + (((size_t)n * 4 + 255) & ~size_t(255));
+    const size_t total = o_ent + (size_t)n * kMaxEnt * 4;
+    rc = idx->ensure_scratch(total, total);
+    if (rc) return rc;
+    std::memcpy(idx->h_scratch, keys, (size_t)n * 8);
+    cudaStream_t s = idx->stream;
+    KVB_CUDA_TRY(cudaMemcpyAsync(idx->d_scratch + o_keys, idx->h_scratch, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    const int threads = 128;
+    index_lookup_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(
+        idx->table, idx->slots - 1, reinterpret_cast<const uint64_t*>(idx->d_scratch + o_keys), n, filt,
+        reinterpret_cast<int32_t*>(idx->d_scratch + o_cnt), reinterpret_cast<uint32_t*>(idx->d_scratch + o_ent));
+    KVB_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    KVB_CUDA_TRY(cudaMemcpyAsync(idx->h_scratch + o_cnt, idx->d_scratch + o_cnt, total - o_cnt, cudaMemcpyDeviceToHost, s));
+    KVB_CUDA_TRY(cudaStreamSynchronize(s));
+    const int32_t* cnt = reinterpret_cast<const int32_t*>(idx->h_scratch + o_cnt);
+    const uint32_t* ent = reinterpret_cast<const uint32_t*>(idx->h_scratch + o_ent);
+    int64_t cut = n;
+    for (int64_t i = 0; i < n; ++i) {
+      if (cut < n) {  // after the cut nothing is looked at (in_memory.go:121-124 returns)
+        out_counts[i] = -1;
+        continue;
+      }
+      if (cnt[i] == -1) {
+        out_counts[i] = -1;
+        continue;
+      }
+      // data.Get refreshes the outer LRU for every key that is found (in_memory.go:120)
+      auto it = idx->data.find(keys[i]);
+      if (it != idx->data.end()) idx->touch(it);
+      if (cnt[i] == -2) {
+        cut = i;
+        out_counts[i] = 0;
+        continue;
+      }
+      out_counts[i] = cnt[i];
+      for (int e = 0; e < cnt[i]; ++e) {
+        const uint32_t v = ent[i * kMaxEnt + e];
+        out_entries[i * kMaxEnt + e].pod = (uint16_t)(v & 0xffffu);
+        out_entries[i * kMaxEnt + e].tier = (uint8_t)((v >> 16) & 0xffu);
+        out_entries[i * kMaxEnt + e].speculative = (uint8_t)((v >> 24) & 1u);
+      }
     }
-    if (cnt[i] == -1) {
-      out_counts[i] = -1;
-      continue;
-    }
-    // data.Get refreshes the outer LRU for every key that is found (in_memory.go:120)
-    auto it = idx->data.find(keys[i]);
-    if (it != idx->data.end()) idx->touch(it);
-    if (cnt[i] == -2) {
-      cut = i;
-      out_counts[i] = 0;
-      continue;
-    }
-    out_counts[i] = cnt[i];
-    for (int e = 0; e < cnt[i]; ++e) {
-      const uint32_t v = ent[i * kMaxEnt + e];
-      out_entries[i * kMaxEnt + e].pod = (uint16_t)(v & 0xffffu);
-      out_entries[i * kMaxEnt + e].tier = (uint8_t)((v >> 16) & 0xffu);
-      out_entries[i * kMaxEnt + e].speculative = (uint8_t)((v >> 24) & 1u);
-    }
-  }
-  *out_cut = cut;
-  return KVB_OK;
+    *out_cut = cut;
+    return KVB_OK;
+  });
 }
 
 // keys already on the device at d_keys / d_koff (inside idx->d_scratch or elsewhere)
@@ -848,26 +880,30 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
 int kvb_index_score_batch(kvb_index_t* idx, const uint64_t* keys, const int64_t* key_off, int32_t n_prompts,
                           const uint16_t* pod_filter, int32_t n_filter, int32_t flags, int32_t* out_n,
                           uint16_t* out_pods, double* out_scores) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
-  if (n_prompts == 0) return KVB_OK;
-  KVB_REQUIRE(key_off && out_n && out_pods && out_scores, "NULL argument");
-  KVB_REQUIRE(keys || key_off[n_prompts] == key_off[0], "keys is NULL");
-  return score_common(idx, keys, key_off, n_prompts, nullptr, nullptr, nullptr, 0, nullptr, nullptr, pod_filter,
-                      n_filter, flags, out_n, out_pods, out_scores);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+    if (n_prompts == 0) return KVB_OK;
+    KVB_REQUIRE(key_off && out_n && out_pods && out_scores, "NULL argument");
+    KVB_REQUIRE(keys || key_off[n_prompts] == key_off[0], "keys is NULL");
+    return score_common(idx, keys, key_off, n_prompts, nullptr, nullptr, nullptr, 0, nullptr, nullptr, pod_filter,
+                        n_filter, flags, out_n, out_pods, out_scores);
+  });
 }
 
 int kvb_index_score_tokens_batch(kvb_index_t* idx, const uint32_t* tokens, const int64_t* prompt_off,
                                  const uint64_t* parents, int32_t n_prompts, int32_t block_size, const uint8_t* extra,
                                  const int64_t* extra_off, const uint16_t* pod_filter, int32_t n_filter,
                                  int32_t flags, int32_t* out_n, uint16_t* out_pods, double* out_scores) {
-  KVB_REQUIRE(idx != nullptr, "index is NULL");
-  KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
-  KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
-  if (n_prompts == 0) return KVB_OK;
-  KVB_REQUIRE(tokens && prompt_off && parents && out_n && out_pods && out_scores, "NULL argument");
-  return score_common(idx, nullptr, nullptr, n_prompts, tokens, prompt_off, parents, block_size, extra, extra_off,
-                      pod_filter, n_filter, flags, out_n, out_pods, out_scores);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
+    KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
+    if (n_prompts == 0) return KVB_OK;
+    KVB_REQUIRE(tokens && prompt_off && parents && out_n && out_pods && out_scores, "NULL argument");
+    return score_common(idx, nullptr, nullptr, n_prompts, tokens, prompt_off, parents, block_size, extra, extra_off,
+                        pod_filter, n_filter, flags, out_n, out_pods, out_scores);
+  });
 }
 
 }  // extern "C"

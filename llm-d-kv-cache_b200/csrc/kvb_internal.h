@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <exception>
+#include <new>
 #include <string>
 
 #include "kvb.h"
@@ -32,6 +34,23 @@ const char* get_error();
       return KVB_ERR_INVALID;             \
     }                                     \
   } while (0)
+
+// No C++ exception may cross the C ABI: every int-returning entry point runs its body through this.
+template <class F>
+static inline int guarded(F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory");
+    return KVB_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    set_error("unexpected exception: %s", e.what());
+    return KVB_ERR_INVALID;
+  } catch (...) {
+    set_error("unexpected exception");
+    return KVB_ERR_INVALID;
+  }
+}
 
 // Set the device for the duration of a scope and restore the caller's on exit
 // (the caller is typically a torch process that owns "current device").

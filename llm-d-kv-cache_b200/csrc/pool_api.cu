@@ -82,67 +82,71 @@ const char* kvb_last_error(void) { return get_error(); }
 int64_t kvb_launch_count(void) { return g_launches.load(); }
 
 int kvb_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return n;
+  return kvb::guarded([&]() -> int {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  });
 }
 
 int kvb_pool_create(int device, const void* const* tensor_ptrs, int32_t num_tensors, int64_t num_blocks,
                     int64_t frag_bytes, int64_t block_stride_bytes, kvb_pool_t** out) {
-  KVB_REQUIRE(out != nullptr, "kvb_pool_create: out is NULL");
-  *out = nullptr;
-  KVB_REQUIRE(tensor_ptrs != nullptr && num_tensors > 0, "kvb_pool_create: tensors is empty");  // tensor_copier.cu:34
-  KVB_REQUIRE(num_blocks > 0 && frag_bytes > 0, "kvb_pool_create: num_blocks and frag_bytes must be > 0");
-  if (block_stride_bytes == 0) block_stride_bytes = frag_bytes;
-  KVB_REQUIRE(block_stride_bytes >= frag_bytes, "kvb_pool_create: block stride smaller than fragment");
-  DeviceGuard g(device);
-  if (!g.ok) {
-    set_error("kvb_pool_create: cannot select CUDA device %d", device);
-    return KVB_ERR_CUDA;
-  }
-  kvb_pool* p = new kvb_pool();
-  p->device = device;
-  p->num_tensors = num_tensors;
-  p->num_blocks = num_blocks;
-  p->frag_bytes = frag_bytes;
-  p->stride_bytes = block_stride_bytes;
-  int vec = 16;
-  while (vec > 1 && ((frag_bytes % vec) || (block_stride_bytes % vec))) vec >>= 1;
-  p->h_tensor_ptrs = new const uint8_t*[num_tensors];
-  for (int i = 0; i < num_tensors; ++i) {
-    if (!tensor_ptrs[i]) {
-      set_error("kvb_pool_create: tensor %d is NULL", i);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(out != nullptr, "kvb_pool_create: out is NULL");
+    *out = nullptr;
+    KVB_REQUIRE(tensor_ptrs != nullptr && num_tensors > 0, "kvb_pool_create: tensors is empty");  // tensor_copier.cu:34
+    KVB_REQUIRE(num_blocks > 0 && frag_bytes > 0, "kvb_pool_create: num_blocks and frag_bytes must be > 0");
+    if (block_stride_bytes == 0) block_stride_bytes = frag_bytes;
+    KVB_REQUIRE(block_stride_bytes >= frag_bytes, "kvb_pool_create: block stride smaller than fragment");
+    DeviceGuard g(device);
+    if (!g.ok) {
+      set_error("kvb_pool_create: cannot select CUDA device %d", device);
+      return KVB_ERR_CUDA;
+    }
+    kvb_pool* p = new kvb_pool();
+    p->device = device;
+    p->num_tensors = num_tensors;
+    p->num_blocks = num_blocks;
+    p->frag_bytes = frag_bytes;
+    p->stride_bytes = block_stride_bytes;
+    int vec = 16;
+    while (vec > 1 && ((frag_bytes % vec) || (block_stride_bytes % vec))) vec >>= 1;
+    p->h_tensor_ptrs = new const uint8_t*[num_tensors];
+    for (int i = 0; i < num_tensors; ++i) {
+      if (!tensor_ptrs[i]) {
+        set_error("kvb_pool_create: tensor %d is NULL", i);
+        delete[] p->h_tensor_ptrs;
+        delete p;
+        return KVB_ERR_INVALID;
+      }
+      p->h_tensor_ptrs[i] = static_cast<const uint8_t*>(tensor_ptrs[i]);
+      while (vec > 1 && (reinterpret_cast<uintptr_t>(tensor_ptrs[i]) % vec)) vec >>= 1;
+    }
+    p->vec_bytes = vec;
+    {  // tensors that live on another GPU (peer-enabled or CUDA-IPC mapped): remember it for kernel selection
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, tensor_ptrs[0]) == cudaSuccess) {
+        p->peer = attr.type == cudaMemoryTypeDevice && attr.device != device;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    cudaError_t e = cudaMalloc(&p->d_tensor_ptrs, sizeof(void*) * num_tensors);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_tensor_ptrs, p->h_tensor_ptrs, sizeof(void*) * num_tensors, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error("kvb_pool_create: %s", cudaGetErrorString(e));
+      if (p->d_tensor_ptrs) cudaFree(p->d_tensor_ptrs);
       delete[] p->h_tensor_ptrs;
       delete p;
-      return KVB_ERR_INVALID;
+      return KVB_ERR_CUDA;
     }
-    p->h_tensor_ptrs[i] = static_cast<const uint8_t*>(tensor_ptrs[i]);
-    while (vec > 1 && (reinterpret_cast<uintptr_t>(tensor_ptrs[i]) % vec)) vec >>= 1;
-  }
-  p->vec_bytes = vec;
-  {  // tensors that live on another GPU (peer-enabled or CUDA-IPC mapped): remember it for kernel selection
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, tensor_ptrs[0]) == cudaSuccess) {
-      p->peer = attr.type == cudaMemoryTypeDevice && attr.device != device;
-    } else {
-      cudaGetLastError();
-    }
-  }
-  cudaError_t e = cudaMalloc(&p->d_tensor_ptrs, sizeof(void*) * num_tensors);
-  if (e == cudaSuccess)
-    e = cudaMemcpy(p->d_tensor_ptrs, p->h_tensor_ptrs, sizeof(void*) * num_tensors, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    set_error("kvb_pool_create: %s", cudaGetErrorString(e));
-    if (p->d_tensor_ptrs) cudaFree(p->d_tensor_ptrs);
-    delete[] p->h_tensor_ptrs;
-    delete p;
-    return KVB_ERR_CUDA;
-  }
-  *out = p;
-  return KVB_OK;
+    *out = p;
+    return KVB_OK;
+  });
 }
 
 void kvb_pool_destroy(kvb_pool_t* p) {
@@ -162,9 +166,11 @@ void kvb_pool_destroy(kvb_pool_t* p) {
 int64_t kvb_pool_block_bytes(const kvb_pool_t* p) { return p ? p->frag_bytes * p->num_tensors : 0; }
 
 int kvb_pool_mark_peer(kvb_pool_t* p, int is_peer) {
-  KVB_REQUIRE(p != nullptr, "pool is NULL");
-  p->peer = is_peer != 0;
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(p != nullptr, "pool is NULL");
+    p->peer = is_peer != 0;
+    return KVB_OK;
+  });
 }
 
 static int gs_host(kvb_pool_t* pool, const int64_t* ids, int64_t n, void* packed, void* stream, int flags,
@@ -186,132 +192,154 @@ static int gs_host(kvb_pool_t* pool, const int64_t* ids, int64_t n, void* packed
 }
 
 int kvb_gather_blocks(kvb_pool_t* pool, const int64_t* ids, int64_t n, void* packed, void* stream, int flags) {
-  return gs_host(pool, ids, n, packed, stream, flags, true);
+  return kvb::guarded([&]() -> int {
+    return gs_host(pool, ids, n, packed, stream, flags, true);
+  });
 }
 int kvb_scatter_blocks(kvb_pool_t* pool, const int64_t* ids, int64_t n, const void* packed, void* stream,
                        int flags) {
-  return gs_host(pool, ids, n, const_cast<void*>(packed), stream, flags, false);
+  return kvb::guarded([&]() -> int {
+    return gs_host(pool, ids, n, const_cast<void*>(packed), stream, flags, false);
+  });
 }
 int kvb_gather_blocks_dev(kvb_pool_t* pool, const int64_t* ids_dev, int64_t n, void* packed, void* stream,
                           int flags) {
-  KVB_REQUIRE(pool && (n == 0 || (ids_dev && packed)), "NULL argument");
-  KVB_REQUIRE(n >= 0, "negative block count");
-  DeviceGuard g(pool->device);
-  return launch_gather(pool, ids_dev, n, packed, static_cast<cudaStream_t>(stream), flags);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(pool && (n == 0 || (ids_dev && packed)), "NULL argument");
+    KVB_REQUIRE(n >= 0, "negative block count");
+    DeviceGuard g(pool->device);
+    return launch_gather(pool, ids_dev, n, packed, static_cast<cudaStream_t>(stream), flags);
+  });
 }
 int kvb_scatter_blocks_dev(kvb_pool_t* pool, const int64_t* ids_dev, int64_t n, const void* packed, void* stream,
                            int flags) {
-  KVB_REQUIRE(pool && (n == 0 || (ids_dev && packed)), "NULL argument");
-  KVB_REQUIRE(n >= 0, "negative block count");
-  DeviceGuard g(pool->device);
-  return launch_scatter(pool, ids_dev, n, packed, static_cast<cudaStream_t>(stream), flags);
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(pool && (n == 0 || (ids_dev && packed)), "NULL argument");
+    KVB_REQUIRE(n >= 0, "negative block count");
+    DeviceGuard g(pool->device);
+    return launch_scatter(pool, ids_dev, n, packed, static_cast<cudaStream_t>(stream), flags);
+  });
 }
 
 // pinned host memory for callers that want zero staging copies (token buffers, host-tier staging)
 int kvb_host_alloc(size_t bytes, void** out) {
-  KVB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
-  KVB_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
+    KVB_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return KVB_OK;
+  });
 }
 int kvb_host_free(void* p) {
-  if (p) KVB_CUDA_TRY(cudaFreeHost(p));
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    if (p) KVB_CUDA_TRY(cudaFreeHost(p));
+    return KVB_OK;
+  });
 }
 
 // ------------------------------------------------------------------------------- migration / IPC
 int kvb_ipc_export(int device, const void* dev_ptr, kvb_ipc_mem_t* out) {
-  KVB_REQUIRE(dev_ptr && out, "NULL argument");
-  static_assert(sizeof(cudaIpcMemHandle_t) == KVB_IPC_HANDLE_BYTES, "handle size");
-  DeviceGuard g(device);
-  // cudaIpcGetMemHandle returns the handle of the containing allocation; find its base for the offset
-  void* base = nullptr;
-  size_t size = 0;
-  cudaPointerAttributes attr;
-  KVB_CUDA_TRY(cudaPointerGetAttributes(&attr, dev_ptr));
-  typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  KVB_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) {
-    set_error("cuMemGetAddressRange entry point unavailable");
-    return KVB_ERR_CUDA;
-  }
-  unsigned long long b = 0;
-  int dr = reinterpret_cast<cuMemGetAddressRange_t>(fn)(&b, &size, (unsigned long long)(uintptr_t)dev_ptr);
-  if (dr != 0) {
-    set_error("cuMemGetAddressRange failed (%d)", dr);
-    return KVB_ERR_CUDA;
-  }
-  base = reinterpret_cast<void*>((uintptr_t)b);
-  cudaIpcMemHandle_t h;
-  KVB_CUDA_TRY(cudaIpcGetMemHandle(&h, base));
-  std::memcpy(out->handle, &h, sizeof(h));
-  out->offset = (int64_t)((const uint8_t*)dev_ptr - (const uint8_t*)base);
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(dev_ptr && out, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KVB_IPC_HANDLE_BYTES, "handle size");
+    DeviceGuard g(device);
+    // cudaIpcGetMemHandle returns the handle of the containing allocation; find its base for the offset
+    void* base = nullptr;
+    size_t size = 0;
+    cudaPointerAttributes attr;
+    KVB_CUDA_TRY(cudaPointerGetAttributes(&attr, dev_ptr));
+    typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    KVB_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuMemGetAddressRange entry point unavailable");
+      return KVB_ERR_CUDA;
+    }
+    unsigned long long b = 0;
+    int dr = reinterpret_cast<cuMemGetAddressRange_t>(fn)(&b, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    if (dr != 0) {
+      set_error("cuMemGetAddressRange failed (%d)", dr);
+      return KVB_ERR_CUDA;
+    }
+    base = reinterpret_cast<void*>((uintptr_t)b);
+    cudaIpcMemHandle_t h;
+    KVB_CUDA_TRY(cudaIpcGetMemHandle(&h, base));
+    std::memcpy(out->handle, &h, sizeof(h));
+    out->offset = (int64_t)((const uint8_t*)dev_ptr - (const uint8_t*)base);
+    return KVB_OK;
+  });
 }
 
 int kvb_ipc_import(int device, const kvb_ipc_mem_t* mem, void** out_ptr) {
-  KVB_REQUIRE(mem && out_ptr, "NULL argument");
-  DeviceGuard g(device);
-  cudaIpcMemHandle_t h;
-  std::memcpy(&h, mem->handle, sizeof(h));
-  void* base = nullptr;
-  KVB_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-  *out_ptr = static_cast<uint8_t*>(base) + mem->offset;
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(mem && out_ptr, "NULL argument");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, mem->handle, sizeof(h));
+    void* base = nullptr;
+    KVB_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *out_ptr = static_cast<uint8_t*>(base) + mem->offset;
+    return KVB_OK;
+  });
 }
 
 int kvb_ipc_close(int device, void* imported_ptr, int64_t offset) {
-  KVB_REQUIRE(imported_ptr, "NULL argument");
-  DeviceGuard g(device);
-  KVB_CUDA_TRY(cudaIpcCloseMemHandle(static_cast<uint8_t*>(imported_ptr) - offset));
-  return KVB_OK;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(imported_ptr, "NULL argument");
+    DeviceGuard g(device);
+    KVB_CUDA_TRY(cudaIpcCloseMemHandle(static_cast<uint8_t*>(imported_ptr) - offset));
+    return KVB_OK;
+  });
 }
 
 int kvb_enable_peer_access(int device, int peer) {
-  DeviceGuard g(device);
-  int can = 0;
-  KVB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
-  if (!can) {
-    set_error("device %d cannot access peer %d", device, peer);
-    return KVB_ERR_UNSUPPORTED;
-  }
-  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
-  if (e == cudaErrorPeerAccessAlreadyEnabled) {
-    cudaGetLastError();
+  return kvb::guarded([&]() -> int {
+    DeviceGuard g(device);
+    int can = 0;
+    KVB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) {
+      set_error("device %d cannot access peer %d", device, peer);
+      return KVB_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      return KVB_OK;
+    }
+    KVB_CUDA_TRY(e);
     return KVB_OK;
-  }
-  KVB_CUDA_TRY(e);
-  return KVB_OK;
+  });
 }
 
 int kvb_migrate_blocks(kvb_pool_t* src, kvb_pool_t* dst, const int64_t* src_ids, const int64_t* dst_ids, int64_t n,
                        void* stream, int flags) {
-  KVB_REQUIRE(src && dst, "pool is NULL");
-  KVB_REQUIRE(n >= 0, "negative block count");
-  if (n == 0) return KVB_OK;
-  KVB_REQUIRE(src_ids && dst_ids, "ids NULL");
-  KVB_REQUIRE(src->num_tensors == dst->num_tensors && src->frag_bytes == dst->frag_bytes,
-              "migrate: pools differ in shape (T %d vs %d, frag %lld vs %lld)", src->num_tensors, dst->num_tensors,
-              (long long)src->frag_bytes, (long long)dst->frag_bytes);
-  KVB_REQUIRE(dst->device == src->device,
-              "migrate: describe the destination pool on the source device (peer/IPC pointers)");
-  int rc = validate_ids(src, src_ids, n);
-  if (rc) return rc;
-  rc = validate_ids(dst, dst_ids, n);
-  if (rc) return rc;
-  DeviceGuard g(src->device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // both id lists go through one scratch upload: [src ids | dst ids]
-  std::vector<int64_t> both(2 * n);
-  std::memcpy(both.data(), src_ids, n * sizeof(int64_t));
-  std::memcpy(both.data() + n, dst_ids, n * sizeof(int64_t));
-  const int64_t* d = nullptr;
-  rc = upload_ids(src, both.data(), 2 * n, s, &d);
-  if (rc) return rc;
-  rc = launch_migrate(src, dst, d, d + n, n, s, flags);
-  cudaEventRecord(src->last_ids_ev, s);
-  return rc;
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(src && dst, "pool is NULL");
+    KVB_REQUIRE(n >= 0, "negative block count");
+    if (n == 0) return KVB_OK;
+    KVB_REQUIRE(src_ids && dst_ids, "ids NULL");
+    KVB_REQUIRE(src->num_tensors == dst->num_tensors && src->frag_bytes == dst->frag_bytes,
+                "migrate: pools differ in shape (T %d vs %d, frag %lld vs %lld)", src->num_tensors, dst->num_tensors,
+                (long long)src->frag_bytes, (long long)dst->frag_bytes);
+    KVB_REQUIRE(dst->device == src->device,
+                "migrate: describe the destination pool on the source device (peer/IPC pointers)");
+    int rc = validate_ids(src, src_ids, n);
+    if (rc) return rc;
+    rc = validate_ids(dst, dst_ids, n);
+    if (rc) return rc;
+    DeviceGuard g(src->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // both id lists go through one scratch upload: [src ids | dst ids]
+    std::vector<int64_t> both(2 * n);
+    std::memcpy(both.data(), src_ids, n * sizeof(int64_t));
+    std::memcpy(both.data() + n, dst_ids, n * sizeof(int64_t));
+    const int64_t* d = nullptr;
+    rc = upload_ids(src, both.data(), 2 * n, s, &d);
+    if (rc) return rc;
+    rc = launch_migrate(src, dst, d, d + n, n, s, flags);
+    cudaEventRecord(src->last_ids_ev, s);
+    return rc;
+  });
 }
 
 }  // extern "C"
