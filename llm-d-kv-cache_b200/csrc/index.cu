@@ -187,14 +187,17 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
     // ---- phase B: serial walk over the tile's keys
     for (int j = 0; j < in_tile; ++j) {
       const int64_t sj = __shfl_sync(FULL, slot, j);
+      // bucket entries sit on lanes 16..28, the reported pods (owners) on lanes 0..12 in the order they appeared at
+      // key 0: ONE match.any per key pairs every owner with the entries that carry its pod (13 x 3 shuffles before)
       bool valid = false;
-      uint32_t pod = 0x10000u + lane;  // unique sentinel for invalid lanes
+      uint32_t pod = 0x10000u + lane;  // unique sentinel for lanes without a valid entry
       double w = 0.0;
       if (sj >= 0) {
         const Bucket& b = tile[warp][j];
         const int cnt = (int)((b.meta >> 8) & 0xff);
-        if (lane < cnt && lane < kMaxEnt) {
-          const uint32_t v = b.ent[lane];
+        const int e = lane - 16;
+        if (e >= 0 && e < cnt && e < kMaxEnt) {
+          const uint32_t v = b.ent[e];
           if (pod_allowed(filter_bits, v & 0xffffu)) {
             valid = true;
             pod = v & 0xffffu;
@@ -204,30 +207,38 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
       }
       if (base + j == 0) {
         // key 0: active set = distinct pods, weight = max over that pod's tiers (fillMaxWeights)
+        const unsigned group = __match_any_sync(FULL, pod) & 0x1fff0000u;  // entry lanes with this lane's pod
+        const bool leader = valid && (group & ((1u << lane) - 1u)) == 0u;   // first entry of its pod
         double wmax = w;
-        bool leader = valid;
-#pragma unroll
-        for (int e = 0; e < kMaxEnt; ++e) {
-          const uint32_t pe = __shfl_sync(FULL, pod, e);
-          const double we = __shfl_sync(FULL, w, e);
-          if (valid && pe == pod) {
+        unsigned rest = valid ? (group & ~(1u << lane)) : 0u;
+        while (__any_sync(FULL, rest != 0u)) {  // usually zero or one round: a pod on two tiers
+          const int src = rest ? __ffs((int)rest) - 1 : lane;
+          const double we = __shfl_sync(FULL, w, src);
+          if (rest) {
             if (we > wmax) wmax = we;
-            if (e < lane) leader = false;
+            rest &= rest - 1u;
           }
         }
-        owner = active = leader;
-        my_pod = leader ? pod : 0xffffffffu;
-        score = wmax;
+        const bool l2 = __shfl_down_sync(FULL, leader ? 1 : 0, 16) != 0;
+        const uint32_t p2 = __shfl_down_sync(FULL, pod, 16);
+        const double w2 = __shfl_down_sync(FULL, wmax, 16);
+        owner = active = lane < kMaxEnt && l2;
+        my_pod = owner ? p2 : 0xffffffffu;
+        score = owner ? w2 : 0.0;
       } else {
-        bool hit = false;
+        const uint32_t val = lane < 16 ? (active ? my_pod : 0x20000u + lane) : pod;
+        unsigned em = __match_any_sync(FULL, val) >> 16;  // entry lanes (as bits 0..12) that carry my_pod
+        if (!(lane < 16 && active)) em = 0u;
+        const bool hit = em != 0u;
         double wm = 0.0;
-#pragma unroll
-        for (int e = 0; e < kMaxEnt; ++e) {
-          const uint32_t pe = __shfl_sync(FULL, pod, e);
-          const double we = __shfl_sync(FULL, w, e);
-          if (pe == my_pod) {
-            if (!hit || we > wm) wm = we;
-            hit = true;
+        bool first = true;
+        while (__any_sync(FULL, em != 0u)) {
+          const int src = em ? 16 + __ffs((int)em) - 1 : lane;
+          const double we = __shfl_sync(FULL, w, src);
+          if (em) {
+            if (first || we > wm) wm = we;
+            first = false;
+            em &= em - 1u;
           }
         }
         if (active) {
