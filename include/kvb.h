@@ -14,6 +14,10 @@
  *   - block ids are int64 (reference: std::vector<int64_t>, storage_offload.hpp:104-109).
  *   - there is NO CPU fallback: every compute entry point fails with KVB_ERR_CUDA
  *     when no sm_100 device is usable.
+ *   - environment switches (diagnostics and A/B runs, never needed for correctness):
+ *       KVB_HASH_KERNEL=lanes   hash with the lane-per-prompt kernels at every batch size (read per call)
+ *       KVB_HASH_ONE_WARP=1     hash with the one-warp lane kernel (read once)
+ *       KVB_NO_NUMA_BIND=1      do not bind engine threads / arena to the GPU's NUMA node
  */
 #ifndef KVB_H_
 #define KVB_H_

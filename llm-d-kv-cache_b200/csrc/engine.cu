@@ -85,9 +85,9 @@ class Arena {
   std::unordered_map<std::string, Entry> entries;
   std::list<std::string> lru;  // front = oldest
 
-  int init(int64_t bytes) {
+  int init(int device, int64_t bytes) {
     cap = bytes;
-    cudaError_t e = cudaHostAlloc(&base, (size_t)bytes, cudaHostAllocPortable);
+    cudaError_t e = host_alloc_near(device, reinterpret_cast<void**>(&base), (size_t)bytes, cudaHostAllocPortable);
     if (e != cudaSuccess) {
       set_error("host arena: cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
       base = nullptr;
@@ -217,54 +217,6 @@ class Arena {
     return false;
   }
 };
-
-// ---------------------------------------------------------------------------------- NUMA placement
-// The reference pins its I/O threads to the GPU-local NUMA node and prefers that node for staging memory
-// (thread_pool.cpp:73-131, numa_utils.cpp).  Same intent without libnuma: read the GPU's node from sysfs and set the
-// affinity of the threads that allocate (first touch => local pages) and drive the copies.
-static int gpu_numa_node(int device) {
-  char bus[32] = {0};
-  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
-    cudaGetLastError();
-    return -1;
-  }
-  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
-  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
-  FILE* f = fopen(path.c_str(), "r");
-  if (!f) return -1;
-  int node = -1;
-  if (fscanf(f, "%d", &node) != 1) node = -1;
-  fclose(f);
-  return node;
-}
-static std::vector<int> cpus_of_node(int node) {
-  std::vector<int> cpus;
-  if (node < 0) return cpus;
-  std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
-  FILE* f = fopen(path.c_str(), "r");
-  if (!f) return cpus;
-  char buf[4096] = {0};
-  if (!fgets(buf, sizeof(buf), f)) buf[0] = 0;
-  fclose(f);
-  char* save = nullptr;
-  for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-31,64-95"
-    int a = 0, b = 0;
-    if (sscanf(tok, "%d-%d", &a, &b) == 2) {
-      for (int c = a; c <= b; ++c) cpus.push_back(c);
-    } else if (sscanf(tok, "%d", &a) == 1) {
-      cpus.push_back(a);
-    }
-  }
-  return cpus;
-}
-static void bind_this_thread(const std::vector<int>& cpus) {
-  if (cpus.empty()) return;
-  cpu_set_t set;
-  CPU_ZERO(&set);
-  for (int c : cpus)
-    if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
-  pthread_setaffinity_np(pthread_self(), sizeof(set), &set);  // best effort
-}
 
 // ---------------------------------------------------------------------------------- file helpers
 static bool file_exists(const std::string& p) {
@@ -808,24 +760,11 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
       set_error("cannot select CUDA device %d", e->device);
       return KVB_ERR_CUDA;
     }
-    if (!std::getenv("KVB_NO_NUMA_BIND")) e->local_cpus = cpus_of_node(gpu_numa_node(e->device));
+    e->local_cpus = gpu_local_cpus(e->device);
     if (opts->tier == KVB_TIER_HOST_ARENA) {
       KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
-      // allocate (and thereby first-touch / pin) the arena from a thread bound to the GPU-local node, without
-      // disturbing the caller's own affinity
-      int rc = KVB_OK;
-      std::string err;
-      std::thread t([&] {
-        bind_this_thread(e->local_cpus);
-        cudaSetDevice(e->device);
-        rc = e->arena.init(opts->host_arena_bytes);
-        if (rc) err = get_error();
-      });
-      t.join();
-      if (rc) {
-        set_error("%s", err.c_str());
-        return rc;
-      }
+      int rc = e->arena.init(e->device, opts->host_arena_bytes);  // pinned and first-touched on the GPU-local node
+      if (rc) return rc;
     }
     const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);
     for (int i = 0; i < opts->io_threads; ++i) {

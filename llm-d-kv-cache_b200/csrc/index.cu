@@ -326,7 +326,7 @@ struct kvb_index {
       h_scratch_cap = 0;
       size_t cap = std::max<size_t>(host_bytes, 1 << 20);
       cap = (cap * 3 / 2 + 255) & ~size_t(255);
-      KVB_CUDA_TRY(cudaHostAlloc(&h_scratch, cap, cudaHostAllocDefault));
+      KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&h_scratch), cap, cudaHostAllocDefault));
       h_scratch_cap = cap;
     }
     return KVB_OK;
@@ -840,10 +840,21 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
       KVB_CUDA_TRY(cudaMemcpyAsync(D + o_poff, H + o_poff, (o_par + (size_t)n_prompts * 8) - o_poff,
                                    cudaMemcpyHostToDevice, s));
     } else {
-      std::memcpy(H + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4);
-      // tokens, prompt_off and parents are adjacent in the scratch: one copy
-      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, H + o_tok, (o_par + (size_t)n_prompts * 8) - o_tok,
-                                   cudaMemcpyHostToDevice, s));
+      // pageable tokens (a Go slice through cgo, a numpy array): staged through the pinned scratch in 1 MiB pieces so
+      // the copy engine moves piece i while the CPU copies piece i + 1; prompt_off and parents ride with the last piece
+      // (tokens, prompt_off and parents are adjacent in the scratch)
+      const size_t tok_bytes = (size_t)total_tok * 4, end = o_par + (size_t)n_prompts * 8;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(tokens + prompt_off[0]);
+      constexpr size_t kPiece = 1u << 20;
+      size_t done = 0;
+      do {
+        const size_t len = std::min(kPiece, tok_bytes - done);
+        std::memcpy(H + o_tok + done, src + done, len);
+        const bool last = done + len == tok_bytes;
+        KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok + done, H + o_tok + done, last ? end - (o_tok + done) : len,
+                                     cudaMemcpyHostToDevice, s));
+        done += len;
+      } while (done < tok_bytes);
     }
     if (extra_off) {
       std::memcpy(H + o_eoff, extra_off, ((size_t)total_keys + 1) * 8);

@@ -9,6 +9,7 @@
 #include <exception>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "kvb.h"
 
@@ -51,6 +52,12 @@ static inline int guarded(F&& f) noexcept {
     return KVB_ERR_INVALID;
   }
 }
+
+// NUMA placement (pool_api.cu): CPUs of the GPU's node (empty: unknown or KVB_NO_NUMA_BIND), thread binding, and
+// pinned host memory first-touched on that node.
+std::vector<int> gpu_local_cpus(int device);
+void bind_this_thread(const std::vector<int>& cpus);
+cudaError_t host_alloc_near(int device, void** out, size_t bytes, unsigned flags);
 
 // Set the device for the duration of a scope and restore the caller's on exit
 // (the caller is typically a torch process that owns "current device").

@@ -1,7 +1,14 @@
 // pool_api.cu — error plumbing, pool objects and the gather/scatter/migrate C entry points.
+#include <pthread.h>
+#include <sched.h>
+
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "kvb_internal.h"
@@ -69,6 +76,80 @@ int upload_ids(kvb_pool* pool, const int64_t* ids_host, int64_t n, cudaStream_t 
   *out_dev = sl.d_ids;
   pool->last_ids_ev = sl.free_ev;
   return KVB_OK;
+}
+
+// ---------------------------------------------------------------------------------- NUMA placement
+// The reference pins its I/O threads to the GPU-local NUMA node and prefers that node for staging memory
+// (thread_pool.cpp:73-131, numa_utils.cpp).  Same intent without libnuma: read the GPU's node from sysfs and set the
+// affinity of the threads that allocate (first touch => local pages) and drive the copies.
+static int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+static std::vector<int> cpus_of_node(int node) {
+  std::vector<int> cpus;
+  if (node < 0) return cpus;
+  std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return cpus;
+  char buf[4096] = {0};
+  if (!fgets(buf, sizeof(buf), f)) buf[0] = 0;
+  fclose(f);
+  char* save = nullptr;
+  for (char* tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-31,64-95"
+    int a = 0, b = 0;
+    if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+      for (int c = a; c <= b; ++c) cpus.push_back(c);
+    } else if (sscanf(tok, "%d", &a) == 1) {
+      cpus.push_back(a);
+    }
+  }
+  return cpus;
+}
+void bind_this_thread(const std::vector<int>& cpus) {
+  if (cpus.empty()) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int c : cpus)
+    if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof(set), &set);  // best effort
+}
+
+
+std::vector<int> gpu_local_cpus(int device) {
+  if (std::getenv("KVB_NO_NUMA_BIND")) return {};
+  static std::mutex mu;
+  static std::map<int, std::vector<int>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(device);
+  if (it == cache.end()) it = cache.emplace(device, cpus_of_node(gpu_numa_node(device))).first;
+  return it->second;
+}
+
+// Pinned host memory placed on the GPU's NUMA node: allocated (pinning touches every page) from a short-lived thread
+// bound to that node, so the caller's own affinity is left alone.
+cudaError_t host_alloc_near(int device, void** out, size_t bytes, unsigned flags) {
+  const std::vector<int> cpus = gpu_local_cpus(device);
+  if (cpus.empty()) return cudaHostAlloc(out, bytes, flags);
+  cudaError_t e = cudaSuccess;
+  std::thread t([&] {
+    bind_this_thread(cpus);
+    cudaSetDevice(device);
+    e = cudaHostAlloc(out, bytes, flags);
+  });
+  t.join();
+  return e;
 }
 
 }  // namespace kvb
@@ -225,7 +306,9 @@ int kvb_scatter_blocks_dev(kvb_pool_t* pool, const int64_t* ids_dev, int64_t n, 
 int kvb_host_alloc(size_t bytes, void** out) {
   return kvb::guarded([&]() -> int {
     KVB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
-    KVB_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    int dev = 0;
+    KVB_CUDA_TRY(cudaGetDevice(&dev));  // placed on the NUMA node of the caller's current device
+    KVB_CUDA_TRY(host_alloc_near(dev, out, bytes, cudaHostAllocPortable));
     return KVB_OK;
   });
 }

@@ -86,3 +86,29 @@ class KVPool:
     def scatter_dev(self, ids_dev, packed, stream=None, flags: int = 0):
         check(_lib.load().kvb_scatter_blocks_dev(self.handle, ids_dev.data_ptr(), ids_dev.numel(),
                                                  packed.data_ptr(), _stream_ptr(stream), flags))
+
+
+class PinnedBuffer:
+    """Pinned host memory from kvb_host_alloc: page-locked and placed on the NUMA node of the current CUDA device, so
+    the copy engine (and the engine's fused host I/O) reads it at full PCIe rate without a staging copy."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(_lib.load().kvb_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr, self.nbytes = int(p.value), int(nbytes)
+
+    def numpy(self, dtype=np.uint8) -> np.ndarray:
+        """A view of the whole buffer; it must not outlive this object."""
+        raw = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        return np.frombuffer(raw, dtype=np.uint8).view(dtype)
+
+    def free(self) -> None:
+        if getattr(self, "ptr", 0):
+            _lib.load().kvb_host_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

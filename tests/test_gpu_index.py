@@ -245,3 +245,28 @@ def test_concurrent_stress(kvb, torch_cuda):
         assert len(got) == per
         assert all(v == [K.PodEntry("pod-%d" % t, "gpu")] for v in got.values())
         assert idx.get_request_key(stable[t][0] ^ 0x5555) == stable[t][0]
+
+
+def test_pinned_token_buffer_scores_like_pageable(kvb, torch_cuda):
+    """kvb_host_alloc memory (pinned, NUMA-local) takes the no-staging path of the fused scorer; same results."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(21)
+    tp = K.ChunkedTokenDatabase(16, "")
+    idx = K.Index()
+    n, ntok = 40, 333
+    tokens = rng.integers(0, 128256, n * ntok).astype(np.uint32)
+    off = np.arange(0, (n + 1) * ntok, ntok, dtype=np.int64)
+    parents = np.full(n, tp.get_init_hash("m"), dtype=np.uint64)
+    keys, koff = tp.tokens_to_kv_block_keys_batch([tokens[off[i]:off[i + 1]] for i in range(n)], "m")
+    for i in range(0, n, 2):
+        idx.add(None, keys[koff[i]:koff[i] + 1 + i % 7], [K.PodEntry("pod-%d" % (i % 5), "gpu")])
+    want = idx.score_tokens_flat(16, tokens, off, parents)
+    buf = kvb.pool.PinnedBuffer(tokens.nbytes)
+    pinned = buf.numpy(np.uint32)
+    pinned[:] = tokens
+    got = idx.score_tokens_flat(16, pinned, off, parents)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    del pinned
+    buf.free()
+    buf.free()  # idempotent

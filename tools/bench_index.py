@@ -106,11 +106,15 @@ def main():
     t_fused = med(lambda: idx.score_tokens_flat(BS, tokens, off, parents, out=out))
     launches = (kvb.lib.kvb_launch_count() - launches0) // 9
     # same call with the tokens in pinned host memory (kvb_host_alloc / cudaHostAlloc): no staging memcpy
-    tok_pin = torch.from_numpy(tokens).pin_memory().numpy()
+    pin1 = kvb.pool.PinnedBuffer(tokens.nbytes)  # kvb_host_alloc: pinned on the GPU's NUMA node
+    tok_pin = pin1.numpy(np.uint32)
+    tok_pin[:] = tokens
     t_fused_pinned = med(lambda: idx.score_tokens_flat(BS, tok_pin, off, parents, out=out))
     # 8x the batch (8192 prompts): fixed per-call costs amortise
     reps = 8
-    tok8 = torch.from_numpy(np.tile(tokens, reps)).pin_memory().numpy()
+    pin8 = kvb.pool.PinnedBuffer(tokens.nbytes * reps)
+    tok8 = pin8.numpy(np.uint32)
+    tok8[:] = np.tile(tokens, reps)
     off8 = np.arange(0, (N_PROMPTS * reps + 1) * N_TOK, N_TOK, dtype=np.int64)
     par8 = np.tile(parents, reps)
     t_fused8 = med(lambda: idx.score_tokens_flat(BS, tok8, off8, par8), iters=5)
