@@ -769,8 +769,37 @@ def run_cpu_baseline(tensors):
             except Exception as e:
                 lat = {"error": repr(e)}
             reference_step.engines.clear()
+            del ref_eng
+            # the reference's opt-in SM-copy path (tensor_copier.cu:41-42 reads the switches when the engine is built).
+            # It runs on its OWN scratch pool: that path stages a block at slot `block_id % blocks_per_file`
+            # (tensor_copier_kernels.cu:78-80), so a file whose ids collide modulo 16 does not round-trip and would
+            # corrupt the workload's pool; whether it round-tripped is reported, not assumed.
+            kc = None
+            try:
+                os.environ["USE_KERNEL_COPY_READ"] = os.environ["USE_KERNEL_COPY_WRITE"] = "1"
+                g = torch.Generator(device="cuda").manual_seed(7)
+                scratch = [torch.randint(0, 127, (1024, FRAG_BYTES), dtype=torch.int8, device="cuda", generator=g)
+                           for _ in range(len(tensors))]
+                want = [t.clone() for t in scratch]
+                # aligned 16-block runs in random order: the only id pattern that path stores without collisions
+                runs = np.random.default_rng(3).permutation(1024 // BLOCKS_PER_FILE)[:512 // BLOCKS_PER_FILE]
+                small = (runs[:, None] * BLOCKS_PER_FILE + np.arange(BLOCKS_PER_FILE)[None, :]).reshape(-1).astype(np.int64)
+                reference_step(mod, scratch, small[:64], "kwarm", io_threads)
+                ka, kb = reference_step(mod, scratch, small, "kcopy", io_threads)
+                exact = all(torch.equal(x, y) for x, y in zip(scratch, want))
+                kc = {"gbs": 2 * len(small) * BLOCK_BYTES / (ka + kb) / 1e9, "store_gbs": len(small) * BLOCK_BYTES / ka / 1e9,
+                      "load_gbs": len(small) * BLOCK_BYTES / kb / 1e9, "roundtrip_bit_exact": bool(exact),
+                      "sample": f"{len(small)} blocks of a 1024-block scratch pool as aligned {BLOCKS_PER_FILE}-block runs "
+                                "(random ids collide in its id % blocks_per_file staging slots), USE_KERNEL_COPY_READ=WRITE=1"}
+                del scratch, want
+            except Exception as e:
+                kc = {"error": repr(e)}
+            finally:
+                os.environ.pop("USE_KERNEL_COPY_READ", None)
+                os.environ.pop("USE_KERNEL_COPY_WRITE", None)
+                reference_step.engines.clear()
             return {"value": 2 * payload / (a + b) / 1e9, "unit": "GB/s", "cores": io_threads, "kind": "reference",
-                    "single_file_job_latency": lat,
+                    "single_file_job_latency": lat, "kernel_copy_path": kc,
                     "pipelined_jobs_gbs": (2 * payload / t_pipe / 1e9) if t_pipe else None,
                     "sample": sample + ", default cudaMemcpyAsync path, io_threads=min(64,nproc)",
                     "store_gbs": payload / a / 1e9, "load_gbs": payload / b / 1e9, "host_cores": cores}
