@@ -2,9 +2,11 @@
 
 A restatement, on the CPU, of the reference algorithms on the hot path
 (llm-d/llm-d-kv-cache @ 82d31d1).  Nothing under ``oracle/`` is part of the
-product: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
-``cpu_baseline`` / ``--impl reference`` legs may import it, and only as the
-checker / the reported baseline.  The product (``llm-d-kv-cache_b200``) never
+product: only ``tests/`` (the pytest suite and the two measurement / sanitizer
+drivers kept there, ``tests/bench_index.py`` and ``tests/sanitize_smoke.py``),
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and only as the checker / the reported
+baseline.  ``tools/`` never does.  The product (``llm-d-kv-cache_b200``) never
 imports this package and has no CPU fallback.
 
 Parity status (see DESIGN.md "Oracle"):

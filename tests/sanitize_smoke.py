@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Every kernel of libkvb.so at small sizes, for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
-    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+    compute-sanitizer --tool memcheck  python tests/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python tests/sanitize_smoke.py
 Results are checked against the oracle as in smoke()."""
 import importlib
 import os

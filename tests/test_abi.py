@@ -43,3 +43,19 @@ def test_header_cites_reference():
     for needle in ("tensor_copier.cu", "storage_offload.cpp", "token_processor.go", "in_memory.go",
                    "kvblock_scorer.go", "indexer.go"):
         assert needle in src
+
+
+def test_oracle_is_only_imported_by_the_checkers():
+    """The product package and tools/ must not import, link or execute anything under oracle/."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|oracle[/.](kvblock|offload|kvevents)_oracle|oracle/_ref", re.M)
+    offenders = []
+    for sub in ("llm-d-kv-cache_b200", "tools", "include", "go"):
+        for dp, _, fns in os.walk(os.path.join(root, sub)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".h", ".hpp", ".go", ".cpp")):
+                    if pat.search(open(os.path.join(dp, fn), errors="ignore").read()):
+                        offenders.append(os.path.relpath(os.path.join(dp, fn), root))
+    assert offenders == []
