@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KVB_ABI_VERSION 1
+#define KVB_ABI_VERSION 2
 
 #define KVB_OK 0
 #define KVB_ERR_INVALID (-1)   /* bad argument */
@@ -108,7 +108,17 @@ typedef struct kvb_engine_opts {
                                       (fused gather+D2H / H2D+scatter, no HBM staging, no cudaMemcpy); 0 = staged */
   int32_t strict_load_errors;      /* 0 = reference behaviour: a failed load still reports ok (storage_offload.cpp:378-383);
                                       1 = report ok=0 */
+  int32_t gds_mode;                /* KVB_GDS_* bits, file tier only: reference gds_mode (gds_file_io.cpp:425-446).  Files
+                                      are then the reference's GDS format (head-aligned, n x block_bytes long) moved by
+                                      cuFile between the file and the packed HBM chunk, ONE call per file.  Falls back to
+                                      the CPU-staged path when libcufile cannot be loaded (storage_offload.cpp:129-134) */
+  int32_t reserved;                /* keeps the struct a multiple of 8 bytes; must be 0 */
 } kvb_engine_opts_t;
+
+#define KVB_GDS_DISABLED 0
+#define KVB_GDS_READ 1   /* loads through cuFileRead */
+#define KVB_GDS_WRITE 2  /* stores through cuFileWrite */
+#define KVB_GDS_BOUNCE 4 /* reference "bb_*" modes; same data path here (the packed chunk is the registered buffer) */
 
 void kvb_engine_default_opts(kvb_engine_opts_t* opts);
 int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engine_t** out);

@@ -28,7 +28,6 @@ class StorageOffloadEngine {
                        int read_preferring_workers, const std::string& gds_mode = "disabled",
                        float max_write_queued_seconds = 10.0f, int device = 0, int tier = KVB_TIER_FILE,
                        int64_t host_arena_bytes = 0) {
-    (void)gds_mode;  // GDS is not implemented; the reference falls back to CPU staging too (storage_offload.cpp:129-134)
     if (tensors.empty()) throw std::invalid_argument("TensorCopier: tensors is empty");            // tensor_copier.cu:34
     if (gpu_blocks_per_file <= 0) throw std::invalid_argument("TensorCopier: gpu_blocks_per_file must be > 0");
     std::vector<const void*> ptrs;
@@ -48,6 +47,13 @@ class StorageOffloadEngine {
     o.max_write_queued_seconds = max_write_queued_seconds;
     o.tier = tier;
     o.host_arena_bytes = host_arena_bytes;
+    // parse_gds_mode (gds_file_io.cpp:425-446): anything else means "disabled"
+    if (gds_mode == "read_only") o.gds_mode = KVB_GDS_READ;
+    else if (gds_mode == "write_only") o.gds_mode = KVB_GDS_WRITE;
+    else if (gds_mode == "read_write") o.gds_mode = KVB_GDS_READ | KVB_GDS_WRITE;
+    else if (gds_mode == "bb_read_only") o.gds_mode = KVB_GDS_READ | KVB_GDS_BOUNCE;
+    else if (gds_mode == "bb_write_only") o.gds_mode = KVB_GDS_WRITE | KVB_GDS_BOUNCE;
+    else if (gds_mode == "bb_read_write") o.gds_mode = KVB_GDS_READ | KVB_GDS_WRITE | KVB_GDS_BOUNCE;
     if (kvb_engine_create(pool_, &o, &eng_) != KVB_OK) {
       std::string msg = kvb_last_error();
       kvb_pool_destroy(pool_);

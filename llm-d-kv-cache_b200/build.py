@@ -69,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed building libkvb.so")
     cmd = [nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-lpthread", "-ldl", "-lrt"]
+           "-Xcompiler", "-fPIC", "-lpthread", "-ldl", "-lrt",
+           "-Xlinker", "--no-undefined"]  # a missing definition must fail the build, not the first dlopen on the GPU box
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         print(r.stdout)

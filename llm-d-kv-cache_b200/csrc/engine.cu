@@ -15,6 +15,8 @@
 //     blocks x tensors cudaMemcpyAsync calls of 16-64 KiB); loads are the inverse H2D -> scatter;
 //   * a host tier in pinned DRAM (KVB_TIER_HOST_ARENA) addressed by the same path strings, D2H lands
 //     directly in its final place (no staging copy on the host).
+#include <cufile.h>  // types only: the library is loaded at run time (the reference does the same, cufile_loader.hpp)
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
@@ -288,6 +290,60 @@ static bool file_rw(int fd, uint8_t* p, int64_t n, int64_t off, bool is_write, i
   return ok.load();
 }
 
+// ---------------------------------------------------------------------------------- cuFile (GDS tier)
+// libcufile is resolved with dlopen so that libkvb.so has no hard dependency on it; the driver is opened once per
+// process and left open.  Without the nvidia-fs kernel module cuFile runs in its compatibility mode (POSIX I/O through
+// its own bounce buffers) — same calls, same file bytes.
+struct CuFile {
+  bool ok = false;
+  CUfileError_t (*DriverOpen)() = nullptr;
+  CUfileError_t (*HandleRegister)(CUfileHandle_t*, CUfileDescr_t*) = nullptr;
+  void (*HandleDeregister)(CUfileHandle_t) = nullptr;
+  CUfileError_t (*BufRegister)(const void*, size_t, int) = nullptr;
+  CUfileError_t (*BufDeregister)(const void*) = nullptr;
+  ssize_t (*Read)(CUfileHandle_t, void*, size_t, off_t, off_t) = nullptr;
+  ssize_t (*Write)(CUfileHandle_t, const void*, size_t, off_t, off_t) = nullptr;
+  std::string why;
+
+  static CuFile& get() {
+    static CuFile c;
+    static std::once_flag once;
+    std::call_once(once, [] { c.load(); });
+    return c;
+  }
+
+ private:
+  void load() {
+    void* lib = nullptr;
+    for (const char* name : {"libcufile.so.0", "libcufile.so", "/usr/local/cuda/lib64/libcufile.so.0"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      why = "libcufile not found";
+      return;
+    }
+    auto sym = [&](const char* n) { return dlsym(lib, n); };
+    DriverOpen = reinterpret_cast<decltype(DriverOpen)>(sym("cuFileDriverOpen"));
+    HandleRegister = reinterpret_cast<decltype(HandleRegister)>(sym("cuFileHandleRegister"));
+    HandleDeregister = reinterpret_cast<decltype(HandleDeregister)>(sym("cuFileHandleDeregister"));
+    BufRegister = reinterpret_cast<decltype(BufRegister)>(sym("cuFileBufRegister"));
+    BufDeregister = reinterpret_cast<decltype(BufDeregister)>(sym("cuFileBufDeregister"));
+    Read = reinterpret_cast<decltype(Read)>(sym("cuFileRead"));
+    Write = reinterpret_cast<decltype(Write)>(sym("cuFileWrite"));
+    if (!DriverOpen || !HandleRegister || !HandleDeregister || !Read || !Write) {
+      why = "libcufile lacks a required symbol";
+      return;
+    }
+    const CUfileError_t st = DriverOpen();
+    if (st.err != CU_FILE_SUCCESS) {
+      why = "cuFileDriverOpen failed (" + std::to_string((int)st.err) + ")";
+      return;
+    }
+    ok = true;
+  }
+};
+
 }  // namespace kvb
 
 using namespace kvb;
@@ -307,6 +363,7 @@ struct kvb_engine {
     cudaStream_t stream = nullptr;
     uint8_t* d_packed = nullptr;
     uint8_t* h_stage = nullptr;  // file tier only
+    bool packed_registered = false;  // d_packed registered with cuFile
     int64_t* d_ids = nullptr;
     int64_t* h_ids = nullptr;
     bool ready = false;
@@ -359,6 +416,15 @@ struct kvb_engine {
   bool run_load(Worker& w, ChunkTask& t);
   bool write_file(const FilePart& f, const uint8_t* payload, int parts);
   bool read_file(const FilePart& f, uint8_t* payload, int parts);
+  // GDS tier: the reference's GDS file format (gds_file_io.cpp:238-418: n x block_bytes, head-aligned, tmp + rename),
+  // ONE cuFile call per file between the file and the worker's packed HBM chunk
+  // When cuFile cannot register a file (observed on the GPU boxes' overlay and tmpfs mounts: CU_FILE_INTERNAL_ERROR),
+  // the same file format moves through the worker's pinned staging buffer instead; cufile_broken makes that sticky.
+  bool gds_read = false, gds_write = false;
+  std::atomic<bool> cufile_broken{false};
+  std::atomic<int64_t> cufile_files{0}, gds_staged_files{0};
+  bool gds_write_file(Worker& w, const FilePart& f, int64_t dev_off);
+  bool gds_read_file(Worker& w, const FilePart& f, int64_t dev_off);
   int submit(int64_t job_id, int32_t n_files, const char* const* files, const int64_t* ids, const int64_t* off,
              void* caller_stream, bool is_store);
 };
@@ -373,8 +439,102 @@ bool kvb_engine::worker_init(Worker& w) {
   if (opts.tier == KVB_TIER_FILE &&
       cudaHostAlloc(&w.h_stage, chunk, cudaHostAllocDefault) != cudaSuccess)
     return false;
+  if ((gds_read || gds_write) && CuFile::get().BufRegister)  // optional: unregistered buffers go through cuFile's own
+    w.packed_registered = CuFile::get().BufRegister(w.d_packed, chunk, 0).err == CU_FILE_SUCCESS;
   w.ready = true;
   return true;
+}
+
+static int open_direct(const std::string& path, int flags, mode_t mode) {
+  int fd = ::open(path.c_str(), flags | O_DIRECT, mode);  // gds_file_io.cpp:262,352 open with O_DIRECT
+  if (fd < 0 && errno == EINVAL) fd = ::open(path.c_str(), flags, mode);  // file systems without O_DIRECT
+  return fd;
+}
+
+bool kvb_engine::gds_write_file(Worker& w, const FilePart& f, int64_t dev_off) {
+  CuFile& cf = CuFile::get();
+  const std::string& target = f.path;
+  size_t pos = target.find_last_of('/');
+  if (pos != std::string::npos && !mkdirs(target.substr(0, pos))) return false;
+  const std::string tmp = target + tmp_suffix + std::to_string((uintptr_t)(w.d_packed + dev_off) & 0xffffff);
+  int fd = open_direct(tmp, O_RDWR | O_CREAT | O_TRUNC, 0644);  // O_RDWR: cuFile needs it even to write (:260-262)
+  if (fd < 0) return false;
+  const int64_t bytes = (int64_t)f.ids.size() * block_bytes;
+  bool ok = false, via_cufile = false;
+  if (!cufile_broken.load()) {
+    CUfileDescr_t descr;
+    std::memset(&descr, 0, sizeof(descr));
+    descr.handle.fd = fd;
+    descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+    CUfileHandle_t h;
+    if (cf.HandleRegister(&h, &descr).err == CU_FILE_SUCCESS) {
+      via_cufile = ok = true;
+      int64_t done = 0;
+      while (ok && done < bytes) {  // one call in practice; the loop only covers short writes
+        const ssize_t n = cf.Write(h, w.d_packed, (size_t)(bytes - done), (off_t)done, (off_t)(dev_off + done));
+        if (n <= 0) ok = false;
+        else done += n;
+      }
+      cf.HandleDeregister(h);
+    } else {
+      cufile_broken = true;
+    }
+  }
+  if (!via_cufile) {  // same bytes through the pinned staging buffer (O_DIRECT wants aligned I/O: reopen buffered)
+    ::close(fd);
+    fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    ok = fd >= 0 &&
+         cudaMemcpyAsync(w.h_stage + dev_off, w.d_packed + dev_off, (size_t)bytes, cudaMemcpyDeviceToHost, w.stream) ==
+             cudaSuccess &&
+         cudaStreamSynchronize(w.stream) == cudaSuccess && write_all(fd, w.h_stage + dev_off, bytes, 0);
+    d2h += bytes;
+    gds_staged_files++;
+  } else {
+    cufile_files++;
+  }
+  if (fd >= 0) ok = (::close(fd) == 0) && ok;
+  if (ok && ::rename(tmp.c_str(), target.c_str()) != 0) ok = false;
+  if (!ok) ::unlink(tmp.c_str());
+  return ok;
+}
+
+bool kvb_engine::gds_read_file(Worker& w, const FilePart& f, int64_t dev_off) {
+  CuFile& cf = CuFile::get();
+  const int64_t bytes = (int64_t)f.ids.size() * block_bytes;  // the FIRST n blocks of the file (:386-414)
+  if (!cufile_broken.load()) {
+    int fd = open_direct(f.path, O_RDONLY, 0);
+    if (fd < 0) return false;
+    CUfileDescr_t descr;
+    std::memset(&descr, 0, sizeof(descr));
+    descr.handle.fd = fd;
+    descr.type = CU_FILE_HANDLE_TYPE_OPAQUE_FD;
+    CUfileHandle_t h;
+    if (cf.HandleRegister(&h, &descr).err == CU_FILE_SUCCESS) {
+      bool ok = true;
+      int64_t done = 0;
+      while (ok && done < bytes) {
+        const ssize_t n = cf.Read(h, w.d_packed, (size_t)(bytes - done), (off_t)done, (off_t)(dev_off + done));
+        if (n <= 0) ok = false;  // 0 = short file
+        else done += n;
+      }
+      cf.HandleDeregister(h);
+      ::close(fd);
+      cufile_files++;
+      return ok;
+    }
+    ::close(fd);
+    cufile_broken = true;
+  }
+  int fd = ::open(f.path.c_str(), O_RDONLY);
+  if (fd < 0) return false;
+  bool ok = read_all(fd, w.h_stage + dev_off, bytes, 0);
+  ::close(fd);
+  if (ok)
+    ok = cudaMemcpyAsync(w.d_packed + dev_off, w.h_stage + dev_off, (size_t)bytes, cudaMemcpyHostToDevice, w.stream) ==
+         cudaSuccess;  // ordered before the scatter on the same stream
+  h2d += bytes;
+  gds_staged_files++;
+  return ok;
 }
 
 // reference on-disk format, CPU path: full-size file, payload tail-aligned inside the bpf slots
@@ -448,14 +608,16 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
   auto t0 = std::chrono::steady_clock::now();
   bool ok = true;
   cudaError_t e = cudaSuccess;
+  const bool gds_w = opts.tier == KVB_TIER_FILE && gds_write;  // files leave from the packed HBM chunk, no host leg
+  const bool direct = opts.direct_host_io && !gds_w;
   if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);  // KV produced on the caller's stream
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
-  if (e == cudaSuccess && !opts.direct_host_io) {
+  if (e == cudaSuccess && !direct) {
     ok = launch_gather(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
     kernels++;
   }
-  if (e == cudaSuccess && ok) {
+  if (e == cudaSuccess && ok && !gds_w) {
     // merge destinations that are contiguous on the host into one run
     size_t i = 0;
     while (i < dests.size() && e == cudaSuccess && ok) {
@@ -465,7 +627,7 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
         ++j;
         bytes += (int64_t)dests[j].f->ids.size() * block_bytes;
       }
-      if (opts.direct_host_io) {
+      if (direct) {
         // fused gather + D2H: the kernel's bulk stores land in the pinned host run (UVA), no HBM staging, no memcpy
         ok = launch_gather(pool, w.d_ids + dests[i].first_block, bytes / block_bytes, dests[i].host, w.stream,
                            opts.copy_flags) == KVB_OK;
@@ -489,7 +651,9 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
   } else if (ok) {
     for (auto& d : dests) {
       if (t.job->cancelled.load()) break;  // in-flight cancelled job skips the file write (storage_offload.cpp:228-229)
-      if (!write_file(*d.f, d.host, t.io_parts)) {
+      const bool wrote = gds_w ? gds_write_file(w, *d.f, d.first_block * block_bytes)
+                               : write_file(*d.f, d.host, t.io_parts);
+      if (!wrote) {
         set_error("store: writing %s failed: %s", d.f->path.c_str(), std::strerror(errno));
         ok = false;
       }
@@ -513,6 +677,8 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
   std::vector<Src> srcs;
   int64_t n = 0;
   bool ok = true;
+  const bool gds_r = opts.tier == KVB_TIER_FILE && gds_read;  // files land in the packed HBM chunk, no host leg
+  const bool direct = opts.direct_host_io && !gds_r;
   for (auto& f : t.files) {
     const int64_t nb = (int64_t)f.ids.size();
     if (nb == 0) continue;
@@ -527,7 +693,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       srcs.push_back({&f, src, n});
     } else {
       uint8_t* dst = w.h_stage + n * block_bytes;
-      if (!read_file(f, dst, t.io_parts)) {
+      if (gds_r ? !gds_read_file(w, f, n * block_bytes) : !read_file(f, dst, t.io_parts)) {
         set_error("load: reading %s failed", f.path.c_str());
         ok = false;
         continue;
@@ -542,7 +708,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
     if (t.ready) e = cudaStreamWaitEvent(w.stream, t.ready, 0);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
-    size_t i = 0;
+    size_t i = gds_r ? srcs.size() : 0;  // GDS: the bytes are in d_packed already
     while (i < srcs.size() && e == cudaSuccess) {
       size_t j = i;
       int64_t bytes = (int64_t)srcs[i].f->ids.size() * block_bytes;
@@ -550,7 +716,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
         ++j;
         bytes += (int64_t)srcs[j].f->ids.size() * block_bytes;
       }
-      if (opts.direct_host_io) {
+      if (direct) {
         // fused H2D + scatter: the kernel's bulk loads read the pinned host run directly
         if (launch_scatter(pool, w.d_ids + srcs[i].first_block, bytes / block_bytes, srcs[i].host, w.stream,
                            opts.copy_flags) != KVB_OK)
@@ -564,7 +730,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       i = j + 1;
     }
     bool moved = true;
-    if (e == cudaSuccess && !opts.direct_host_io) {
+    if (e == cudaSuccess && !direct) {
       moved = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
       kernels++;
     }
@@ -638,6 +804,8 @@ void kvb_engine::worker_loop(Worker* w) {
 void kvb_engine::worker_release(Worker& w) {
   cudaSetDevice(device);
   if (w.stream) cudaStreamSynchronize(w.stream);
+  if (w.packed_registered && CuFile::get().BufDeregister) CuFile::get().BufDeregister(w.d_packed);
+  w.packed_registered = false;
   if (w.d_packed) cudaFree(w.d_packed);
   if (w.d_ids) cudaFree(w.d_ids);
   if (w.h_ids) cudaFreeHost(w.h_ids);
@@ -733,6 +901,8 @@ void kvb_engine_default_opts(kvb_engine_opts_t* o) {
   o->chunk_bytes = 64ll << 20;
   o->direct_host_io = 0;
   o->strict_load_errors = 0;
+  o->gds_mode = KVB_GDS_DISABLED;
+  o->reserved = 0;
 }
 
 int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engine_t** out) {
@@ -761,6 +931,16 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
       return KVB_ERR_CUDA;
     }
     e->local_cpus = gpu_local_cpus(e->device);
+    if (opts->tier == KVB_TIER_FILE && (opts->gds_mode & (KVB_GDS_READ | KVB_GDS_WRITE))) {
+      cudaFree(nullptr);  // cuFileDriverOpen wants a CUDA context
+      if (CuFile::get().ok) {
+        e->gds_read = (opts->gds_mode & KVB_GDS_READ) != 0;
+        e->gds_write = (opts->gds_mode & KVB_GDS_WRITE) != 0;
+      } else {  // storage_offload.cpp:129-134: warn and use CPU staging for both directions
+        fprintf(stderr, "[kvb][WARN] GDS requested but unavailable (%s): falling back to CPU staging\n",
+                CuFile::get().why.c_str());
+      }
+    }
     if (opts->tier == KVB_TIER_HOST_ARENA) {
       KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
       int rc = e->arena.init(e->device, opts->host_arena_bytes);  // pinned and first-touched on the GPU-local node

@@ -20,16 +20,18 @@ class StorageOffloadEngine:
     extensions select the B200-native host tier:
       tier="file"        reference on-disk format under the given file paths (default, drop-in)
       tier="host_arena"  pinned host DRAM arena of ``host_arena_bytes`` keyed by the same path strings
+    ``gds_mode`` (file tier) takes the reference's strings (gds_file_io.cpp:425-446): reads and/or writes then use its
+    GDS file format (head-aligned, exactly n x block_bytes) through cuFile on the packed HBM chunk, one call per file;
+    without a usable cuFile the same format goes through the pinned staging buffer.
     """
 
     def __init__(self, io_threads: int, gpu_blocks_per_file: int, tensors: Sequence, read_preferring_workers: int,
                  gds_mode: str = "disabled", max_write_queued_seconds: float = 10.0, *, tier: str = "file",
                  host_arena_bytes: int = 0, chunk_bytes: int = 0, copy_variant: int = 0,
                  strict_load_errors: bool = False, direct_host_io: bool = False):
-        if gds_mode != "disabled":
-            # GDS file tier is SURVEY §8(f) "next"; the reference itself falls back to the CPU
-            # staging path when GDS is unavailable (storage_offload.cpp:129-134).
-            gds_mode = "disabled"
+        # reference parse_gds_mode (gds_file_io.cpp:425-446): unknown strings mean "disabled"
+        gds_bits = {"read_only": 1, "write_only": 2, "read_write": 3, "bb_read_only": 5, "bb_write_only": 6,
+                    "bb_read_write": 7}.get(gds_mode, 0)
         lib = _lib.load()
         self.pool = tensors if isinstance(tensors, KVPool) else KVPool(tensors)
         opts = EngineOpts()
@@ -45,6 +47,7 @@ class StorageOffloadEngine:
             opts.chunk_bytes = int(chunk_bytes)
         opts.strict_load_errors = 1 if strict_load_errors else 0
         opts.direct_host_io = 1 if direct_host_io else 0
+        opts.gds_mode = gds_bits if tier == "file" else 0
         h = C.c_void_p()
         check(lib.kvb_engine_create(self.pool.handle, C.byref(opts), C.byref(h)))
         self._h = h
