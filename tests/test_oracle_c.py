@@ -54,3 +54,42 @@ def test_c_score_matches_python_oracle():
         got = {str(int(out_p[p * 13 + j])): float(out_s[p * 13 + j]) for j in range(int(out_n[p]))}
         assert got == want
     lib.kvo_index_free(ix)
+
+
+def test_c_hash_short_parents_and_extras_match_python_oracle():
+    """The C restatement is the checker of the GPU fuzz (tests/soak_hash.py) for short parent heads and pre-encoded
+    multimodal extras: it must agree with the golden-pinned Python oracle on exactly those."""
+    rng = np.random.default_rng(8)
+    for bs in (4, 8, 16, 17):
+        otp = o.TokenProcessor(bs)
+        prompts, parents, feats = [], [], []
+        for i in range(24):
+            n = int(rng.integers(0, 6 * bs))
+            prompts.append(rng.integers(0, 1 << int(rng.choice([5, 8, 16, 17, 32])), n, dtype=np.uint64).astype(np.uint32))
+            cands = [0, 1, 23, 24, 255, 256, 65535, 65536, (1 << 32) - 1, 1 << 32, (1 << 64) - 1]
+            parents.append(cands[int(rng.integers(0, len(cands)))])
+            nk = n // bs
+            if i % 3 == 0 or nk == 0:
+                feats.append(None)
+            else:
+                feats.append([None if rng.random() < 0.5 else
+                              o.BlockExtraFeatures([o.MMHash("h%d-%d" % (i, int(rng.integers(0, 99)))) for _ in range(int(rng.integers(1, 3)))])
+                              for _ in range(nk)])
+        off = np.zeros(len(prompts) + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in prompts], out=off[1:])
+        # pre-encoded X(extra) per block, empty = nil (what the product hands to the device)
+        chunks = []
+        for p, f in zip(prompts, feats):
+            for b in range(len(p) // bs):
+                ef = None if f is None else f[b]
+                chunks.append(b"" if ef is None else o.encode_extra_suffix(ef))
+        eoff = np.zeros(len(chunks) + 1, dtype=np.int64)
+        np.cumsum([len(c) for c in chunks], out=eoff[1:])
+        extra = np.frombuffer(b"".join(chunks) or b"\0", dtype=np.uint8).copy()
+        keys, koff = oc.hash_batch(np.concatenate(prompts) if off[-1] else np.zeros(0, np.uint32), off,
+                                   np.asarray(parents, dtype=np.uint64), bs, extra, eoff, threads=3)
+        for i, p in enumerate(prompts):
+            want = otp.tokens_to_kv_block_keys(parents[i], [int(x) for x in p], "m", feats[i]) or []
+            if parents[i] == 0:
+                continue       # parent 0 means "start from the model's init hash" in the Python API, not a literal parent
+            assert [int(k) for k in keys[koff[i]:koff[i + 1]]] == want, (bs, i)
