@@ -77,3 +77,20 @@ def test_block_streams_of_the_kernel_shape():
                 stream += [0x1A] + list(t.to_bytes(4, "big"))
         stream += [0xF6]
         assert len(stream) <= 92 and wpc(stream) == fnv(stream)
+
+
+def test_three_redux_limb_split_is_exact():
+    """Planned change: sum the 32 lanes' 64-bit terms with THREE redux.sync.add.u32 instead of
+    four — 27-bit low limbs of both halves, and the two 5-bit tops packed into one word (10-bit fields: 32 * 31 < 1024)."""
+    rng = random.Random(5)
+    m27 = (1 << 27) - 1
+    for _ in range(300):
+        terms = [rng.getrandbits(64) if rng.random() < 0.9 else M for _ in range(32)]
+        lo = [t & 0xFFFFFFFF for t in terms]
+        hi = [t >> 32 for t in terms]
+        a = sum(x & m27 for x in lo)                                   # redux 1 (< 2^32: no wrap)
+        b = sum((x >> 27) | ((y >> 27) << 10) for x, y in zip(lo, hi))  # redux 2, two 10-bit fields
+        c = sum(y & m27 for y in hi)                                   # redux 3
+        assert a < 1 << 32 and b < 1 << 32 and c < 1 << 32
+        total = (a + ((b & 0x3FF) << 27) + ((c + ((b >> 10) << 27)) << 32)) & M
+        assert total == sum(terms) & M
