@@ -94,3 +94,33 @@ def test_three_redux_limb_split_is_exact():
         assert a < 1 << 32 and b < 1 << 32 and c < 1 << 32
         total = (a + ((b & 0x3FF) << 27) + ((c + ((b >> 10) << 27)) << 32)) & M
         assert total == sum(terms) & M
+
+
+def test_round_without_the_shift():
+    """Planned change: keep C_j = (resolved low bits of z_j) * 0xb3 as an accumulator and add
+    zeta * (0xb3 << k) per round, zeta = the newly resolved bit taken from the popcount's bit 0 — the parity then needs no
+    shift on the vote -> popc -> vote chain.  Must resolve the same z bytes as the shipped formulation."""
+    rng = random.Random(6)
+    for _ in range(300):
+        m = rng.randrange(0, 97)
+        stream = [rng.randrange(256) for _ in range(m)]
+        b = [[stream[3 * L + j] if 3 * L + j < m else 0 for j in range(3)] for L in range(32)]
+        C = [[0, 0, 0] for _ in range(32)]
+        z = [[0, 0, 0] for _ in range(32)]
+        for k in range(8):
+            t = [[((C[L][j] >> k) ^ (b[L][j] >> k)) & 1 for j in range(3)] for L in range(32)]
+            votes = sum((t[L][0] ^ t[L][1] ^ t[L][2]) << L for L in range(32))
+            l0k = ((H0 & 0xFF) >> k) & 1
+            for L in range(32):
+                par = bin(votes & ((1 << L) - 1)).count("1")            # only bit 0 is used
+                local = [0, t[L][0], t[L][0] ^ t[L][1]]
+                for j in range(3):
+                    pre = l0k ^ local[j] ^ ((b[L][j] >> k) & 1)         # prepared while the vote is in flight
+                    zeta = (pre ^ par) & 1
+                    C[L][j] += zeta * (0xB3 << k)
+                    z[L][j] |= zeta << k
+        # z must be the xor of the running low byte and the stream byte at every position
+        h = H0
+        for i, byte in enumerate(stream):
+            assert z[i // 3][i % 3] == (h & 0xFF) ^ byte
+            h = ((h ^ byte) * P) & M
