@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KVB_ABI_VERSION 2
+#define KVB_ABI_VERSION 3
 
 #define KVB_OK 0
 #define KVB_ERR_INVALID (-1)   /* bad argument */
@@ -106,8 +106,12 @@ typedef struct kvb_engine_opts {
                                       a chunk always holds whole files */
   int32_t direct_host_io;          /* 1 = the gather/scatter kernels read/write the pinned host buffers directly
                                       (fused gather+D2H / H2D+scatter, no HBM staging, no cudaMemcpy); 0 = staged */
-  int32_t strict_load_errors;      /* 0 = reference behaviour: a failed load still reports ok (storage_offload.cpp:378-383);
-                                      1 = report ok=0 */
+  int32_t strict_load_errors;      /* file tier only.  0 = reference behaviour: a FILE that is missing / short / unreadable is
+                                      logged and the job still reports ok (storage_offload.cpp:378-383); 1 = report ok=0.
+                                      Anything else that kept pages from being restored — a host-arena miss (the arena's own
+                                      LRU dropped the entry), a CUDA error, a failed launch — ALWAYS reports ok=0.  Worker
+                                      resources are allocated inside kvb_engine_create: if io_threads x chunk_bytes does not
+                                      fit, create fails with KVB_ERR_NOMEM */
   int32_t gds_mode;                /* KVB_GDS_* bits, file tier only: reference gds_mode (gds_file_io.cpp:425-446).  Files
                                       are then the reference's GDS format (head-aligned, n x block_bytes long) moved by
                                       cuFile between the file and the packed HBM chunk, ONE call per file.  Falls back to
@@ -137,6 +141,10 @@ int kvb_engine_poll(kvb_engine_t* eng, int64_t* job_ids, int32_t* ok, int32_t ca
 int kvb_engine_wait(kvb_engine_t* eng, int64_t job_id);
 /* manager-side lookup (llmd_fs_backend/manager.py:43-53): 1 if the file/arena entry exists */
 int kvb_engine_exists(kvb_engine_t* eng, const char* file);
+/* SharedStorageOffloadingManager.lookup in ONE call (manager.py:43-53): the number of CONSECUTIVE entries of files[]
+ * from the start that exist — the loop stops at the first miss, like the reference's.  Arena tier: hash-map probes
+ * under one lock; file tier: one statx per file, nothing else (no Python, no per-block FFI crossing). */
+int kvb_engine_lookup_prefix(kvb_engine_t* eng, int32_t n_files, const char* const* files, int32_t* out_hits);
 /* drop every host-arena entry (test / bench helper) */
 int kvb_engine_arena_clear(kvb_engine_t* eng);
 
@@ -206,8 +214,22 @@ int kvb_index_add(kvb_index_t* idx, const uint64_t* engine_keys, int64_t n_engin
 int kvb_index_evict(kvb_index_t* idx, uint64_t key, int key_type, const kvb_pod_entry_t* entries, int32_t n_entries);
 int kvb_index_get_request_key(kvb_index_t* idx, uint64_t engine_key, uint64_t* out);
 int64_t kvb_index_num_keys(kvb_index_t* idx);
-/* push pending host-side mutations to the device table (lookups do this implicitly) */
+/* apply the queued Add / Evict operations to the device table and wait for it (reads do this implicitly) */
 int kvb_index_flush(kvb_index_t* idx, void* stream);
+
+/* The index is device-authoritative: buckets, per-key pod lists and the outer LRU order (one recency stamp per slot)
+ * live in HBM and are mutated by kernels; the host keeps only the engine-key map.  Counters for tests and the bench. */
+typedef struct kvb_index_stats {
+  int64_t live_keys, tombstones, table_slots, engine_keys;
+  int64_t ops_applied;        /* Add / Evict records applied on the device */
+  int64_t flushes_parallel;   /* sorted, one thread per distinct key */
+  int64_t flushes_sequential; /* one thread in the reference's order (tiny batches, or the index is at capacity) */
+  int64_t rehashes;           /* device-side table growth / tombstone purge */
+  int64_t lru_evictions;      /* keys dropped because the index held `max_keys` (in_memory.go:197) */
+  int64_t order_builds, order_stale_skipped, order_scans; /* LRU order array: sorts, stale records skipped, fallbacks */
+  float last_hash_us, last_score_us; /* device time of the last scoring call made with KVB_SCORE_TIME_KERNELS */
+} kvb_index_stats_t;
+int kvb_index_get_stats(kvb_index_t* idx, kvb_index_stats_t* out);
 
 /* Lookup (in_memory.go:107-148) on the device.  pod_filter: interned ids (n_filter = 0 => all pods).
  * out_counts[i]: -1 key absent, otherwise number of entries written to
@@ -219,7 +241,11 @@ int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const ui
 /* Batched Lookup + Score for many prompts: keys HOST uint64 flat, key_off HOST int64[n_prompts+1].
  * Per prompt up to KVB_INDEX_MAX_PODS_PER_KEY (pod, score) pairs: out_n[p] pairs in
  * out_pods/out_scores[p*KVB_INDEX_MAX_PODS_PER_KEY ...].  Scores are float64 sums in key order. */
-#define KVB_SCORE_TOUCH_LRU 1 /* refresh outer-LRU recency of every found key, as Lookup's data.Get does (in_memory.go:120) */
+/* flags.  Every found key's outer-LRU recency is refreshed BY DEFAULT, as Lookup's data.Get does (in_memory.go:120):
+ * the scoring kernel stamps the slot, the host does nothing. */
+#define KVB_SCORE_TOUCH_LRU 1    /* accepted for source compatibility; this is the default now */
+#define KVB_SCORE_NO_TOUCH 2     /* opt out: read-only scoring (e.g. what-if queries that must not disturb eviction order) */
+#define KVB_SCORE_TIME_KERNELS 4 /* record CUDA events around the kernels; read them with kvb_index_get_stats */
 int kvb_index_score_batch(kvb_index_t* idx, const uint64_t* keys, const int64_t* key_off, int32_t n_prompts,
                           const uint16_t* pod_filter, int32_t n_filter, int32_t flags, int32_t* out_n,
                           uint16_t* out_pods, double* out_scores);
@@ -230,7 +256,8 @@ int kvb_index_score_tokens_batch(kvb_index_t* idx, const uint32_t* tokens, const
                                  const uint64_t* parents, int32_t n_prompts, int32_t block_size, const uint8_t* extra,
                                  const int64_t* extra_off, const uint16_t* pod_filter, int32_t n_filter,
                                  int32_t flags, int32_t* out_n, uint16_t* out_pods, double* out_scores);
-/* debug / CPU-testable: host-side image of one key (entries oldest->newest); returns count or -1 if absent */
+/* debug: the entries of one key (oldest->newest) read back from the device WITHOUT refreshing its recency;
+ * returns the count or -1 if absent */
 int kvb_index_host_peek(kvb_index_t* idx, uint64_t request_key, kvb_pod_entry_t* out_entries, int32_t cap);
 
 /* ------------------------------------------------------------------------------------------

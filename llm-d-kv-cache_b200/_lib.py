@@ -9,11 +9,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkvb.so")
 
 KVB_OK = 0
+ABI_VERSION = 3
 COPY_DEFAULT, COPY_LDG, COPY_BULK = 0, 1, 2
 TIER_FILE, TIER_HOST_ARENA = 0, 1
 MAX_PODS_PER_KEY = 13
 KEY_ENGINE, KEY_REQUEST = 0, 1
-SCORE_TOUCH_LRU = 1
+SCORE_TOUCH_LRU, SCORE_NO_TOUCH, SCORE_TIME_KERNELS = 1, 2, 4
 
 
 class KvbError(RuntimeError):
@@ -36,6 +37,13 @@ class EngineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "bytes_stored", "bytes_loaded", "files_stored", "files_loaded", "files_skipped_existing",
         "writes_dropped", "load_failures", "kernels_launched", "h2d_bytes", "d2h_bytes")]
+
+
+class IndexStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "live_keys", "tombstones", "table_slots", "engine_keys", "ops_applied", "flushes_parallel",
+        "flushes_sequential", "rehashes", "lru_evictions", "order_builds", "order_stale_skipped", "order_scans")] + [
+        ("last_hash_us", C.c_float), ("last_score_us", C.c_float)]
 
 
 class PodEntryC(C.Structure):
@@ -73,6 +81,7 @@ SIGNATURES = {
     "kvb_engine_poll": (C.c_int, [_vp, _P(_i64), _P(_i32), _i32]),
     "kvb_engine_wait": (C.c_int, [_vp, _i64]),
     "kvb_engine_exists": (C.c_int, [_vp, C.c_char_p]),
+    "kvb_engine_lookup_prefix": (C.c_int, [_vp, _i32, _P(C.c_char_p), _P(_i32)]),
     "kvb_engine_arena_clear": (C.c_int, [_vp]),
     "kvb_engine_get_stats": (C.c_int, [_vp, _P(EngineStats)]),
     "kvb_fnv64a": (_u64, [_vp, C.c_size_t]),
@@ -87,6 +96,7 @@ SIGNATURES = {
     "kvb_index_get_request_key": (C.c_int, [_vp, _u64, _P(_u64)]),
     "kvb_index_num_keys": (_i64, [_vp]),
     "kvb_index_flush": (C.c_int, [_vp, _vp]),
+    "kvb_index_get_stats": (C.c_int, [_vp, _P(IndexStats)]),
     "kvb_index_lookup": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _P(_i64)]),
     "kvb_index_score_batch": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "kvb_index_score_tokens_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32,
@@ -112,14 +122,21 @@ def load() -> C.CDLL:
             f"{LIB_PATH} is missing: build it with `python llm-d-kv-cache_b200/build.py` "
             "(nvcc, sm_100a).  There is no CPU fallback for this path.")
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError => ABI mismatch, fail loudly
-        fn.restype = res
-        fn.argtypes = args
-    if lib.kvb_abi_version() != 2:
-        raise ImportError(f"libkvb ABI version {lib.kvb_abi_version()} != 2")
+    bind(lib)  # AttributeError => ABI mismatch, fail loudly
+    if lib.kvb_abi_version() != ABI_VERSION:
+        raise ImportError(f"libkvb ABI version {lib.kvb_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def bind(lib, names=None) -> None:
+    """Attach restype / argtypes of the declared entry points to a loaded library."""
+    for name, (res, args) in SIGNATURES.items():
+        if names is not None and name not in names:
+            continue
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
 
 
 def check(rc: int) -> int:

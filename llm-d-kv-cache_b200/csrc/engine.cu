@@ -107,6 +107,16 @@ class Arena {
     auto it = entries.find(k);
     return it != entries.end() && it->second.valid;
   }
+  int32_t count_prefix(const char* const* keys, int32_t n) {  // consecutive valid entries from the start, one lock
+    std::lock_guard<std::mutex> lk(mu);
+    int32_t hits = 0;
+    for (; hits < n; ++hits) {
+      if (!keys[hits]) break;
+      auto it = entries.find(keys[hits]);
+      if (it == entries.end() || !it->second.valid) break;
+    }
+    return hits;
+  }
   void clear() {  // drops every entry that is not pinned by an in-flight store or load
     std::lock_guard<std::mutex> lk(mu);
     for (auto it = entries.begin(); it != entries.end();) {
@@ -369,6 +379,13 @@ struct kvb_engine {
     bool ready = false;
   };
   std::vector<std::unique_ptr<Worker>> workers;
+  // every worker allocates its stream / staging when its thread starts; kvb_engine_create waits for all of them, so an
+  // allocation failure is a constructor error and never a silently failing load later
+  std::mutex init_mu;
+  std::condition_variable init_cv;
+  int init_done = 0;
+  bool init_failed = false;
+  std::string init_error;
 
   std::mutex qmu;
   std::condition_variable qcv;
@@ -413,7 +430,11 @@ struct kvb_engine {
   void worker_release(Worker& w);
   void worker_loop(Worker* w);
   bool run_store(Worker& w, ChunkTask& t);
-  bool run_load(Worker& w, ChunkTask& t);
+  // load outcome: only kSoft (a file that is missing / short / unreadable) may be reported as success, and only in the
+  // file tier without strict_load_errors — that is the reference's swallow (storage_offload.cpp:378-383).  An arena
+  // miss, a CUDA error or a failed kernel launch always fails the job: nothing was restored.
+  enum LoadResult { kLoaded = 0, kSoft = 1, kHard = 2 };
+  LoadResult run_load(Worker& w, ChunkTask& t);
   bool write_file(const FilePart& f, const uint8_t* payload, int parts);
   bool read_file(const FilePart& f, uint8_t* payload, int parts);
   // GDS tier: the reference's GDS file format (gds_file_io.cpp:238-418: n x block_bytes, head-aligned, tmp + rename),
@@ -668,7 +689,7 @@ bool kvb_engine::run_store(Worker& w, ChunkTask& t) {
   return ok;
 }
 
-bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
+kvb_engine::LoadResult kvb_engine::run_load(Worker& w, ChunkTask& t) {
   struct Src {
     const FilePart* f;
     const uint8_t* host;
@@ -676,7 +697,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
   };
   std::vector<Src> srcs;
   int64_t n = 0;
-  bool ok = true;
+  bool soft = false, hard = false;
   const bool gds_r = opts.tier == KVB_TIER_FILE && gds_read;  // files land in the packed HBM chunk, no host leg
   const bool direct = opts.direct_host_io && !gds_r;
   for (auto& f : t.files) {
@@ -685,17 +706,19 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
     if (opts.tier == KVB_TIER_HOST_ARENA) {
       const uint8_t* src = arena.pin_read(f.path, nb, block_bytes);
       if (!src) {
-        // the reference runs one task per file: a missing file fails alone, the others still load
+        // the arena's own LRU may have dropped the entry between the scheduler's lookup and this load: the pages were
+        // NOT restored, so the job must say so (the reference's swallow covers a vanished FILE, not this)
         set_error("load: %s not in host arena (or holds fewer than %lld blocks)", f.path.c_str(), (long long)nb);
-        ok = false;
+        hard = true;
         continue;
       }
       srcs.push_back({&f, src, n});
     } else {
       uint8_t* dst = w.h_stage + n * block_bytes;
       if (gds_r ? !gds_read_file(w, f, n * block_bytes) : !read_file(f, dst, t.io_parts)) {
+        // the reference runs one task per file: a missing file fails alone, the others still load
         set_error("load: reading %s failed", f.path.c_str());
-        ok = false;
+        soft = true;
         continue;
       }
       srcs.push_back({&f, dst, n});
@@ -709,6 +732,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(w.d_ids, w.h_ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, w.stream);
     size_t i = gds_r ? srcs.size() : 0;  // GDS: the bytes are in d_packed already
+    bool moved = true;
     while (i < srcs.size() && e == cudaSuccess) {
       size_t j = i;
       int64_t bytes = (int64_t)srcs[i].f->ids.size() * block_bytes;
@@ -720,7 +744,7 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
         // fused H2D + scatter: the kernel's bulk loads read the pinned host run directly
         if (launch_scatter(pool, w.d_ids + srcs[i].first_block, bytes / block_bytes, srcs[i].host, w.stream,
                            opts.copy_flags) != KVB_OK)
-          ok = false;
+          moved = false;
         kernels++;
       } else {
         e = cudaMemcpyAsync(w.d_packed + srcs[i].first_block * block_bytes, srcs[i].host, (size_t)bytes,
@@ -729,9 +753,8 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       h2d += bytes;
       i = j + 1;
     }
-    bool moved = true;
     if (e == cudaSuccess && !direct) {
-      moved = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK;
+      moved = launch_scatter(pool, w.d_ids, n, w.d_packed, w.stream, opts.copy_flags) == KVB_OK && moved;
       kernels++;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
@@ -744,18 +767,31 @@ bool kvb_engine::run_load(Worker& w, ChunkTask& t) {
       bytes_loaded += n * block_bytes;
       files_loaded += (int64_t)srcs.size();
     } else {
-      ok = false;
+      hard = true;
     }
   }
   if (opts.tier == KVB_TIER_HOST_ARENA)
     for (auto& s : srcs) arena.unpin(s.f->path);
-  if (!ok) load_failures++;
-  return ok;
+  if (soft || hard) load_failures++;
+  return hard ? kHard : (soft ? kSoft : kLoaded);
 }
 
 void kvb_engine::worker_loop(Worker* w) {
   bind_this_thread(local_cpus);
-  bool inited = false, init_failed = false;
+  const bool inited = worker_init(*w);
+  {
+    std::lock_guard<std::mutex> lk(init_mu);
+    ++init_done;
+    if (!inited) {
+      init_failed = true;
+      init_error = "engine worker: CUDA resource allocation failed (stream / packed HBM chunk / pinned staging)";
+    }
+  }
+  init_cv.notify_all();
+  if (!inited) {  // kvb_engine_create reports the failure and tears the engine down; this thread takes no task
+    worker_release(*w);
+    return;
+  }
   for (;;) {
     std::unique_ptr<ChunkTask> task;
     {
@@ -769,33 +805,26 @@ void kvb_engine::worker_loop(Worker* w) {
       q.pop_front();
       if (q_high.empty() && q_normal.empty() && opts.tier == KVB_TIER_FILE) task->io_parts = 4;
     }
-    if (!inited && !init_failed) {
-      inited = worker_init(*w);
-      if (!inited) {  // one attempt: release what was allocated, every task of this worker fails from now on
-        init_failed = true;
-        worker_release(*w);
-      }
-    }
-    if (init_failed) set_error("engine worker: CUDA resource allocation failed");
     bool ok = false;
-    if (inited) {
-      try {
-        ok = task->is_store ? run_store(*w, *task) : run_load(*w, *task);
-      } catch (...) {
-        set_error("exception in engine worker");
-        ok = false;
+    try {
+      if (task->is_store) {
+        ok = run_store(*w, *task);
+      } else {
+        const LoadResult r = run_load(*w, *task);
+        // reference parity (storage_offload.cpp:378-383): a FILE that could not be read is logged and the job still
+        // reports success — unless strict_load_errors; everything else that kept the pages from being restored fails
+        ok = r == kLoaded || (r == kSoft && !opts.strict_load_errors);
+        if (r != kLoaded)
+          fprintf(stderr, "[kvb][ERROR] load chunk of job %lld failed%s: %s\n", (long long)task->job->id,
+                  ok ? " (reported as success, reference parity)" : "", get_error());
       }
+    } catch (...) {
+      set_error("exception in engine worker");
+      ok = false;
     }
-    if (!ok)  // reference logs failures at ERROR level (storage_offload.cpp:330-346,399-410)
-      fprintf(stderr, "[kvb][ERROR] %s chunk of job %lld failed: %s\n", task->is_store ? "store" : "load",
-              (long long)task->job->id, get_error());
-    if (task->is_store) {
-      queued_store_files -= (int64_t)task->files.size();
-    } else if (!ok && !opts.strict_load_errors) {
-      // reference parity: read failures are swallowed, the job still reports success
-      // (storage_offload.cpp:378-383); opts.strict_load_errors != 0 (strict) reports them
-      ok = true;
-    }
+    if (!ok && task->is_store)  // reference logs failures at ERROR level (storage_offload.cpp:330-346)
+      fprintf(stderr, "[kvb][ERROR] store chunk of job %lld failed: %s\n", (long long)task->job->id, get_error());
+    if (task->is_store) queued_store_files -= (int64_t)task->files.size();
     task_done(task->job, ok);
   }
   worker_release(*w);
@@ -953,6 +982,20 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
       e->workers.push_back(std::move(w));
     }
     for (auto& w : e->workers) w->th = std::thread([eng = e.get(), wp = w.get()] { eng->worker_loop(wp); });
+    {  // worker resources (io_threads x chunk_bytes of HBM, the same again pinned in the file tier) are part of
+       // construction: if they do not fit, say so HERE, not through loads that quietly restore nothing
+      std::unique_lock<std::mutex> lk(e->init_mu);
+      e->init_cv.wait(lk, [&] { return e->init_done == (int)e->workers.size(); });
+      if (e->init_failed) {
+        const std::string why = e->init_error;
+        const long long per_worker = (long long)(e->blocks_per_chunk * e->block_bytes);
+        lk.unlock();
+        kvb_engine_destroy(e.release());
+        set_error("%s: %d workers x %lld bytes per worker do not fit; lower io_threads or chunk_bytes", why.c_str(),
+                  opts->io_threads, per_worker);
+        return KVB_ERR_NOMEM;
+      }
+    }
     *out = e.release();
     return KVB_OK;
   });
@@ -1028,6 +1071,26 @@ int kvb_engine_exists(kvb_engine_t* e, const char* file) {
     if (!e || !file) return 0;
     if (e->opts.tier == KVB_TIER_HOST_ARENA) return e->arena.exists(file) ? 1 : 0;
     return file_exists(file) ? 1 : 0;
+  });
+}
+
+int kvb_engine_lookup_prefix(kvb_engine_t* e, int32_t n_files, const char* const* files, int32_t* out_hits) {
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e && out_hits, "NULL argument");
+    KVB_REQUIRE(n_files >= 0 && (n_files == 0 || files), "bad file list");
+    *out_hits = 0;
+    if (e->opts.tier == KVB_TIER_HOST_ARENA) {
+      *out_hits = e->arena.count_prefix(files, n_files);
+      return KVB_OK;
+    }
+    int32_t hits = 0;
+    for (; hits < n_files; ++hits) {  // manager.py:49-53: stop at the first block that is not offloaded
+      if (!files[hits]) break;
+      struct statx sx;
+      if (::statx(AT_FDCWD, files[hits], AT_STATX_DONT_SYNC, 0, &sx) != 0) break;  // existence only: no attributes asked
+    }
+    *out_hits = hits;
+    return KVB_OK;
   });
 }
 

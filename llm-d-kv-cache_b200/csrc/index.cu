@@ -1,34 +1,59 @@
-// index.cu — kvblock index (request key -> pod entries) and longest-prefix scorer.
+// index.cu — kvblock index (request key -> pod entries) and longest-prefix scorer, DEVICE-AUTHORITATIVE.
 //
 // Replaces InMemoryIndex (pkg/kvcache/kvblock/in_memory.go:57-304) and
 // LongestPrefixScorer.Score (pkg/kvcache/kvblock_scorer.go:91-154).
 //
-// Split of work
-//   * MUTATIONS (Add / Evict / GetRequestKey; in_memory.go:154-304) arrive serially from the KV-event
-//     stream and carry exact LRU semantics (10 pods per key, `Size` keys, engine->request map).  They are
-//     applied to a host-side authoritative structure and recorded as dirty keys.
-//   * READS — Lookup (in_memory.go:107-148) and Score — run on the GPU against a device mirror:
-//     an open-addressing table of 64 B buckets {key, state|count, 13 x (pod:16 | tier:8 | spec:8)} in HBM.
-//     Dirty keys are pushed as 64 B bucket images by one upsert kernel before the next read.
-//   * Batched scoring: one warp per prompt.  32 keys are probed in parallel (random 64 B reads), their
-//     buckets staged in shared memory, then the serial prefix walk adds float64 weights in key order,
-//     which keeps the sums bit-identical to the Go loop (kvblock_scorer.go:132-150).
+// Where the state lives
+//   * request key -> pod entries: an open-addressing table of 64 B buckets {key, state|count, 13 x (pod:16|tier:8|spec:8)}
+//     in HBM, plus one 64-bit recency stamp per slot (ts[]).  There is NO host copy: Add / Evict are applied to the
+//     buckets by kernels, Lookup / Score read them, and the outer LRU of the reference (golang-lru, `Size` keys) is the
+//     order of the stamps — every operation that golang-lru would move to the front (`data.Get` in Lookup, Add and
+//     Evict) stamps the slot with a global sequence number handed out in the reference's operation order.
+//   * engine key -> request keys (in_memory.go:166-177): a flat hash map with an intrusive LRU list on the host; it is
+//     touched once per engine key of an event, never by reads.
+// Mutations
+//   Add / Evict append 16 B op records to a pinned queue and return.  A flush (before the next read, or when the queue
+//   is full) ships the queue and applies it in one of two ways:
+//     parallel   sort ops by key (stable, cub radix sort), one thread per DISTINCT key replays that key's ops in order
+//                on the bucket held in registers (the 13-entry inner LRU is a register loop) and writes it back once;
+//                used whenever no outer-LRU eviction can happen (live + new <= Size);
+//     sequential one thread replays the queue in order, evicting the oldest key exactly when the reference would
+//                (contains_or_add past `Size`).  "Oldest" comes from an order array (stamp, slot) sorted once on the
+//                device and consumed lazily: a record is stale when its slot was re-stamped or freed.  Exact LRU at
+//                capacity, amortised O(1) per eviction; also used for tiny batches (one launch, no sort).
+//   The table grows by a device-side rehash; nothing is ever rebuilt from the host.
+// Reads
+//   Lookup: one thread per key.  Score: one warp per prompt — 32 independent probes staged in shared memory, then the
+//   serial float64 prefix walk in key order (bit-identical sums, kvblock_scorer.go:132-150).  Found keys are stamped
+//   by the kernel (atomicMax), so refreshing recency costs the host nothing.
 // Random-access bound (2 sectors per probe), not bandwidth bound.
+//
+// The same source compiles with g++ -DKVB_HOST_SIM against tests/cpp/sim_cuda.h (malloc + loops instead of a device) so
+// the mutation logic is checked against the oracle on CPU-only boxes; the product build has no such path.
+#ifdef KVB_HOST_SIM
+#include "sim_cuda.h"
+#define KVB_DEV
+#else
+#define KVB_DEV __device__
+#include <cub/cub.cuh>
+
+#include "kvb_internal.h"
+#define KVB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
-#include <list>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 
-#include "kvb_internal.h"
-
 namespace kvb {
 
 constexpr int kMaxEnt = KVB_INDEX_MAX_PODS_PER_KEY;  // 13
 constexpr uint32_t kEmpty = 0, kFull = 1, kTomb = 2, kBusy = 3;
+constexpr uint32_t kNoSlot = 0xffffffffu;
 
 struct __align__(64) Bucket {
   uint64_t key;
@@ -37,12 +62,27 @@ struct __align__(64) Bucket {
 };
 static_assert(sizeof(Bucket) == 64, "bucket must be one 64 B line");
 
-struct __align__(64) Op {  // one mutation shipped to the device
+constexpr uint8_t kOpAdd = 0, kOpEvict = 1;
+struct OpRec {  // one queued mutation of one request key
   uint64_t key;
-  uint32_t count;  // 0xffffffff = delete
-  uint32_t ent[kMaxEnt];
+  uint32_t ent_off;  // first entry in the entry pool
+  uint16_t ent_cnt;
+  uint8_t type;
+  uint8_t pad;
 };
-static_assert(sizeof(Op) == 64, "op must be 64 B");
+static_assert(sizeof(OpRec) == 16, "op record must be 16 B");
+
+struct Counters {  // device resident
+  unsigned long long live, tombs, order_head, evicted, inserted, removed, stale_skipped, scans;
+};
+
+struct TableRef {
+  Bucket* table;
+  unsigned long long* ts;
+  uint64_t mask;
+  Counters* ctr;
+  int ppk;
+};
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {  // murmur3 fmix64
   k ^= k >> 33;
@@ -55,59 +95,286 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {  // murmur3 fmi
 __host__ __device__ __forceinline__ uint32_t pack_entry(uint16_t pod, uint8_t tier, uint8_t spec) {
   return (uint32_t)pod | ((uint32_t)tier << 16) | ((uint32_t)(spec ? 1 : 0) << 24);
 }
+KVB_DEV __forceinline__ uint32_t ld_meta(const Bucket* b) {
+  return *reinterpret_cast<const volatile uint32_t*>(&b->meta);
+}
+KVB_DEV __forceinline__ uint64_t ld_key(const Bucket* b) {
+  return *reinterpret_cast<const volatile uint64_t*>(&b->key);
+}
 
-// ----------------------------------------------------------------------------------------- kernels
-__global__ void index_apply_kernel(Bucket* __restrict__ table, uint64_t mask, const Op* __restrict__ ops, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Op op = ops[i];
-  const bool del = op.count == 0xffffffffu;
-  uint64_t slot = mix64(op.key) & mask;
-  int64_t found = -1, reuse = -1;
-  for (uint64_t probes = 0; probes <= mask; ++probes, slot = (slot + 1) & mask) {
-    const uint32_t m = *reinterpret_cast<volatile uint32_t*>(&table[slot].meta);
-    const uint32_t st = m & 3u;
+// slot of `key` or -1; *reuse = first free (empty or tombstone) slot on the probe path, -1 if the table is full
+KVB_DEV inline int64_t find_slot(const TableRef& t, uint64_t key, int64_t* reuse) {
+  uint64_t slot = mix64(key) & t.mask;
+  int64_t free_slot = -1;
+  for (uint64_t probes = 0; probes <= t.mask; ++probes, slot = (slot + 1) & t.mask) {
+    const uint32_t st = ld_meta(&t.table[slot]) & 3u;
     if (st == kEmpty) {
-      if (reuse < 0) reuse = (int64_t)slot;
+      if (free_slot < 0) free_slot = (int64_t)slot;
       break;
     }
     if (st == kTomb) {
-      if (reuse < 0) reuse = (int64_t)slot;
-    } else if (st == kFull && *reinterpret_cast<volatile uint64_t*>(&table[slot].key) == op.key) {
-      found = (int64_t)slot;
+      if (free_slot < 0) free_slot = (int64_t)slot;
+    } else if (st == kFull && ld_key(&t.table[slot]) == key) {
+      if (reuse) *reuse = free_slot;
+      return (int64_t)slot;
+    }
+  }
+  if (reuse) *reuse = free_slot;
+  return -1;
+}
+
+// claim a free slot for a NEW key (threads of one launch carry distinct keys, so a lost race just moves on);
+// the slot is left in state kBusy for the caller to fill.  Returns -1 only if the table has no free slot.
+KVB_DEV inline int64_t claim_slot(const TableRef& t, uint64_t key, int64_t hint, bool* was_tomb) {
+  uint64_t slot = hint >= 0 ? (uint64_t)hint : (mix64(key) & t.mask);
+  for (uint64_t probes = 0; probes <= t.mask; ++probes, slot = (slot + 1) & t.mask) {
+    const uint32_t m = ld_meta(&t.table[slot]);
+    const uint32_t st = m & 3u;
+    if (st != kEmpty && st != kTomb) continue;
+    if (atomicCAS(&t.table[slot].meta, m, kBusy) != m) {
+      --probes;  // somebody else moved this slot: look at it again
+      slot = (slot - 1) & t.mask;
+      continue;
+    }
+    *was_tomb = st == kTomb;
+    return (int64_t)slot;
+  }
+  return -1;
+}
+
+// inner LRU of one key (golang-lru Add on PodEntry, oldest first): an entry already present moves to newest, a new
+// one evicts the oldest when the key already holds `ppk` entries (in_memory.go:205-221, in_memory_test.go:86-120)
+KVB_DEV inline void inner_add(uint32_t* ent, int& cnt, uint32_t e, int ppk) {
+  int at = -1;
+  for (int k = 0; k < cnt; ++k)
+    if (ent[k] == e) {
+      at = k;
       break;
+    }
+  if (at >= 0) {
+    for (int k = at; k + 1 < cnt; ++k) ent[k] = ent[k + 1];
+    ent[cnt - 1] = e;
+    return;
+  }
+  if (cnt == ppk) {
+    for (int k = 0; k + 1 < cnt; ++k) ent[k] = ent[k + 1];
+    --cnt;
+  }
+  ent[cnt++] = e;
+}
+KVB_DEV inline void inner_remove(uint32_t* ent, int& cnt, uint32_t e) {  // exact triple match (:266-269)
+  for (int k = 0; k < cnt; ++k)
+    if (ent[k] == e) {
+      for (int q = k; q + 1 < cnt; ++q) ent[q] = ent[q + 1];
+      --cnt;
+      return;
+    }
+}
+
+KVB_DEV inline void store_bucket(const TableRef& t, int64_t slot, uint64_t key, const uint32_t* ent,
+                                              int cnt, bool fresh) {
+  Bucket& b = t.table[slot];
+  if (fresh) b.key = key;
+  for (int e = 0; e < kMaxEnt; ++e) b.ent[e] = e < cnt ? ent[e] : 0u;
+  __threadfence();
+  *reinterpret_cast<volatile uint32_t*>(&b.meta) = kFull | ((uint32_t)cnt << 8);
+}
+KVB_DEV inline void kill_slot(const TableRef& t, int64_t slot) {
+  *reinterpret_cast<volatile uint32_t*>(&t.table[slot].meta) = kTomb;
+  t.ts[slot] = 0ull;
+}
+
+// ---- parallel path: thread i owns the run of ops that carry sorted key skey[i] (only the run's first thread works)
+KVB_DEV inline void apply_run(const TableRef& t, const OpRec* ops, const uint32_t* ents,
+                                          const uint64_t* skey, const uint32_t* sidx, int64_t i, int64_t n,
+                                          unsigned long long seq_base) {
+  const uint64_t key = skey[i];
+  if (i > 0 && skey[i - 1] == key) return;
+  int64_t reuse = -1;
+  const int64_t found = find_slot(t, key, &reuse);
+  uint32_t ent[kMaxEnt];
+  int cnt = 0;
+  bool present = found >= 0;
+  if (present) {
+    const Bucket& b = t.table[found];
+    cnt = (int)((ld_meta(&b) >> 8) & 0xffu);
+    for (int e = 0; e < kMaxEnt; ++e) ent[e] = b.ent[e];
+  }
+  unsigned long long stamp = 0ull;
+  for (int64_t j = i; j < n && skey[j] == key; ++j) {
+    const OpRec op = ops[sidx[j]];
+    if (op.type == kOpAdd) {
+      if (!present) {  // data.Get missed: a fresh inner LRU (in_memory.go:186-199)
+        present = true;
+        cnt = 0;
+      }
+      stamp = seq_base + sidx[j];
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_add(ent, cnt, ents[op.ent_off + e], t.ppk);
+    } else if (present) {  // evictPodsFromRequestKey: Get refreshes recency, then removes (in_memory.go:260-292)
+      stamp = seq_base + sidx[j];
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_remove(ent, cnt, ents[op.ent_off + e]);
+      if (cnt == 0) present = false;
     }
   }
   if (found >= 0) {
-    Bucket& b = table[found];
-    if (del) {
-      b.meta = kTomb;
+    if (present) {
+      store_bucket(t, found, key, ent, cnt, false);
+      if (stamp) t.ts[found] = stamp;
     } else {
-#pragma unroll
-      for (int e = 0; e < kMaxEnt; ++e) b.ent[e] = op.ent[e];
-      b.meta = kFull | (op.count << 8);
+      kill_slot(t, found);
+      atomicAdd(&t.ctr->live, (unsigned long long)-1ll);
+      atomicAdd(&t.ctr->tombs, 1ull);
+      atomicAdd(&t.ctr->removed, 1ull);
     }
-    return;
-  }
-  if (del) return;
-  // claim a free slot; ops in one batch carry distinct keys, so a lost race just moves on
-  slot = reuse >= 0 ? (uint64_t)reuse : (mix64(op.key) & mask);
-  for (uint64_t probes = 0; probes <= mask; ++probes, slot = (slot + 1) & mask) {
-    const uint32_t m = *reinterpret_cast<volatile uint32_t*>(&table[slot].meta);
-    const uint32_t st = m & 3u;
-    if (st != kEmpty && st != kTomb) continue;
-    if (atomicCAS(&table[slot].meta, m, kBusy) != m) continue;
-    Bucket& b = table[slot];
-    b.key = op.key;
-#pragma unroll
-    for (int e = 0; e < kMaxEnt; ++e) b.ent[e] = op.ent[e];
-    __threadfence();
-    b.meta = kFull | (op.count << 8);
-    return;
+  } else if (present) {
+    bool was_tomb = false;
+    const int64_t s = claim_slot(t, key, reuse, &was_tomb);
+    if (s < 0) return;  // cannot happen: the host grows the table before it fills
+    store_bucket(t, s, key, ent, cnt, true);
+    t.ts[s] = stamp;
+    atomicAdd(&t.ctr->live, 1ull);
+    atomicAdd(&t.ctr->inserted, 1ull);
+    if (was_tomb) atomicAdd(&t.ctr->tombs, (unsigned long long)-1ll);
   }
 }
 
-__device__ __forceinline__ int64_t probe(const Bucket* __restrict__ table, uint64_t mask, uint64_t key) {
+// ---- sequential path (one thread): the reference's order, including outer-LRU eviction at `max_keys`
+KVB_DEV inline void evict_oldest(const TableRef& t, const unsigned long long* order_ts,
+                                             const uint32_t* order_slot, unsigned long long order_n) {
+  Counters& c = *t.ctr;
+  while (c.order_head < order_n) {  // lazily validated order array
+    const unsigned long long h = c.order_head++;
+    const uint32_t s = order_slot[h];
+    if ((ld_meta(&t.table[s]) & 3u) == kFull && t.ts[s] == order_ts[h]) {
+      kill_slot(t, s);
+      c.live--;
+      c.tombs++;
+      c.evicted++;
+      return;
+    }
+    c.stale_skipped++;
+  }
+  // order exhausted (more insertions than the array held): the keys left are newer than every record — scan for the min
+  c.scans++;
+  int64_t best = -1;
+  unsigned long long best_ts = ~0ull;
+  for (uint64_t s = 0; s <= t.mask; ++s)
+    if ((ld_meta(&t.table[s]) & 3u) == kFull && t.ts[s] < best_ts) {
+      best_ts = t.ts[s];
+      best = (int64_t)s;
+    }
+  if (best >= 0) {
+    kill_slot(t, best);
+    c.live--;
+    c.tombs++;
+    c.evicted++;
+  }
+}
+
+KVB_DEV inline void apply_seq(const TableRef& t, const OpRec* ops, const uint32_t* ents, int64_t n,
+                                          unsigned long long seq_base, unsigned long long max_keys,
+                                          const unsigned long long* order_ts, const uint32_t* order_slot,
+                                          unsigned long long order_n) {
+  Counters& c = *t.ctr;
+  for (int64_t j = 0; j < n; ++j) {
+    const OpRec op = ops[j];
+    int64_t reuse = -1;
+    int64_t slot = find_slot(t, op.key, &reuse);
+    uint32_t ent[kMaxEnt] = {};
+    int cnt = 0;
+    if (op.type == kOpAdd) {
+      bool fresh = false;
+      if (slot < 0) {
+        bool was_tomb = false;
+        slot = claim_slot(t, op.key, reuse, &was_tomb);
+        if (slot < 0) return;
+        fresh = true;
+        c.live++;
+        c.inserted++;
+        if (was_tomb) c.tombs--;
+        store_bucket(t, slot, op.key, ent, 0, true);
+        t.ts[slot] = seq_base + j;  // newest before the eviction looks for the oldest
+        if (c.live > max_keys) evict_oldest(t, order_ts, order_slot, order_n);  // lru.Add past Size (in_memory.go:197)
+      } else {
+        const Bucket& b = t.table[slot];
+        cnt = (int)((ld_meta(&b) >> 8) & 0xffu);
+        for (int e = 0; e < kMaxEnt; ++e) ent[e] = b.ent[e];
+        t.ts[slot] = seq_base + j;
+      }
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_add(ent, cnt, ents[op.ent_off + e], t.ppk);
+      store_bucket(t, slot, op.key, ent, cnt, fresh);
+    } else if (slot >= 0) {
+      const Bucket& b = t.table[slot];
+      cnt = (int)((ld_meta(&b) >> 8) & 0xffu);
+      for (int e = 0; e < kMaxEnt; ++e) ent[e] = b.ent[e];
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_remove(ent, cnt, ents[op.ent_off + e]);
+      if (cnt == 0) {
+        kill_slot(t, slot);
+        c.live--;
+        c.tombs++;
+        c.removed++;
+      } else {
+        store_bucket(t, slot, op.key, ent, cnt, false);
+        t.ts[slot] = seq_base + j;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------- kernels
+__global__ void index_apply_par_kernel(TableRef t, const OpRec* __restrict__ ops, const uint32_t* __restrict__ ents,
+                                       const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx, int64_t n,
+                                       unsigned long long seq_base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  apply_run(t, ops, ents, skey, sidx, i, n, seq_base);
+}
+
+__global__ void index_apply_seq_kernel(TableRef t, const OpRec* __restrict__ ops, const uint32_t* __restrict__ ents,
+                                       int64_t n, unsigned long long seq_base, unsigned long long max_keys,
+                                       const unsigned long long* __restrict__ order_ts,
+                                       const uint32_t* __restrict__ order_slot, unsigned long long order_n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  apply_seq(t, ops, ents, n, seq_base, max_keys, order_ts, order_slot, order_n);
+}
+
+__global__ void index_sort_keys_kernel(const OpRec* __restrict__ ops, int64_t n, uint64_t* __restrict__ keys,
+                                       uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = ops[i].key;
+  idx[i] = (uint32_t)i;
+}
+
+// move every live bucket (and its stamp) into a larger table
+__global__ void index_rehash_kernel(const Bucket* __restrict__ old_table, const unsigned long long* __restrict__ old_ts,
+                                    uint64_t old_slots, TableRef t) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= old_slots) return;
+  const Bucket& b = old_table[s];
+  if ((b.meta & 3u) != kFull) return;
+  bool was_tomb = false;
+  const int64_t d = claim_slot(t, b.key, -1, &was_tomb);
+  if (d < 0) return;
+  store_bucket(t, d, b.key, b.ent, (int)((b.meta >> 8) & 0xffu), true);
+  t.ts[d] = old_ts[s];
+}
+
+// (stamp, slot) of every live bucket, in arbitrary order (sorted afterwards)
+__global__ void index_collect_order_kernel(TableRef t, unsigned long long* __restrict__ out_ts,
+                                           uint32_t* __restrict__ out_slot, unsigned long long* __restrict__ cursor,
+                                           unsigned long long cap) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > t.mask) return;
+  if ((t.table[s].meta & 3u) != kFull) return;
+  const unsigned long long at = atomicAdd(cursor, 1ull);
+  if (at < cap) {
+    out_ts[at] = t.ts[s];
+    out_slot[at] = (uint32_t)s;
+  }
+}
+
+__device__ __host__ __forceinline__ int64_t probe(const Bucket* __restrict__ table, uint64_t mask, uint64_t key) {
   uint64_t slot = mix64(key) & mask;
   for (uint64_t probes = 0; probes <= mask; ++probes, slot = (slot + 1) & mask) {
     const uint32_t st = table[slot].meta & 3u;
@@ -117,14 +384,16 @@ __device__ __forceinline__ int64_t probe(const Bucket* __restrict__ table, uint6
   return -1;
 }
 
-__device__ __forceinline__ bool pod_allowed(const uint32_t* __restrict__ filter_bits, uint32_t pod) {
+__device__ __host__ __forceinline__ bool pod_allowed(const uint32_t* __restrict__ filter_bits, uint32_t pod) {
   return filter_bits == nullptr || ((filter_bits[pod >> 5] >> (pod & 31)) & 1u);
 }
 
 // Lookup: one thread per key.  counts: -1 absent, -2 present but empty, else #entries after the pod filter.
+// stamp_base != 0: found keys are re-stamped (data.Get, in_memory.go:120) with stamp_base + position.
 __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t mask, const uint64_t* __restrict__ keys,
                                     int64_t n, const uint32_t* __restrict__ filter_bits, int32_t* __restrict__ counts,
-                                    uint32_t* __restrict__ out_ent) {
+                                    uint32_t* __restrict__ out_ent, unsigned long long* __restrict__ ts,
+                                    unsigned long long stamp_base) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t s = probe(table, mask, keys[i]);
@@ -132,6 +401,7 @@ __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t m
     counts[i] = -1;
     return;
   }
+  if (stamp_base) atomicMax(&ts[s], stamp_base + (unsigned long long)i);
   const Bucket& b = table[s];
   const int cnt = (int)((b.meta >> 8) & 0xff);
   if (cnt == 0) {
@@ -146,6 +416,7 @@ __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t m
   counts[i] = k;
 }
 
+#ifndef KVB_HOST_SIM
 // Score: one warp per prompt (4 warps per CTA).
 constexpr int kScoreWarps = 4;
 
@@ -154,7 +425,8 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
                        const int64_t* __restrict__ key_off, int32_t n_prompts,
                        const uint32_t* __restrict__ filter_bits, const double* __restrict__ tier_w,
                        int32_t* __restrict__ out_n, uint16_t* __restrict__ out_pods, double* __restrict__ out_scores,
-                       uint8_t* __restrict__ found_flags /* nullable: one byte per key */) {
+                       unsigned long long* __restrict__ ts /* nullable: stamp found keys */,
+                       unsigned long long stamp_base) {
   __shared__ Bucket tile[kScoreWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * kScoreWarps + warp;
@@ -170,12 +442,13 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
   bool chain_alive = true;
 
   for (int64_t base = 0; base < nk; base += 32) {
-    if (!chain_alive && found_flags == nullptr) break;
+    if (!chain_alive && ts == nullptr) break;
     // ---- phase A: 32 independent probes, buckets staged in shared memory
     const int64_t ki = base + lane;
     int64_t slot = -1;
     if (ki < nk) slot = probe(table, mask, keys[k0 + ki]);
-    if (found_flags != nullptr && ki < nk) found_flags[k0 + ki] = slot >= 0 ? 1 : 0;
+    // Lookup walks EVERY key and data.Get refreshes each one it finds (in_memory.go:119-120): stamp in key order
+    if (ts != nullptr && slot >= 0) atomicMax(&ts[slot], stamp_base + (unsigned long long)(k0 + ki));
     if (slot >= 0) {
       const uint4* src = reinterpret_cast<const uint4*>(&table[slot]);
       uint4* dst = reinterpret_cast<uint4*>(&tile[warp][lane]);
@@ -189,7 +462,7 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
     for (int j = 0; j < in_tile; ++j) {
       const int64_t sj = __shfl_sync(FULL, slot, j);
       // bucket entries sit on lanes 16..28, the reported pods (owners) on lanes 0..12 in the order they appeared at
-      // key 0: ONE match.any per key pairs every owner with the entries that carry its pod (13 x 3 shuffles before)
+      // key 0: ONE match.any per key pairs every owner with the entries that carry its pod
       bool valid = false;
       uint32_t pod = 0x10000u + lane;  // unique sentinel for lanes without a valid entry
       double w = 0.0;
@@ -263,21 +536,139 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
   }
   if (lane == 0) out_n[p] = __popc(om);
 }
+#endif  // !KVB_HOST_SIM
 
 // ----------------------------------------------------------------------------------------- host side
-struct KeyNode {
-  uint8_t count = 0;
-  kvb_pod_entry_t e[kMaxEnt];  // oldest -> newest (golang-lru Keys() order)
-  std::list<uint64_t>::iterator lru;
-};
-struct EngNode {
-  std::vector<uint64_t> rks;
-  std::list<uint64_t>::iterator lru;
-};
+// engine key -> request keys with golang-lru semantics (Add: update + move to newest, evict oldest past `cap`;
+// Get: move to newest).  Flat: nodes in a vector linked by index, open-addressing index with backward-shift delete.
+class EngMap {
+ public:
+  static constexpr uint32_t kNil = 0xffffffffu;
+  struct Node {
+    uint64_t ek = 0, rk_last = 0;
+    uint32_t n = 0, prev = kNil, next = kNil;
+    std::vector<uint64_t>* many = nullptr;  // all request keys when n > 1
+  };
+  explicit EngMap(int64_t cap) : cap_(cap) { rebuild(1024); }
+  ~EngMap() {
+    for (auto& nd : nodes_) delete nd.many;
+  }
+  size_t size() const { return size_; }
+  int64_t find(uint64_t ek) const {
+    for (size_t i = home(ek);; i = (i + 1) & mask_) {
+      const uint32_t v = tab_[i];
+      if (v == 0) return -1;
+      if (nodes_[v - 1].ek == ek) return (int64_t)(v - 1);
+    }
+  }
+  const Node& node(int64_t id) const { return nodes_[(size_t)id]; }
+  void touch(int64_t id) {
+    unlink((uint32_t)id);
+    push_back((uint32_t)id);
+  }
+  void put(uint64_t ek, const uint64_t* rks, size_t n) {
+    int64_t id = find(ek);
+    if (id >= 0) {
+      set_value(nodes_[(size_t)id], rks, n);
+      touch(id);
+      return;
+    }
+    uint32_t nid;
+    if (!free_.empty()) {
+      nid = free_.back();
+      free_.pop_back();
+    } else {
+      nid = (uint32_t)nodes_.size();
+      nodes_.emplace_back();
+    }
+    if ((size_ + 1) * 2 > tab_.size()) rebuild(tab_.size() * 2);  // before the node joins the list rebuild() walks
+    Node& nd = nodes_[nid];
+    nd.ek = ek;
+    set_value(nd, rks, n);
+    push_back(nid);
+    insert_index(nid);
+    ++size_;
+    if ((int64_t)size_ > cap_ && head_ != kNil) erase(head_);
+  }
+  void erase(int64_t id) {
+    const Node& nd = nodes_[(size_t)id];
+    size_t i = home(nd.ek);
+    while (tab_[i] != (uint32_t)id + 1) i = (i + 1) & mask_;
+    for (;;) {  // backward-shift deletion
+      tab_[i] = 0;
+      size_t j = i;
+      for (;;) {
+        j = (j + 1) & mask_;
+        if (tab_[j] == 0) goto done;
+        const size_t k = home(nodes_[tab_[j] - 1].ek);
+        const bool stays = (i <= j) ? (i < k && k <= j) : (i < k || k <= j);
+        if (!stays) break;
+      }
+      tab_[i] = tab_[j];
+      i = j;
+    }
+  done:
+    unlink((uint32_t)id);
+    delete nodes_[(size_t)id].many;
+    nodes_[(size_t)id] = Node();
+    free_.push_back((uint32_t)id);
+    --size_;
+  }
+  template <class F>
+  void for_each_rk(int64_t id, F&& f) const {
+    const Node& nd = nodes_[(size_t)id];
+    if (nd.n == 1) f(nd.rk_last);
+    else if (nd.many)
+      for (uint64_t rk : *nd.many) f(rk);
+  }
 
-static inline bool same_entry(const kvb_pod_entry_t& a, const kvb_pod_entry_t& b) {
-  return a.pod == b.pod && a.tier == b.tier && (a.speculative != 0) == (b.speculative != 0);
-}
+ private:
+  int64_t cap_;
+  std::vector<Node> nodes_;
+  std::vector<uint32_t> free_;
+  std::vector<uint32_t> tab_;
+  size_t mask_ = 0, size_ = 0;
+  uint32_t head_ = kNil, tail_ = kNil;  // head = oldest
+
+  size_t home(uint64_t ek) const { return (size_t)mix64(ek) & mask_; }
+  static void set_value(Node& nd, const uint64_t* rks, size_t n) {
+    nd.n = (uint32_t)n;
+    nd.rk_last = n ? rks[n - 1] : 0;
+    if (n > 1) {
+      if (!nd.many) nd.many = new std::vector<uint64_t>();
+      nd.many->assign(rks, rks + n);
+    } else {
+      delete nd.many;
+      nd.many = nullptr;
+    }
+  }
+  void insert_index(uint32_t nid) {
+    size_t i = home(nodes_[nid].ek);
+    while (tab_[i] != 0) i = (i + 1) & mask_;
+    tab_[i] = nid + 1;
+  }
+  void rebuild(size_t cap) {
+    tab_.assign(cap, 0u);
+    mask_ = cap - 1;
+    for (uint32_t id = head_; id != kNil; id = nodes_[id].next) insert_index(id);
+  }
+  void unlink(uint32_t id) {
+    Node& nd = nodes_[id];
+    if (nd.prev != kNil) nodes_[nd.prev].next = nd.next;
+    else if (head_ == id) head_ = nd.next;
+    if (nd.next != kNil) nodes_[nd.next].prev = nd.prev;
+    else if (tail_ == id) tail_ = nd.prev;
+    nd.prev = nd.next = kNil;
+  }
+  void push_back(uint32_t id) {
+    Node& nd = nodes_[id];
+    nd.prev = tail_;
+    nd.next = kNil;
+    if (tail_ != kNil) nodes_[tail_].next = id;
+    tail_ = id;
+    if (head_ == kNil) head_ = id;
+  }
+};
 
 }  // namespace kvb
 
@@ -288,28 +679,60 @@ struct kvb_index {
   int64_t max_keys = 0;
   int pods_per_key = 10;
   std::mutex mu;
+  std::unique_ptr<EngMap> eng;
 
-  // host authoritative state
-  std::unordered_map<uint64_t, KeyNode> data;
-  std::list<uint64_t> data_lru;  // front = oldest
-  std::unordered_map<uint64_t, EngNode> eng;
-  std::list<uint64_t> eng_lru;
-  std::vector<uint64_t> dirty;
-
-  // device mirror
+  // device table
   Bucket* table = nullptr;
+  unsigned long long* ts = nullptr;
   uint64_t slots = 0;
-  int64_t dev_live = 0, dev_tomb = 0;
-  bool stale_mirror = false;  // the device table misses host entries (a rebuild failed after the swap)
+  Counters* d_ctr = nullptr;
+  Counters h_ctr{};        // last value read back
+  int64_t live_ub = 0;     // upper bound on live keys, including queued adds
+  int64_t tomb_ub = 0;     // upper bound on tombstones
+  unsigned long long seq = 1;  // next recency stamp (0 = never stamped)
+  cudaStream_t stream = nullptr;
   double tier_w_host[256];
   double* tier_w = nullptr;
-  cudaStream_t stream = nullptr;
-  // scratch
+
+  // pinned op queue + device copies and sort buffers
+  static constexpr size_t kOpsCap = 1u << 18, kEntsCap = 1u << 20;
+  static constexpr int64_t kSeqThreshold = 16;  // batches this small skip the sort and replay on one thread
+  OpRec* h_ops = nullptr;
+  uint32_t* h_ents = nullptr;
+  size_t n_ops = 0, n_ents = 0;
+  int64_t q_adds = 0, q_evicts = 0;
+  cudaEvent_t q_free = nullptr;  // the previous flush's H2D copies have read the pinned queue
+  bool q_busy = false;
+  OpRec* d_ops = nullptr;
+  uint32_t* d_ents = nullptr;
+  uint64_t *d_skey_in = nullptr, *d_skey_out = nullptr;
+  uint32_t *d_sidx_in = nullptr, *d_sidx_out = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+
+  // LRU order array (built on demand, only when the index runs at capacity)
+  unsigned long long* order_ts = nullptr;
+  uint32_t* order_slot = nullptr;
+  unsigned long long *order_ts_in = nullptr, *d_cursor = nullptr;
+  uint32_t* order_slot_in = nullptr;
+  int64_t order_cap = 0, order_n = 0;
+  bool order_valid = false;
+
+  // read scratch
   uint8_t* d_scratch = nullptr;
   size_t d_scratch_cap = 0;
   uint8_t* h_scratch = nullptr;
   size_t h_scratch_cap = 0;
   uint32_t* d_filter = nullptr;  // 65536 bits
+  std::vector<uint16_t> filter_cached;
+  bool filter_valid = false;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+  float last_hash_us = 0.f, last_score_us = 0.f;
+
+  // statistics
+  int64_t n_flush_par = 0, n_flush_seq = 0, n_rehash = 0, n_order_builds = 0, n_ops_total = 0;
+
+  TableRef ref() const { return TableRef{table, ts, slots - 1, d_ctr, pods_per_key}; }
 
   int ensure_scratch(size_t dev_bytes, size_t host_bytes) {
     if (dev_bytes > d_scratch_cap) {
@@ -327,159 +750,258 @@ struct kvb_index {
       h_scratch_cap = 0;
       size_t cap = std::max<size_t>(host_bytes, 1 << 20);
       cap = (cap * 3 / 2 + 255) & ~size_t(255);
-      KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&h_scratch), cap, cudaHostAllocDefault));
+      KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&h_scratch), cap,
+                                   cudaHostAllocPortable | cudaHostAllocMapped));
       h_scratch_cap = cap;
     }
     return KVB_OK;
   }
 
-  void touch(std::unordered_map<uint64_t, KeyNode>::iterator it) {
-    data_lru.erase(it->second.lru);
-    data_lru.push_back(it->first);
-    it->second.lru = std::prev(data_lru.end());
-  }
-  void touch_eng(std::unordered_map<uint64_t, EngNode>::iterator it) {
-    eng_lru.erase(it->second.lru);
-    eng_lru.push_back(it->first);
-    it->second.lru = std::prev(eng_lru.end());
-  }
-  void eng_add(uint64_t ek, std::vector<uint64_t>&& rks) {  // lru.Add: update + move to front, evict oldest
-    auto it = eng.find(ek);
-    if (it != eng.end()) {
-      it->second.rks = std::move(rks);
-      touch_eng(it);
-      return;
+  int alloc_table(uint64_t n_slots, Bucket** t_out, unsigned long long** ts_out) {
+    Bucket* t = nullptr;
+    unsigned long long* s = nullptr;
+    KVB_CUDA_TRY(cudaMalloc(&t, n_slots * sizeof(Bucket)));
+    if (cudaMalloc(&s, n_slots * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaFree(t);
+      set_error("index: cannot allocate %llu recency stamps", (unsigned long long)n_slots);
+      return KVB_ERR_CUDA;
     }
-    EngNode n;
-    n.rks = std::move(rks);
-    eng_lru.push_back(ek);
-    n.lru = std::prev(eng_lru.end());
-    eng.emplace(ek, std::move(n));
-    if ((int64_t)eng.size() > max_keys) {
-      uint64_t old = eng_lru.front();
-      eng_lru.pop_front();
-      eng.erase(old);
+    cudaError_t e = cudaMemsetAsync(t, 0, n_slots * sizeof(Bucket), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s, 0, n_slots * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) {
+      cudaFree(t);
+      cudaFree(s);
+      set_error("index: clearing a new table failed: %s", cudaGetErrorString(e));
+      return KVB_ERR_CUDA;
     }
-  }
-  void erase_key(std::unordered_map<uint64_t, KeyNode>::iterator it) {
-    dirty.push_back(it->first);
-    data_lru.erase(it->second.lru);
-    data.erase(it);
-  }
-
-  int set_filter(const uint16_t* pods, int32_t n, const uint32_t** out) {
-    *out = nullptr;
-    if (n <= 0) return KVB_OK;
-    std::vector<uint32_t> bits(2048, 0u);
-    for (int32_t i = 0; i < n; ++i) bits[pods[i] >> 5] |= 1u << (pods[i] & 31);
-    if (!d_filter) KVB_CUDA_TRY(cudaMalloc(&d_filter, 2048 * sizeof(uint32_t)));
-    KVB_CUDA_TRY(cudaMemcpyAsync(d_filter, bits.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    KVB_CUDA_TRY(cudaStreamSynchronize(stream));  // bits is a stack temporary
-    *out = d_filter;
+    *t_out = t;
+    *ts_out = s;
     return KVB_OK;
   }
 
-  int rebuild(uint64_t new_slots);
+  int sync_counters() {  // exact live / tombstone counts (waits for everything queued on the stream)
+    KVB_CUDA_TRY(cudaMemcpyAsync(&h_ctr, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    KVB_CUDA_TRY(cudaStreamSynchronize(stream));
+    live_ub = (int64_t)h_ctr.live + q_adds;
+    tomb_ub = (int64_t)h_ctr.tombs + q_evicts;
+    return KVB_OK;
+  }
+
+  int rehash(uint64_t new_slots);
+  int ensure_order();
   int flush_locked();
+  int queue_ops(uint8_t type, const uint64_t* keys, int64_t n_keys, const kvb_pod_entry_t* entries, int32_t n_entries);
+  int set_filter(const uint16_t* pods, int32_t n, uint8_t* h_stage, bool* staged, const uint32_t** out);
 };
 
-static void node_image(uint64_t key, const KeyNode& n, Op* op) {
-  op->key = key;
-  op->count = n.count;
-  for (int e = 0; e < kMaxEnt; ++e)
-    op->ent[e] = e < n.count ? pack_entry(n.e[e].pod, n.e[e].tier, n.e[e].speculative) : 0u;
-}
-
-static int apply_ops(kvb_index* idx, const std::vector<Op>& ops) {
-  if (ops.empty()) return KVB_OK;
-  const size_t bytes = ops.size() * sizeof(Op);
-  int rc = idx->ensure_scratch(bytes, 0);
+int kvb_index::rehash(uint64_t new_slots) {
+  Bucket* fresh = nullptr;
+  unsigned long long* fresh_ts = nullptr;
+  int rc = alloc_table(new_slots, &fresh, &fresh_ts);  // a failed allocation leaves the index as it was
   if (rc) return rc;
-  // ops is pageable host memory: the copy is staged by the runtime before returning
-  KVB_CUDA_TRY(cudaMemcpyAsync(idx->d_scratch, ops.data(), bytes, cudaMemcpyHostToDevice, idx->stream));
-  const int threads = 128;
-  const int64_t grid = ((int64_t)ops.size() + threads - 1) / threads;
-  index_apply_kernel<<<(unsigned)grid, threads, 0, idx->stream>>>(idx->table, idx->slots - 1,
-                                                                 reinterpret_cast<const Op*>(idx->d_scratch),
-                                                                 (int64_t)ops.size());
+  TableRef nt{fresh, fresh_ts, new_slots - 1, d_ctr, pods_per_key};
+  const unsigned threads = 256;
+  KVB_LAUNCH(index_rehash_kernel, (unsigned)((slots + threads - 1) / threads), threads, stream, table, ts, slots, nt);
   KVB_CUDA_TRY(cudaGetLastError());
   count_launch();
-  KVB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  Counters zero_tombs;
+  KVB_CUDA_TRY(cudaMemcpyAsync(&zero_tombs, d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+  KVB_CUDA_TRY(cudaStreamSynchronize(stream));
+  zero_tombs.tombs = 0;
+  KVB_CUDA_TRY(cudaMemcpy(d_ctr, &zero_tombs, sizeof(Counters), cudaMemcpyHostToDevice));
+  cudaFree(table);
+  cudaFree(ts);
+  table = fresh;
+  ts = fresh_ts;
+  slots = new_slots;
+  h_ctr = zero_tombs;
+  live_ub = (int64_t)h_ctr.live + q_adds;
+  tomb_ub = q_evicts;
+  order_valid = false;  // slots moved
+  ++n_rehash;
   return KVB_OK;
 }
 
-int kvb_index::rebuild(uint64_t new_slots) {
-  // the new table is allocated BEFORE the old one goes: a failed allocation leaves the mirror as it was (stale but
-  // consistent; dirty keys stay queued), a failure while refilling leaves stale_mirror set so the next flush retries
-  Bucket* fresh = nullptr;
-  KVB_CUDA_TRY(cudaMalloc(&fresh, new_slots * sizeof(Bucket)));
-  cudaError_t e = cudaMemsetAsync(fresh, 0, new_slots * sizeof(Bucket), stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) {
-    cudaFree(fresh);
-    set_error("index rebuild: %s", cudaGetErrorString(e));
-    return KVB_ERR_CUDA;
-  }
-  if (table) cudaFree(table);
-  table = fresh;
-  slots = new_slots;
-  dev_live = 0;
-  dev_tomb = 0;
-  stale_mirror = true;
-  std::vector<Op> ops;
-  const size_t batch = 1 << 20;
-  ops.reserve(std::min(batch, data.size()));
-  for (auto& kv : data) {
-    Op op;
-    node_image(kv.first, kv.second, &op);
-    ops.push_back(op);
-    if (ops.size() == batch) {
-      int rc = apply_ops(this, ops);
-      if (rc) return rc;
-      ops.clear();
-    }
-  }
-  int rc = apply_ops(this, ops);
+// (stamp, slot) of every live key sorted by stamp: the outer LRU order at this moment.  Later stamps only make
+// records stale, and keys inserted later are newer than every valid record, so the array serves until it runs out.
+int kvb_index::ensure_order() {
+  if (order_valid && h_ctr.order_head < (unsigned long long)order_n) return KVB_OK;
+  int rc = sync_counters();
   if (rc) return rc;
-  dev_live = (int64_t)data.size();
-  dirty.clear();
-  stale_mirror = false;
+  const int64_t live = (int64_t)h_ctr.live;
+  if (live > order_cap) {
+    for (void* p : {(void*)order_ts, (void*)order_slot, (void*)order_ts_in, (void*)order_slot_in})
+      if (p) cudaFree(p);
+    order_ts = order_ts_in = nullptr;
+    order_slot = order_slot_in = nullptr;
+    order_cap = 0;
+    const int64_t cap = std::max<int64_t>(live * 5 / 4, 1024);
+    KVB_CUDA_TRY(cudaMalloc(&order_ts, cap * sizeof(unsigned long long)));
+    KVB_CUDA_TRY(cudaMalloc(&order_ts_in, cap * sizeof(unsigned long long)));
+    KVB_CUDA_TRY(cudaMalloc(&order_slot, cap * sizeof(uint32_t)));
+    KVB_CUDA_TRY(cudaMalloc(&order_slot_in, cap * sizeof(uint32_t)));
+    order_cap = cap;
+  }
+  if (!d_cursor) KVB_CUDA_TRY(cudaMalloc(&d_cursor, sizeof(unsigned long long)));
+  KVB_CUDA_TRY(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), stream));
+  const unsigned threads = 256;
+  KVB_LAUNCH(index_collect_order_kernel, (unsigned)((slots + threads - 1) / threads), threads, stream, ref(),
+             order_ts_in, order_slot_in, d_cursor, (unsigned long long)order_cap);
+  KVB_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  order_n = live;
+  if (live > 0) {
+#ifdef KVB_HOST_SIM
+    sim_sort_pairs(order_ts_in, order_ts, order_slot_in, order_slot, live);
+#else
+    size_t need = 0;
+    KVB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, order_ts_in, order_ts, order_slot_in, order_slot,
+                                                 (int)live, 0, 64, stream));
+    if (need > sort_tmp_bytes) {
+      if (d_sort_tmp) cudaFree(d_sort_tmp);
+      d_sort_tmp = nullptr;
+      sort_tmp_bytes = 0;
+      KVB_CUDA_TRY(cudaMalloc(&d_sort_tmp, need));
+      sort_tmp_bytes = need;
+    }
+    KVB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_sort_tmp, need, order_ts_in, order_ts, order_slot_in, order_slot,
+                                                 (int)live, 0, 64, stream));
+    count_launch();
+#endif
+  }
+  Counters c = h_ctr;
+  c.order_head = 0;
+  KVB_CUDA_TRY(cudaStreamSynchronize(stream));
+  KVB_CUDA_TRY(cudaMemcpy(d_ctr, &c, sizeof(Counters), cudaMemcpyHostToDevice));
+  h_ctr = c;
+  order_valid = true;
+  ++n_order_builds;
   return KVB_OK;
 }
 
 int kvb_index::flush_locked() {
-  if (stale_mirror) return rebuild(slots);  // an earlier rebuild stopped half-way
-  if (dirty.empty()) return KVB_OK;
-  std::sort(dirty.begin(), dirty.end());
-  dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
-  // grow before the table gets crowded: live + tombstones + incoming <= 0.6 * slots
-  const uint64_t need = (uint64_t)(data.size() + dev_tomb + dirty.size());
-  if (need * 10 > slots * 6) {
-    uint64_t ns = slots;
-    while ((uint64_t)data.size() * 10 > ns * 3) ns <<= 1;  // target load <= 0.3 after rebuild
-    if (ns == slots && (uint64_t)(data.size() + dirty.size()) * 10 > slots * 6) ns <<= 1;
-    return rebuild(ns);  // rebuild drops every tombstone and clears dirty
-  }
-  std::vector<Op> ops;
-  ops.reserve(dirty.size());
-  int64_t dels = 0;
-  for (uint64_t k : dirty) {
-    Op op;
-    auto it = data.find(k);
-    if (it == data.end()) {
-      op.key = k;
-      op.count = 0xffffffffu;
-      std::memset(op.ent, 0, sizeof(op.ent));
-      ++dels;
-    } else {
-      node_image(k, it->second, &op);
+  if (n_ops == 0) return KVB_OK;
+  // grow before the table gets crowded: live + tombstones + incoming <= 0.6 * slots (bounds first, exact if they trip)
+  if ((uint64_t)(live_ub + tomb_ub) * 10 > slots * 6) {
+    int rc = sync_counters();
+    if (rc) return rc;
+    if ((uint64_t)(live_ub + tomb_ub) * 10 > slots * 6) {
+      uint64_t ns = slots;
+      while ((uint64_t)live_ub * 10 > ns * 3) ns <<= 1;  // target load <= 0.3 after the move
+      rc = rehash(ns);                                   // same size: only drops the tombstones
+      if (rc) return rc;
     }
-    ops.push_back(op);
   }
-  int rc = apply_ops(this, ops);
-  if (rc) return rc;
-  dev_tomb += dels;  // upper bound (a delete of a never-flushed key leaves no tombstone)
-  dirty.clear();
+  bool may_evict = live_ub > max_keys;
+  if (may_evict) {
+    int rc = sync_counters();
+    if (rc) return rc;
+    may_evict = live_ub > max_keys;
+  }
+  const bool sequential = may_evict || (int64_t)n_ops <= kSeqThreshold;
+  if (may_evict) {
+    int rc = ensure_order();
+    if (rc) return rc;
+  }
+  KVB_CUDA_TRY(cudaMemcpyAsync(d_ops, h_ops, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, stream));
+  KVB_CUDA_TRY(cudaMemcpyAsync(d_ents, h_ents, n_ents * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  KVB_CUDA_TRY(cudaEventRecord(q_free, stream));
+  q_busy = true;
+  const unsigned long long seq_base = seq;
+  seq += n_ops;
+  const int64_t n = (int64_t)n_ops;
+  if (sequential) {
+    KVB_LAUNCH(index_apply_seq_kernel, 1, 1, stream, ref(), d_ops, d_ents, n, seq_base, (unsigned long long)max_keys,
+               order_ts, order_slot, (unsigned long long)(may_evict ? order_n : 0));
+    KVB_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    ++n_flush_seq;
+  } else {
+    const unsigned threads = 128;
+    const unsigned grid = (unsigned)((n + threads - 1) / threads);
+    KVB_LAUNCH(index_sort_keys_kernel, grid, threads, stream, d_ops, n, d_skey_in, d_sidx_in);
+    KVB_CUDA_TRY(cudaGetLastError());
+#ifdef KVB_HOST_SIM
+    sim_sort_pairs(d_skey_in, d_skey_out, d_sidx_in, d_sidx_out, n);
+#else
+    size_t need = sort_tmp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(d_sort_tmp, need, d_skey_in, d_skey_out, d_sidx_in, d_sidx_out,
+                                                    (int)n, 0, 64, stream);
+    if (e != cudaSuccess) {
+      set_error("index: sorting %lld ops failed: %s", (long long)n, cudaGetErrorString(e));
+      return KVB_ERR_CUDA;
+    }
+#endif
+    KVB_LAUNCH(index_apply_par_kernel, grid, threads, stream, ref(), d_ops, d_ents, d_skey_out, d_sidx_out, n,
+               seq_base);
+    KVB_CUDA_TRY(cudaGetLastError());
+    count_launch(3);
+    ++n_flush_par;
+  }
+  n_ops_total += n;
+  n_ops = n_ents = 0;
+  q_adds = q_evicts = 0;  // they stay counted inside live_ub / tomb_ub until the next exact read
+  if (may_evict) {
+    int rc = sync_counters();  // the order head moved; exact counts keep the bounds from drifting at capacity
+    if (rc) return rc;
+  }
+  return KVB_OK;
+}
+
+int kvb_index::queue_ops(uint8_t type, const uint64_t* keys, int64_t n_keys, const kvb_pod_entry_t* entries,
+                         int32_t n_entries) {
+  int64_t done = 0;
+  while (done < n_keys) {
+    if (n_ops == kOpsCap || n_ents + (size_t)n_entries > kEntsCap) {
+      int rc = flush_locked();
+      if (rc) return rc;
+    }
+    if (q_busy) {  // the pinned queue is still being read by the previous flush's copies
+      KVB_CUDA_TRY(cudaEventSynchronize(q_free));
+      q_busy = false;
+    }
+    const uint32_t ent_off = (uint32_t)n_ents;
+    for (int32_t e = 0; e < n_entries; ++e)
+      h_ents[n_ents++] = pack_entry(entries[e].pod, entries[e].tier, entries[e].speculative);
+    const int64_t take = std::min<int64_t>(n_keys - done, (int64_t)(kOpsCap - n_ops));
+    for (int64_t i = 0; i < take; ++i) {
+      OpRec& r = h_ops[n_ops++];
+      r.key = keys[done + i];
+      r.ent_off = ent_off;
+      r.ent_cnt = (uint16_t)n_entries;
+      r.type = type;
+      r.pad = 0;
+    }
+    if (type == kOpAdd) {
+      q_adds += take;
+      live_ub += take;
+    } else {
+      q_evicts += take;
+      tomb_ub += take;
+    }
+    done += take;
+  }
+  return KVB_OK;
+}
+
+// pod filter bitmap (65536 bits), resident on the device and re-uploaded only when the filter changes.  When it does
+// change the bitmap is written into the caller's pinned staging block (*staged = true) and copied from there on the
+// stream — no synchronisation, the staging block outlives the call's own stream sync.
+int kvb_index::set_filter(const uint16_t* pods, int32_t n, uint8_t* h_stage, bool* staged, const uint32_t** out) {
+  *out = nullptr;
+  *staged = false;
+  if (n <= 0) return KVB_OK;
+  if (!d_filter) KVB_CUDA_TRY(cudaMalloc(&d_filter, 2048 * sizeof(uint32_t)));
+  *out = d_filter;
+  if (filter_valid && filter_cached.size() == (size_t)n && std::memcmp(filter_cached.data(), pods, (size_t)n * 2) == 0)
+    return KVB_OK;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(h_stage);
+  std::memset(bits, 0, 2048 * sizeof(uint32_t));
+  for (int32_t i = 0; i < n; ++i) bits[pods[i] >> 5] |= 1u << (pods[i] & 31);
+  KVB_CUDA_TRY(cudaMemcpyAsync(d_filter, bits, 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  filter_cached.assign(pods, pods + n);
+  filter_valid = true;
+  *staged = true;
   return KVB_OK;
 }
 
@@ -505,18 +1027,43 @@ int kvb_index_create(int device, int64_t max_keys, int32_t pods_per_key, int64_t
     idx->device = device;
     idx->max_keys = max_keys;
     idx->pods_per_key = pods_per_key;
+    idx->eng.reset(new EngMap(max_keys));
     for (int i = 0; i < 256; ++i) idx->tier_w_host[i] = 1.0;  // unknown tier -> 1.0 (kvblock_scorer.go:93-98)
     KVB_CUDA_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+    KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->q_free, cudaEventDisableTiming));
+    KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_a, cudaEventDefault));
+    KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_b, cudaEventDefault));
+    KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_c, cudaEventDefault));
     KVB_CUDA_TRY(cudaMalloc(&idx->tier_w, 256 * sizeof(double)));
     KVB_CUDA_TRY(cudaMemcpy(idx->tier_w, idx->tier_w_host, 256 * sizeof(double), cudaMemcpyHostToDevice));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_ctr, sizeof(Counters)));
+    KVB_CUDA_TRY(cudaMemset(idx->d_ctr, 0, sizeof(Counters)));
     int64_t exp_keys = std::max<int64_t>(expected_keys, 1024);
     exp_keys = std::min<int64_t>(exp_keys, max_keys);
     uint64_t slots = 2048;
     while (slots * 3 < (uint64_t)exp_keys * 10) slots <<= 1;  // load <= 0.3 at expected size
     idx->slots = slots;
-    KVB_CUDA_TRY(cudaMalloc(&idx->table, slots * sizeof(Bucket)));
-    KVB_CUDA_TRY(cudaMemset(idx->table, 0, slots * sizeof(Bucket)));
-    if (expected_keys > 0) idx->data.reserve((size_t)std::min<int64_t>(expected_keys, max_keys));
+    int rc = idx->alloc_table(slots, &idx->table, &idx->ts);
+    if (rc) return rc;
+    // op queue: pinned on the GPU's NUMA node; device copies and sort buffers sized for a full queue
+    KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&idx->h_ops), kvb_index::kOpsCap * sizeof(OpRec),
+                                 cudaHostAllocPortable));
+    KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&idx->h_ents), kvb_index::kEntsCap * sizeof(uint32_t),
+                                 cudaHostAllocPortable));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_ops, kvb_index::kOpsCap * sizeof(OpRec)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_ents, kvb_index::kEntsCap * sizeof(uint32_t)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_skey_in, kvb_index::kOpsCap * sizeof(uint64_t)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_skey_out, kvb_index::kOpsCap * sizeof(uint64_t)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_sidx_in, kvb_index::kOpsCap * sizeof(uint32_t)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_sidx_out, kvb_index::kOpsCap * sizeof(uint32_t)));
+#ifndef KVB_HOST_SIM
+    size_t need = 0;
+    KVB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, idx->d_skey_in, idx->d_skey_out, idx->d_sidx_in,
+                                                 idx->d_sidx_out, (int)kvb_index::kOpsCap, 0, 64, idx->stream));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_sort_tmp, need));
+    idx->sort_tmp_bytes = need;
+#endif
+    KVB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
     *out = idx.release();
     return KVB_OK;
   });
@@ -526,11 +1073,16 @@ void kvb_index_destroy(kvb_index_t* idx) {
   if (!idx) return;
   DeviceGuard g(idx->device);
   if (idx->stream) cudaStreamSynchronize(idx->stream);
-  if (idx->table) cudaFree(idx->table);
-  if (idx->tier_w) cudaFree(idx->tier_w);
-  if (idx->d_scratch) cudaFree(idx->d_scratch);
-  if (idx->h_scratch) cudaFreeHost(idx->h_scratch);
-  if (idx->d_filter) cudaFree(idx->d_filter);
+  for (void* p : {(void*)idx->table, (void*)idx->ts, (void*)idx->d_ctr, (void*)idx->tier_w, (void*)idx->d_ops,
+                  (void*)idx->d_ents, (void*)idx->d_skey_in, (void*)idx->d_skey_out, (void*)idx->d_sidx_in,
+                  (void*)idx->d_sidx_out, idx->d_sort_tmp, (void*)idx->order_ts, (void*)idx->order_slot,
+                  (void*)idx->order_ts_in, (void*)idx->order_slot_in, (void*)idx->d_cursor, (void*)idx->d_scratch,
+                  (void*)idx->d_filter})
+    if (p) cudaFree(p);
+  for (void* p : {(void*)idx->h_ops, (void*)idx->h_ents, (void*)idx->h_scratch})
+    if (p) cudaFreeHost(p);
+  for (cudaEvent_t e : {idx->q_free, idx->ev_a, idx->ev_b, idx->ev_c})
+    if (e) cudaEventDestroy(e);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
 }
@@ -541,6 +1093,7 @@ int kvb_index_set_tier_weight(kvb_index_t* idx, uint8_t tier, double weight, int
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->device);
     idx->tier_w_host[tier] = known ? weight : 1.0;
+    KVB_CUDA_TRY(cudaStreamSynchronize(idx->stream));  // no scoring kernel may be reading the table
     KVB_CUDA_TRY(cudaMemcpy(idx->tier_w + tier, &idx->tier_w_host[tier], sizeof(double), cudaMemcpyHostToDevice));
     return KVB_OK;
   });
@@ -554,108 +1107,64 @@ int kvb_index_add(kvb_index_t* idx, const uint64_t* engine_keys, int64_t n_engin
     KVB_REQUIRE(n_request > 0 && n_entries > 0 && request_keys && entries,
                 "no keys or entries provided for adding to index");
     KVB_REQUIRE(!has_engine_keys || n_engine > 0, "engineKeys is non-nil but empty");
+    KVB_REQUIRE(n_entries <= 65535, "too many entries in one Add");
     std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
     if (has_engine_keys) {  // in_memory.go:166-177
-      const int64_t n = std::max(n_engine, n_request);
-      std::vector<uint64_t> order;
-      std::unordered_map<uint64_t, std::vector<uint64_t>> m;
-      for (int64_t i = 0; i < n; ++i) {
-        const uint64_t ek = engine_keys[i * n_engine / n];
-        const uint64_t rk = request_keys[i * n_request / n];
-        auto it = m.find(ek);
-        if (it == m.end()) {
-          order.push_back(ek);
-          m[ek].push_back(rk);
-        } else {
-          it->second.push_back(rk);
-        }
+      EngMap& em = *idx->eng;
+      bool one_to_one = n_engine == n_request;  // the common shape: one request key per engine key, no repeats
+      if (one_to_one && n_engine > 1) {
+        std::vector<uint64_t> sorted(engine_keys, engine_keys + n_engine);
+        std::sort(sorted.begin(), sorted.end());
+        one_to_one = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
       }
-      for (uint64_t ek : order) idx->eng_add(ek, std::move(m[ek]));
-    }
-    for (int64_t i = 0; i < n_request; ++i) {  // in_memory.go:180-221
-      const uint64_t rk = request_keys[i];
-      auto it = idx->data.find(rk);
-      if (it != idx->data.end()) {
-        idx->touch(it);
+      if (one_to_one) {
+        for (int64_t i = 0; i < n_engine; ++i) em.put(engine_keys[i], &request_keys[i], 1);
       } else {
-        KeyNode n;
-        idx->data_lru.push_back(rk);
-        n.lru = std::prev(idx->data_lru.end());
-        it = idx->data.emplace(rk, n).first;
-        if ((int64_t)idx->data.size() > idx->max_keys) {  // outer LRU evicts the oldest key
-          const uint64_t old = idx->data_lru.front();
-          auto oit = idx->data.find(old);
-          if (oit != idx->data.end()) idx->erase_key(oit);
+        const int64_t n = std::max(n_engine, n_request);
+        std::vector<uint64_t> order;
+        std::unordered_map<uint64_t, std::vector<uint64_t>> m;
+        for (int64_t i = 0; i < n; ++i) {
+          const uint64_t ek = engine_keys[i * n_engine / n];
+          const uint64_t rk = request_keys[i * n_request / n];
+          auto it = m.find(ek);
+          if (it == m.end()) {
+            order.push_back(ek);
+            m[ek].push_back(rk);
+          } else {
+            it->second.push_back(rk);
+          }
+        }
+        // Go iterates newMappings in random order (in_memory.go:174-176); first-seen order here (only observable when
+        // the engine-key LRU is at capacity)
+        for (uint64_t ek : order) {
+          const auto& v = m[ek];
+          em.put(ek, v.data(), v.size());
         }
       }
-      KeyNode& node = it->second;
-      for (int32_t e = 0; e < n_entries; ++e) {  // inner lru.Add
-        int at = -1;
-        for (int k = 0; k < node.count; ++k)
-          if (same_entry(node.e[k], entries[e])) {
-            at = k;
-            break;
-          }
-        kvb_pod_entry_t v = entries[e];
-        v.speculative = v.speculative ? 1 : 0;
-        if (at >= 0) {  // move to newest
-          for (int k = at; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
-          node.e[node.count - 1] = v;
-        } else {
-          if (node.count == idx->pods_per_key) {  // evict oldest pod entry
-            for (int k = 0; k + 1 < node.count; ++k) node.e[k] = node.e[k + 1];
-            node.count--;
-          }
-          node.e[node.count++] = v;
-        }
-      }
-      idx->dirty.push_back(rk);
     }
-    return KVB_OK;
+    return idx->queue_ops(kOpAdd, request_keys, n_request, entries, n_entries);  // in_memory.go:180-221
   });
-}
-
-static void evict_from_request_key(kvb_index* idx, uint64_t rk, const kvb_pod_entry_t* entries, int32_t n) {
-  auto it = idx->data.find(rk);  // in_memory.go:260-264 (Get refreshes recency)
-  if (it == idx->data.end()) return;
-  idx->touch(it);
-  KeyNode& node = it->second;
-  for (int32_t e = 0; e < n; ++e) {
-    for (int k = 0; k < node.count; ++k)
-      if (same_entry(node.e[k], entries[e])) {
-        for (int q = k; q + 1 < node.count; ++q) node.e[q] = node.e[q + 1];
-        node.count--;
-        break;
-      }
-  }
-  if (node.count == 0) {
-    idx->erase_key(it);  // in_memory.go:279-292
-  } else {
-    idx->dirty.push_back(rk);
-  }
 }
 
 int kvb_index_evict(kvb_index_t* idx, uint64_t key, int key_type, const kvb_pod_entry_t* entries, int32_t n_entries) {
   return kvb::guarded([&]() -> int {
     KVB_REQUIRE(idx != nullptr, "index is NULL");
     KVB_REQUIRE(n_entries > 0 && entries, "no entries provided for eviction from index");  // in_memory.go:230-232
+    KVB_REQUIRE(n_entries <= 65535, "too many entries in one Evict");
     std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
     if (key_type == KVB_KEY_ENGINE) {
-      auto it = idx->eng.find(key);
-      if (it == idx->eng.end()) return KVB_OK;  // nothing to evict (in_memory.go:238-242)
-      std::vector<uint64_t> rks = it->second.rks;
-      for (uint64_t rk : rks) evict_from_request_key(idx, rk, entries, n_entries);
-      it = idx->eng.find(key);
-      if (it != idx->eng.end()) {
-        idx->eng_lru.erase(it->second.lru);
-        idx->eng.erase(it);
-      }
-      return KVB_OK;
+      EngMap& em = *idx->eng;
+      const int64_t id = em.find(key);
+      if (id < 0) return KVB_OK;  // nothing to evict (in_memory.go:238-242)
+      std::vector<uint64_t> rks;
+      em.for_each_rk(id, [&](uint64_t rk) { rks.push_back(rk); });
+      em.erase(id);  // in_memory.go:247
+      if (rks.empty()) return KVB_OK;
+      return idx->queue_ops(kOpEvict, rks.data(), (int64_t)rks.size(), entries, n_entries);
     }
-    if (key_type == KVB_KEY_REQUEST) {
-      evict_from_request_key(idx, key, entries, n_entries);
-      return KVB_OK;
-    }
+    if (key_type == KVB_KEY_REQUEST) return idx->queue_ops(kOpEvict, &key, 1, entries, n_entries);
     set_error("unknown key type: %d", key_type);  // in_memory.go:252-254
     return KVB_ERR_INVALID;
   });
@@ -665,34 +1174,30 @@ int kvb_index_get_request_key(kvb_index_t* idx, uint64_t engine_key, uint64_t* o
   return kvb::guarded([&]() -> int {
     KVB_REQUIRE(idx && out, "NULL argument");
     std::lock_guard<std::mutex> lk(idx->mu);
-    auto it = idx->eng.find(engine_key);
-    if (it == idx->eng.end() || it->second.rks.empty()) {  // in_memory.go:299-302
+    const int64_t id = idx->eng->find(engine_key);
+    if (id < 0 || idx->eng->node(id).n == 0) {  // in_memory.go:299-302
       set_error("engine key not found: %llu", (unsigned long long)engine_key);
       *out = 0;
       return KVB_ERR_NOTFOUND;
     }
-    idx->touch_eng(it);
-    *out = it->second.rks.back();
+    idx->eng->touch(id);
+    *out = idx->eng->node(id).rk_last;
     return KVB_OK;
   });
 }
 
 int64_t kvb_index_num_keys(kvb_index_t* idx) {
   if (!idx) return 0;
-  std::lock_guard<std::mutex> lk(idx->mu);
-  return (int64_t)idx->data.size();
-}
-
-int kvb_index_host_peek(kvb_index_t* idx, uint64_t request_key, kvb_pod_entry_t* out_entries, int32_t cap) {
-  return kvb::guarded([&]() -> int {
-    if (!idx) return -1;
+  int64_t n = 0;
+  kvb::guarded([&]() -> int {
     std::lock_guard<std::mutex> lk(idx->mu);
-    auto it = idx->data.find(request_key);
-    if (it == idx->data.end()) return -1;
-    const int n = std::min<int>(it->second.count, cap);
-    for (int i = 0; i < n; ++i) out_entries[i] = it->second.e[i];
-    return it->second.count;
+    DeviceGuard g(idx->device);
+    int rc = idx->flush_locked();
+    if (rc == KVB_OK) rc = idx->sync_counters();
+    n = rc == KVB_OK ? (int64_t)idx->h_ctr.live : 0;
+    return rc;
   });
+  return n;
 }
 
 int kvb_index_flush(kvb_index_t* idx, void* stream) {
@@ -701,8 +1206,97 @@ int kvb_index_flush(kvb_index_t* idx, void* stream) {
     KVB_REQUIRE(idx != nullptr, "index is NULL");
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->device);
-    return idx->flush_locked();
+    int rc = idx->flush_locked();
+    if (rc) return rc;
+    KVB_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    return KVB_OK;
   });
+}
+
+int kvb_index_get_stats(kvb_index_t* idx, kvb_index_stats_t* out) {
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx && out, "NULL argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    int rc = idx->flush_locked();
+    if (rc == KVB_OK) rc = idx->sync_counters();
+    if (rc) return rc;
+    std::memset(out, 0, sizeof(*out));
+    out->live_keys = (int64_t)idx->h_ctr.live;
+    out->tombstones = (int64_t)idx->h_ctr.tombs;
+    out->table_slots = (int64_t)idx->slots;
+    out->engine_keys = (int64_t)idx->eng->size();
+    out->ops_applied = idx->n_ops_total;
+    out->flushes_parallel = idx->n_flush_par;
+    out->flushes_sequential = idx->n_flush_seq;
+    out->rehashes = idx->n_rehash;
+    out->lru_evictions = (int64_t)idx->h_ctr.evicted;
+    out->order_builds = idx->n_order_builds;
+    out->order_stale_skipped = (int64_t)idx->h_ctr.stale_skipped;
+    out->order_scans = (int64_t)idx->h_ctr.scans;
+    out->last_hash_us = idx->last_hash_us;
+    out->last_score_us = idx->last_score_us;
+    return KVB_OK;
+  });
+}
+
+// shared by kvb_index_lookup and kvb_index_host_peek; caller holds the lock and the device
+static int lookup_locked(kvb_index* idx, const uint64_t* keys, int64_t n, const uint16_t* pod_filter, int32_t n_filter,
+                         bool stamp, const int32_t** cnt_out, const uint32_t** ent_out) {
+  int rc = idx->flush_locked();
+  if (rc) return rc;
+  const size_t o_keys = 0, o_cnt = (size_t)n * 8, o_ent = o_cnt + (((size_t)n * 4 + 255) & ~size_t(255));
+  const size_t o_filt = o_ent + (((size_t)n * kMaxEnt * 4 + 255) & ~size_t(255));
+  const size_t total = o_filt + 2048 * sizeof(uint32_t);
+  rc = idx->ensure_scratch(total, total);
+  if (rc) return rc;
+  const uint32_t* filt = nullptr;
+  bool staged = false;
+  rc = idx->set_filter(pod_filter, n_filter, idx->h_scratch + o_filt, &staged, &filt);
+  if (rc) return rc;
+  std::memcpy(idx->h_scratch, keys, (size_t)n * 8);
+  cudaStream_t s = idx->stream;
+  KVB_CUDA_TRY(cudaMemcpyAsync(idx->d_scratch + o_keys, idx->h_scratch, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  unsigned long long stamp_base = 0ull;
+  if (stamp) {
+    stamp_base = idx->seq;
+    idx->seq += (unsigned long long)n;
+  }
+  const int threads = 128;
+  KVB_LAUNCH(index_lookup_kernel, (unsigned)((n + threads - 1) / threads), threads, s, idx->table, idx->slots - 1,
+             reinterpret_cast<const uint64_t*>(idx->d_scratch + o_keys), n, filt,
+             reinterpret_cast<int32_t*>(idx->d_scratch + o_cnt), reinterpret_cast<uint32_t*>(idx->d_scratch + o_ent),
+             idx->ts, stamp_base);
+  KVB_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  KVB_CUDA_TRY(cudaMemcpyAsync(idx->h_scratch + o_cnt, idx->d_scratch + o_cnt, o_filt - o_cnt, cudaMemcpyDeviceToHost, s));
+  KVB_CUDA_TRY(cudaStreamSynchronize(s));
+  *cnt_out = reinterpret_cast<const int32_t*>(idx->h_scratch + o_cnt);
+  *ent_out = reinterpret_cast<const uint32_t*>(idx->h_scratch + o_ent);
+  return KVB_OK;
+}
+
+int kvb_index_host_peek(kvb_index_t* idx, uint64_t request_key, kvb_pod_entry_t* out_entries, int32_t cap) {
+  int n_out = -1;
+  kvb::guarded([&]() -> int {
+    if (!idx) return KVB_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    const int32_t* cnt = nullptr;
+    const uint32_t* ent = nullptr;
+    int rc = lookup_locked(idx, &request_key, 1, nullptr, 0, false, &cnt, &ent);  // no recency refresh: a debug read
+    if (rc) return rc;
+    if (cnt[0] == -1) return KVB_OK;
+    const int c = cnt[0] == -2 ? 0 : cnt[0];
+    for (int i = 0; i < c && i < cap; ++i) {
+      out_entries[i].pod = (uint16_t)(ent[i] & 0xffffu);
+      out_entries[i].tier = (uint8_t)((ent[i] >> 16) & 0xffu);
+      out_entries[i].speculative = (uint8_t)((ent[i] >> 24) & 1u);
+    }
+    n_out = c;
+    return KVB_OK;
+  });
+  return n_out;
 }
 
 int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const uint16_t* pod_filter, int32_t n_filter,
@@ -713,42 +1307,18 @@ int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const ui
     KVB_REQUIRE(out_counts && out_entries && out_cut, "NULL output");
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->device);
-    int rc = idx->flush_locked();
+    const int32_t* cnt = nullptr;
+    const uint32_t* ent = nullptr;
+    // data.Get refreshes the outer LRU for every key that is found (in_memory.go:120): stamped by the kernel
+    int rc = lookup_locked(idx, keys, n, pod_filter, n_filter, true, &cnt, &ent);
     if (rc) return rc;
-    const uint32_t* filt = nullptr;
-    rc = idx->set_filter(pod_filter, n_filter, &filt);
-    if (rc) return rc;
-    const size_t o_keys = 0, o_cnt = (size_t)n * 8, o_ent = o_cnt + (((size_t)n * 4 + 255) & ~size_t(255));
-    const size_t total = o_ent + (size_t)n * kMaxEnt * 4;
-    rc = idx->ensure_scratch(total, total);
-    if (rc) return rc;
-    std::memcpy(idx->h_scratch, keys, (size_t)n * 8);
-    cudaStream_t s = idx->stream;
-    KVB_CUDA_TRY(cudaMemcpyAsync(idx->d_scratch + o_keys, idx->h_scratch, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    const int threads = 128;
-    index_lookup_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(
-        idx->table, idx->slots - 1, reinterpret_cast<const uint64_t*>(idx->d_scratch + o_keys), n, filt,
-        reinterpret_cast<int32_t*>(idx->d_scratch + o_cnt), reinterpret_cast<uint32_t*>(idx->d_scratch + o_ent));
-    KVB_CUDA_TRY(cudaGetLastError());
-    count_launch();
-    KVB_CUDA_TRY(cudaMemcpyAsync(idx->h_scratch + o_cnt, idx->d_scratch + o_cnt, total - o_cnt, cudaMemcpyDeviceToHost, s));
-    KVB_CUDA_TRY(cudaStreamSynchronize(s));
-    const int32_t* cnt = reinterpret_cast<const int32_t*>(idx->h_scratch + o_cnt);
-    const uint32_t* ent = reinterpret_cast<const uint32_t*>(idx->h_scratch + o_ent);
     int64_t cut = n;
     for (int64_t i = 0; i < n; ++i) {
-      if (cut < n) {  // after the cut nothing is looked at (in_memory.go:121-124 returns)
+      if (cut < n || cnt[i] == -1) {  // after the cut nothing is looked at (in_memory.go:121-124 returns)
         out_counts[i] = -1;
         continue;
       }
-      if (cnt[i] == -1) {
-        out_counts[i] = -1;
-        continue;
-      }
-      // data.Get refreshes the outer LRU for every key that is found (in_memory.go:120)
-      auto it = idx->data.find(keys[i]);
-      if (it != idx->data.end()) idx->touch(it);
-      if (cnt[i] == -2) {
+      if (cnt[i] == -2) {  // present but empty: cannot occur (a key whose last pod leaves is removed), kept for parity
         cut = i;
         out_counts[i] = 0;
         continue;
@@ -766,15 +1336,17 @@ int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const ui
   });
 }
 
-// keys already on the device at d_keys / d_koff (inside idx->d_scratch or elsewhere)
-static int score_device(kvb_index* idx, const uint64_t* d_keys, const int64_t* d_koff, int32_t n_prompts,
-                        const uint32_t* filt, uint8_t* d_found, int32_t* d_n, uint16_t* d_pods, double* d_scores) {
-  const int64_t grid = ((int64_t)n_prompts + kScoreWarps - 1) / kScoreWarps;
-  index_score_kernel<<<(unsigned)grid, kScoreWarps * 32, 0, idx->stream>>>(
-      idx->table, idx->slots - 1, d_keys, d_koff, n_prompts, filt, idx->tier_w, d_n, d_pods, d_scores, d_found);
-  KVB_CUDA_TRY(cudaGetLastError());
-  count_launch();
-  return KVB_OK;
+#ifndef KVB_HOST_SIM
+// memory a kernel can address in place: device memory, or pinned host memory (cudaHostAlloc / kvb_host_alloc /
+// cudaHostRegister) through its device alias; nullptr for pageable host memory
+static void* device_alias(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice) return a.devicePointer;
+  return nullptr;
 }
 
 static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t* key_off, int32_t n_prompts,
@@ -786,96 +1358,123 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
   DeviceGuard g(idx->device);
   int rc = idx->flush_locked();
   if (rc) return rc;
-  const uint32_t* filt = nullptr;
-  rc = idx->set_filter(pod_filter, n_filter, &filt);
-  if (rc) return rc;
   const bool from_tokens = tokens != nullptr;
-  std::vector<int64_t> koff_local;
+  const bool touch = (flags & KVB_SCORE_NO_TOUCH) == 0;
+  const bool timing = (flags & KVB_SCORE_TIME_KERNELS) != 0;
+  // ---- sizes
+  int64_t total_keys = 0;
   if (from_tokens) {
-    koff_local.resize((size_t)n_prompts + 1);
-    koff_local[0] = 0;
     for (int32_t p = 0; p < n_prompts; ++p) {
       KVB_REQUIRE(prompt_off[p + 1] >= prompt_off[p], "prompt_off not monotonic at %d", p);
-      koff_local[p + 1] = koff_local[p] + (prompt_off[p + 1] - prompt_off[p]) / block_size;
+      total_keys += (prompt_off[p + 1] - prompt_off[p]) / block_size;
     }
-    key_off = koff_local.data();
+  } else {
+    total_keys = key_off[n_prompts] - key_off[0];
   }
-  const int64_t total_keys = key_off[n_prompts] - key_off[0];
   const int64_t total_tok = from_tokens ? prompt_off[n_prompts] - prompt_off[0] : 0;
   const int64_t extra_bytes = (from_tokens && extra_off) ? extra_off[total_keys] : 0;
-  const bool touch = (flags & KVB_SCORE_TOUCH_LRU) != 0;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  // device/host scratch layout (same offsets on both sides)
+  // ---- one staging block, same offsets on the pinned host side and on the device:
+  //      [koff | poff | parents | eoff | ext | host keys | filter bits]  -> ONE H2D;   [n | pods | scores]  <- kernel
   size_t o = 0;
-  const size_t o_keys = o;   o += al((size_t)total_keys * 8);
   const size_t o_koff = o;   o += al(((size_t)n_prompts + 1) * 8);
-  const size_t o_n = o;      o += al((size_t)n_prompts * 4);
-  const size_t o_pods = o;   o += al((size_t)n_prompts * kMaxEnt * 2);
-  const size_t o_sc = o;     o += al((size_t)n_prompts * kMaxEnt * 8);
-  const size_t o_found = o;  o += touch ? al((size_t)total_keys) : 0;
-  const size_t o_tok = o;    o += from_tokens ? al((size_t)total_tok * 4) : 0;
   const size_t o_poff = o;   o += from_tokens ? al(((size_t)n_prompts + 1) * 8) : 0;
   const size_t o_par = o;    o += from_tokens ? al((size_t)n_prompts * 8) : 0;
   const size_t o_eoff = o;   o += (from_tokens && extra_off) ? al(((size_t)total_keys + 1) * 8) : 0;
   const size_t o_ext = o;    o += (from_tokens && extra_off) ? al((size_t)extra_bytes) : 0;
-  rc = idx->ensure_scratch(o, o);
+  const size_t o_hkeys = o;  o += from_tokens ? 0 : al((size_t)total_keys * 8);
+  const size_t o_filt = o;   o += n_filter > 0 ? 2048 * sizeof(uint32_t) : 0;
+  const size_t in_end = o;
+  const size_t o_n = o;      o += al((size_t)n_prompts * 4);
+  const size_t o_pods = o;   o += al((size_t)n_prompts * kMaxEnt * 2);
+  const size_t o_sc = o;     o += al((size_t)n_prompts * kMaxEnt * 8);
+  const size_t host_end = o;
+  const size_t o_keys = o;   o += from_tokens ? al((size_t)total_keys * 8) : 0;  // device only: hashed keys
+  const size_t o_tok = o;    o += from_tokens ? al((size_t)total_tok * 4) : 0;   // device only: copied tokens
+  rc = idx->ensure_scratch(o, host_end);
   if (rc) return rc;
   uint8_t* H = idx->h_scratch;
   uint8_t* D = idx->d_scratch;
   cudaStream_t s = idx->stream;
-  // stage inputs in pinned memory, one H2D per array
+  const uint32_t* filt = nullptr;
+  bool filt_staged = false;
+  rc = idx->set_filter(pod_filter, n_filter, H + o_filt, &filt_staged, &filt);
+  if (rc) return rc;
   int64_t* h_koff = reinterpret_cast<int64_t*>(H + o_koff);
-  for (int32_t p = 0; p <= n_prompts; ++p) h_koff[p] = key_off[p] - key_off[0];
-  KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, ((size_t)n_prompts + 1) * 8, cudaMemcpyHostToDevice, s));
   if (from_tokens) {
     int64_t* h_poff = reinterpret_cast<int64_t*>(H + o_poff);
-    for (int32_t p = 0; p <= n_prompts; ++p) h_poff[p] = prompt_off[p] - prompt_off[0];
+    h_koff[0] = 0;
+    for (int32_t p = 0; p < n_prompts; ++p) {
+      h_poff[p] = prompt_off[p] - prompt_off[0];
+      h_koff[p + 1] = h_koff[p] + (prompt_off[p + 1] - prompt_off[p]) / block_size;
+    }
+    h_poff[n_prompts] = prompt_off[n_prompts] - prompt_off[0];
     std::memcpy(H + o_par, parents, (size_t)n_prompts * 8);
-    // tokens go straight from the caller's buffer: pinned memory (kvb_host_alloc / cudaHostAlloc / registered) is read
-    // by the copy engine in place, pageable memory is staged by the driver (measured faster than staging it here:
-    // 0.32 vs 0.36-0.42 ms per 4 MB batch, tools/ab_stage.py); prompt_off and parents are adjacent in the scratch
-    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
-    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_poff, H + o_poff, (o_par + (size_t)n_prompts * 8) - o_poff,
-                                 cudaMemcpyHostToDevice, s));
     if (extra_off) {
       std::memcpy(H + o_eoff, extra_off, ((size_t)total_keys + 1) * 8);
       if (extra_bytes) std::memcpy(H + o_ext, extra, (size_t)extra_bytes);
-      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_eoff, H + o_eoff, (o_ext + (size_t)extra_bytes) - o_eoff,
-                                   cudaMemcpyHostToDevice, s));
     }
-    if (total_keys > 0) {
-      rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
-                              reinterpret_cast<uint64_t*>(D + o_par), n_prompts, block_size,
-                              extra_off ? D + o_ext : nullptr,
-                              extra_off ? reinterpret_cast<int64_t*>(D + o_eoff) : nullptr,
-                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
-      if (rc) return rc;
-    }
-  } else if (total_keys > 0) {
-    std::memcpy(H + o_keys, keys_host + key_off[0], (size_t)total_keys * 8);
-    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_keys, H + o_keys, (size_t)total_keys * 8, cudaMemcpyHostToDevice, s));
+  } else {
+    for (int32_t p = 0; p <= n_prompts; ++p) h_koff[p] = key_off[p] - key_off[0];
+    if (total_keys > 0) std::memcpy(H + o_hkeys, keys_host + key_off[0], (size_t)total_keys * 8);
   }
-  rc = score_device(idx, reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), n_prompts,
-                    filt, touch ? D + o_found : nullptr, reinterpret_cast<int32_t*>(D + o_n),
-                    reinterpret_cast<uint16_t*>(D + o_pods), reinterpret_cast<double*>(D + o_sc));
-  if (rc) return rc;
-  // results: n | pods | scores (| found) are adjacent: one D2H
-  const size_t back_end = touch ? o_found + (size_t)total_keys : o_sc + (size_t)n_prompts * kMaxEnt * 8;
-  KVB_CUDA_TRY(cudaMemcpyAsync(H + o_n, D + o_n, back_end - o_n, cudaMemcpyDeviceToHost, s));
-  if (touch && from_tokens && total_keys > 0)
-    KVB_CUDA_TRY(cudaMemcpyAsync(H + o_keys, D + o_keys, (size_t)total_keys * 8, cudaMemcpyDeviceToHost, s));
-  KVB_CUDA_TRY(cudaStreamSynchronize(s));
-  std::memcpy(out_n, H + o_n, (size_t)n_prompts * 4);
-  std::memcpy(out_pods, H + o_pods, (size_t)n_prompts * kMaxEnt * 2);
-  std::memcpy(out_scores, H + o_sc, (size_t)n_prompts * kMaxEnt * 8);
-  if (touch) {
-    const uint64_t* hk = reinterpret_cast<const uint64_t*>(H + o_keys);
-    const uint8_t* hf = H + o_found;
-    for (int64_t i = 0; i < total_keys; ++i) {
-      if (!hf[i]) continue;
-      auto it = idx->data.find(hk[i]);
-      if (it != idx->data.end()) idx->touch(it);
+  // the filter bitmap was copied by set_filter already (only when it changed); everything else in one copy
+  const size_t small_end = (n_filter > 0) ? o_filt : in_end;
+  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_a, s));
+  KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, small_end - o_koff, cudaMemcpyHostToDevice, s));
+  const uint64_t* d_keys = reinterpret_cast<const uint64_t*>(D + (from_tokens ? o_keys : o_hkeys));
+  if (from_tokens && total_keys > 0) {
+    // tokens: pinned buffers are read by the copy engine in place, pageable ones are staged by the driver (measured
+    // faster than staging them here, tools/ab_stage.py)
+    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
+    rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
+                            reinterpret_cast<uint64_t*>(D + o_par), n_prompts, block_size,
+                            extra_off ? D + o_ext : nullptr,
+                            extra_off ? reinterpret_cast<int64_t*>(D + o_eoff) : nullptr,
+                            reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
+    if (rc) return rc;
+  }
+  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_b, s));
+  // results land where the caller wants them when that memory is pinned (no D2H copy, no memcpy); otherwise in the
+  // pinned staging block through its device alias
+  int32_t* k_n = static_cast<int32_t*>(device_alias(out_n));
+  uint16_t* k_pods = static_cast<uint16_t*>(device_alias(out_pods));
+  double* k_sc = static_cast<double*>(device_alias(out_scores));
+  const bool direct_out = k_n && k_pods && k_sc;
+  if (!direct_out) {
+    uint8_t* Hd = static_cast<uint8_t*>(device_alias(H));
+    if (!Hd) {
+      set_error("index: the pinned staging block has no device alias");
+      return KVB_ERR_CUDA;
     }
+    k_n = reinterpret_cast<int32_t*>(Hd + o_n);
+    k_pods = reinterpret_cast<uint16_t*>(Hd + o_pods);
+    k_sc = reinterpret_cast<double*>(Hd + o_sc);
+  }
+  unsigned long long stamp_base = 0ull;
+  if (touch) {
+    stamp_base = idx->seq;
+    idx->seq += (unsigned long long)total_keys;
+  }
+  const int64_t grid = ((int64_t)n_prompts + kScoreWarps - 1) / kScoreWarps;
+  index_score_kernel<<<(unsigned)grid, kScoreWarps * 32, 0, s>>>(
+      idx->table, idx->slots - 1, d_keys, reinterpret_cast<const int64_t*>(D + o_koff), n_prompts, filt, idx->tier_w,
+      k_n, k_pods, k_sc, touch ? idx->ts : nullptr, stamp_base);
+  KVB_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_c, s));
+  KVB_CUDA_TRY(cudaStreamSynchronize(s));
+  if (!direct_out) {
+    std::memcpy(out_n, H + o_n, (size_t)n_prompts * 4);
+    std::memcpy(out_pods, H + o_pods, (size_t)n_prompts * kMaxEnt * 2);
+    std::memcpy(out_scores, H + o_sc, (size_t)n_prompts * kMaxEnt * 8);
+  }
+  if (timing) {
+    float ab = 0.f, bc = 0.f;
+    cudaEventElapsedTime(&ab, idx->ev_a, idx->ev_b);
+    cudaEventElapsedTime(&bc, idx->ev_b, idx->ev_c);
+    idx->last_hash_us = ab * 1e3f;  // staging copies + hash kernel
+    idx->last_score_us = bc * 1e3f;
   }
   return KVB_OK;
 }
@@ -908,5 +1507,6 @@ int kvb_index_score_tokens_batch(kvb_index_t* idx, const uint32_t* tokens, const
                         pod_filter, n_filter, flags, out_n, out_pods, out_scores);
   });
 }
+#endif  // !KVB_HOST_SIM
 
 }  // extern "C"

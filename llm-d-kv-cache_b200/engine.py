@@ -98,6 +98,17 @@ class StorageOffloadEngine:
     def exists(self, file: str) -> bool:
         return bool(_lib.load().kvb_engine_exists(self._h, file.encode()))
 
+    def lookup_prefix(self, files: Sequence[str]) -> int:
+        """How many CONSECUTIVE entries of ``files`` from the start exist in this engine's tier — the whole
+        ``SharedStorageOffloadingManager.lookup`` loop (manager.py:43-53) in one library call."""
+        n = len(files)
+        if n == 0:
+            return 0
+        paths = (C.c_char_p * n)(*[f.encode() for f in files])
+        hits = C.c_int32()
+        check(_lib.load().kvb_engine_lookup_prefix(self._h, n, paths, C.byref(hits)))
+        return int(hits.value)
+
     def arena_clear(self) -> None:
         check(_lib.load().kvb_engine_arena_clear(self._h))
 

@@ -225,11 +225,12 @@ class Index:
     Pod identifiers / device tiers are interned to the dense ids the C ABI carries."""
 
     def __init__(self, size: int = int(1e8), pod_cache_size: int = 10, device: int = 0, expected_keys: int = 0,
-                 medium_weights: Optional[dict] = None):
+                 medium_weights: Optional[dict] = None, lib=None):
         self.device = int(device)
+        self._lib = lib if lib is not None else _lib.load()  # tests hand in the host-simulation build of index.cu
         h = C.c_void_p()
-        check(_lib.load().kvb_index_create(self.device, int(size), int(pod_cache_size), int(expected_keys),
-                                           C.byref(h)))
+        self._check(self._lib.kvb_index_create(self.device, int(size), int(pod_cache_size), int(expected_keys),
+                                               C.byref(h)))
         self._h = h
         self.pods = _Interner(65536, "pod identifiers")
         self.tiers = _Interner(256, "device tiers")
@@ -237,9 +238,14 @@ class Index:
         self._weights: dict = {}
         self.set_medium_weights({"gpu": 1.0, "cpu": 0.8} if medium_weights is None else medium_weights)  # backend.go:26-31
 
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise _lib.KvbError(rc, self._lib.kvb_last_error().decode("utf-8", "replace"))
+        return rc
+
     def close(self):
         if getattr(self, "_h", None):
-            _lib.load().kvb_index_destroy(self._h)
+            self._lib.kvb_index_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -251,13 +257,14 @@ class Index:
     # -- interning ------------------------------------------------------------------------------
     def set_medium_weights(self, weights: Optional[dict]):
         """LongestPrefixScorer.MediumWeights (kvblock_scorer.go:82-85): unknown tier -> 1.0."""
-        self._weights = dict(weights or {})
-        for name, tid in self.tiers.ids.items():
-            self._push_weight(name, tid)
+        with self._tier_lock:  # _tier_id registers new tiers under the same lock
+            self._weights = dict(weights or {})
+            for name, tid in list(self.tiers.ids.items()):
+                self._push_weight(name, tid)
 
     def _push_weight(self, name: str, tid: int):
         known = name in self._weights
-        check(_lib.load().kvb_index_set_tier_weight(self._h, tid, float(self._weights.get(name, 1.0)), int(known)))
+        self._check(self._lib.kvb_index_set_tier_weight(self._h, tid, float(self._weights.get(name, 1.0)), int(known)))
 
     def _tier_id(self, name: str) -> int:
         tid = self.tiers.ids.get(name)
@@ -268,7 +275,7 @@ class Index:
                     # register the weight BEFORE the id becomes visible to other threads
                     nxt = len(self.tiers.names)
                     known = name in self._weights
-                    check(_lib.load().kvb_index_set_tier_weight(self._h, nxt, float(self._weights.get(name, 1.0)), int(known)))
+                    self._check(self._lib.kvb_index_set_tier_weight(self._h, nxt, float(self._weights.get(name, 1.0)), int(known)))
                     tid = self.tiers.get(name)
         return tid
 
@@ -300,7 +307,7 @@ class Index:
             raise ValueError("no keys or entries provided for adding to index")  # in_memory.go:155-157
         rk = np.asarray(request_keys, dtype=np.uint64)
         ek = None if engine_keys is None else np.asarray(engine_keys, dtype=np.uint64)
-        check(_lib.load().kvb_index_add(self._h, None if ek is None else ek.ctypes.data,
+        self._check(self._lib.kvb_index_add(self._h, None if ek is None else ek.ctypes.data,
                                         0 if ek is None else ek.size, int(ek is not None), rk.ctypes.data, rk.size,
                                         self._entries(entries), len(entries)))
 
@@ -309,14 +316,14 @@ class Index:
             raise ValueError("no entries provided for eviction from index")  # in_memory.go:230-232
         if key_type not in (ENGINE_KEY, REQUEST_KEY):
             raise ValueError(f"unknown key type: {key_type}")
-        check(_lib.load().kvb_index_evict(self._h, int(key), int(key_type), self._entries(entries), len(entries)))
+        self._check(self._lib.kvb_index_evict(self._h, int(key), int(key_type), self._entries(entries), len(entries)))
 
     def get_request_key(self, engine_key: int) -> int:
         out = C.c_uint64()
-        rc = _lib.load().kvb_index_get_request_key(self._h, int(engine_key), C.byref(out))
+        rc = self._lib.kvb_index_get_request_key(self._h, int(engine_key), C.byref(out))
         if rc == -4:
             raise KeyError(f"engine key not found: {engine_key}")  # in_memory.go:299-302
-        check(rc)
+        self._check(rc)
         return int(out.value)
 
     def lookup(self, request_keys: Sequence[int], pod_identifier_set: Optional[Iterable[str]] = None) -> dict:
@@ -328,7 +335,7 @@ class Index:
         counts = np.empty(keys.size, dtype=np.int32)
         ents = (PodEntryC * (keys.size * MAX_PODS_PER_KEY))()
         cut = C.c_int64()
-        check(_lib.load().kvb_index_lookup(self._h, keys.ctypes.data, keys.size,
+        self._check(self._lib.kvb_index_lookup(self._h, keys.ctypes.data, keys.size,
                                            None if filt is None else filt.ctypes.data, nf, counts.ctypes.data,
                                            C.addressof(ents), C.byref(cut)))
         out: dict = {}
@@ -344,11 +351,22 @@ class Index:
         return out
 
     def __len__(self) -> int:
-        return int(_lib.load().kvb_index_num_keys(self._h))
+        return int(self._lib.kvb_index_num_keys(self._h))
+
+    def stats(self) -> dict:
+        """Counters of the device-resident index (kvb_index_get_stats): live keys, table slots, how many op batches went
+        through the parallel / sequential apply kernels, LRU evictions, ..."""
+        st = _lib.IndexStats()
+        self._check(self._lib.kvb_index_get_stats(self._h, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in _lib.IndexStats._fields_}
+
+    def flush(self) -> None:
+        """Apply every queued Add / Evict on the device and wait for it."""
+        self._check(self._lib.kvb_index_flush(self._h, None))
 
     def host_peek(self, request_key: int):
         ents = (PodEntryC * MAX_PODS_PER_KEY)()
-        n = _lib.load().kvb_index_host_peek(self._h, int(request_key), ents, MAX_PODS_PER_KEY)
+        n = self._lib.kvb_index_host_peek(self._h, int(request_key), ents, MAX_PODS_PER_KEY)
         return None if n < 0 else [self._entry_from_c(ents[i]) for i in range(n)]
 
     # -- batched read path ----------------------------------------------------------------------
@@ -360,7 +378,7 @@ class Index:
             res.append({self.pods.names[int(out_pods[base + j])]: float(out_scores[base + j]) for j in range(k)})
         return res
 
-    def score_keys_batch(self, keys: np.ndarray, key_off: np.ndarray, pod_identifiers=None, touch_lru: bool = False):
+    def score_keys_batch(self, keys: np.ndarray, key_off: np.ndarray, pod_identifiers=None, touch_lru: bool = True):
         """Lookup + LongestPrefixScorer.Score for many prompts (kvblock_scorer.go:106-154)."""
         n = len(key_off) - 1
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -369,14 +387,14 @@ class Index:
         out_n = np.zeros(max(n, 1), dtype=np.int32)
         out_pods = np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.uint16)
         out_scores = np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.float64)
-        check(_lib.load().kvb_index_score_batch(
+        self._check(self._lib.kvb_index_score_batch(
             self._h, keys.ctypes.data if keys.size else None, key_off.ctypes.data, n,
-            None if filt is None else filt.ctypes.data, nf, _lib.SCORE_TOUCH_LRU if touch_lru else 0,
+            None if filt is None else filt.ctypes.data, nf, 0 if touch_lru else _lib.SCORE_NO_TOUCH,
             out_n.ctypes.data, out_pods.ctypes.data, out_scores.ctypes.data))
         return self._unpack_scores(n, out_n, out_pods, out_scores)
 
     def score_tokens_flat(self, block_size: int, tokens: np.ndarray, prompt_off: np.ndarray, parents: np.ndarray,
-                          pod_identifiers=None, touch_lru: bool = False, out=None):
+                          pod_identifiers=None, touch_lru: bool = True, out=None):
         """Same fused call on pre-flattened arrays (uint32 tokens, int64 offsets, uint64 parents); returns the raw
         (n, pods, scores) arrays — the zero-copy form a host-language shim would use."""
         n = len(prompt_off) - 1
@@ -384,14 +402,14 @@ class Index:
         if out is None:
             out = (np.zeros(max(n, 1), dtype=np.int32), np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.uint16),
                    np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.float64))
-        check(_lib.load().kvb_index_score_tokens_batch(
+        self._check(self._lib.kvb_index_score_tokens_batch(
             self._h, tokens.ctypes.data, prompt_off.ctypes.data, parents.ctypes.data, n, int(block_size), None, None,
-            None if filt is None else filt.ctypes.data, nf, _lib.SCORE_TOUCH_LRU if touch_lru else 0,
+            None if filt is None else filt.ctypes.data, nf, 0 if touch_lru else _lib.SCORE_NO_TOUCH,
             out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
         return out
 
     def score_tokens_batch(self, tp: ChunkedTokenDatabase, prompts, model_names, pod_identifiers=None,
-                           extra_features=None, touch_lru: bool = False, raw: bool = False):
+                           extra_features=None, touch_lru: bool = True, raw: bool = False):
         """Fused tokens -> keys -> lookup -> score on the device for a batch of prompts."""
         tokens, off, parents, nblk, extra, extra_off = tp.prepare_batch(prompts, model_names, None, extra_features)
         n = len(prompts)
@@ -399,10 +417,10 @@ class Index:
         out_n = np.zeros(max(n, 1), dtype=np.int32)
         out_pods = np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.uint16)
         out_scores = np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.float64)
-        check(_lib.load().kvb_index_score_tokens_batch(
+        self._check(self._lib.kvb_index_score_tokens_batch(
             self._h, tokens.ctypes.data, off.ctypes.data, parents.ctypes.data, n, tp.block_size(),
             None if extra is None else extra.ctypes.data, None if extra_off is None else extra_off.ctypes.data,
-            None if filt is None else filt.ctypes.data, nf, _lib.SCORE_TOUCH_LRU if touch_lru else 0,
+            None if filt is None else filt.ctypes.data, nf, 0 if touch_lru else _lib.SCORE_NO_TOUCH,
             out_n.ctypes.data, out_pods.ctypes.data, out_scores.ctypes.data))
         if raw:
             return out_n, out_pods, out_scores, nblk

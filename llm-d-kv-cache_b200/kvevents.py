@@ -155,8 +155,9 @@ def realign_extra_features(engine_features, canonical_block_count: int):
             continue
         slot = i * canonical_block_count // n
         if merged[slot] is None:
-            merged[slot] = K.BlockExtraFeatures([])
-        merged[slot].mm_hashes = merged[slot].mm_hashes + list(ef.mm_hashes)
+            merged[slot] = K.BlockExtraFeatures(None)  # Go: &BlockExtraFeatures{} — MMHashes is a nil slice ...
+        if ef.mm_hashes:  # ... and append(nil, <nothing>...) stays nil, which CBOR-encodes as null (f6), not as [] (80)
+            merged[slot].mm_hashes = (merged[slot].mm_hashes or []) + list(ef.mm_hashes)
     return merged
 
 

@@ -21,14 +21,19 @@ class PrepareStoreOutput:
 
 
 class SharedStorageOffloadingManager:
-    def __init__(self, file_mapper: FileMapper, exists: Optional[Callable[[str], bool]] = None):
-        """``exists`` defaults to os.path.exists (file tier, manager.py:49-53); pass ``engine.exists`` for the
-        host-arena tier."""
+    def __init__(self, file_mapper: FileMapper, exists: Optional[Callable[[str], bool]] = None, engine=None):
+        """``engine``: a StorageOffloadEngine — ``lookup`` then asks the library ONCE per call
+        (``kvb_engine_lookup_prefix``: arena hash-map probes under one lock, or one ``statx`` per file in C) instead of
+        one existence probe per block from Python.  Without an engine the reference's loop runs with ``exists``
+        (default os.path.exists, manager.py:49-53)."""
         self.file_mapper = file_mapper
+        self._engine = engine
         self._exists = exists or os.path.exists
 
     def lookup(self, block_hashes: Iterable) -> int:
         """How many consecutive blocks from the start are already offloaded (manager.py:43-53)."""
+        if self._engine is not None:
+            return self._engine.lookup_prefix([self.file_mapper.get_file_name(h) for h in block_hashes])
         hits = 0
         for h in block_hashes:
             if not self._exists(self.file_mapper.get_file_name(h)):

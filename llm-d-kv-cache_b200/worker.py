@@ -16,6 +16,10 @@ DEFAULT_MAX_STAGING_MEMORY_GB = 150  # worker.py:58-61
 DEFAULT_THREADS_PER_GPU = 64
 DEFAULT_READ_PREFERRING_WORKERS_RATIO = 0.75
 DEFAULT_MAX_WRITE_QUEUED_SECONDS = 10.0
+# This engine packs a chunk of whole files in HBM before the host leg (the reference has no HBM staging at all), and vLLM
+# has already sized its KV cache from gpu_memory_utilization when the handlers are built: keep the workers' packed
+# chunks inside a fixed HBM budget instead of io_threads x 64 MiB.
+DEFAULT_MAX_HBM_STAGING_MB = 1024
 
 
 class BaseStorageOffloadingHandler:
@@ -103,10 +107,18 @@ class StorageOffloadingHandlers:
         tensors = [getattr(t, "tensor", t) for t in raw]
         assert tensors
         per_block_bytes = sum(t.stride(0) * t.element_size() for t in tensors)  # worker.py:336
-        # staging budget clamp (worker.py:303-319): one staging buffer per thread
-        buffer_mb = math.ceil(per_block_bytes * gpu_blocks_per_file / (1 << 20))
-        if buffer_mb * threads_per_gpu > max_staging_memory_gb * 1024:
-            threads_per_gpu = max(1, min(threads_per_gpu, int(max_staging_memory_gb * 1024 / buffer_mb)))
+        # staging budget clamp (worker.py:303-319).  What a worker of THIS engine allocates is one chunk (whole files,
+        # >= one file) of HBM plus, in the file tier, the same amount of pinned host memory — not the reference's one
+        # file-sized host buffer — so the clamp is on the chunk, for both memories.
+        file_bytes = per_block_bytes * gpu_blocks_per_file
+        chunk_bytes = int(extra_config.get("chunk_bytes", 0)) or file_bytes
+        chunk_bytes = max(chunk_bytes, file_bytes)
+        chunk_mb = math.ceil(chunk_bytes / (1 << 20))
+        hbm_budget_mb = int(extra_config.get("max_hbm_staging_mb", DEFAULT_MAX_HBM_STAGING_MB))
+        budget_mb = min(max_staging_memory_gb * 1024, hbm_budget_mb)
+        if chunk_mb * threads_per_gpu > budget_mb:
+            threads_per_gpu = max(1, min(threads_per_gpu, int(budget_mb / chunk_mb)))
+        extra_config = dict(extra_config, chunk_bytes=chunk_bytes)
         read_preferring_workers = max(1, int(threads_per_gpu * read_preferring_ratio))  # worker.py:322
         self.engine = self._create_engine(
             io_threads=threads_per_gpu, gpu_blocks_per_file=gpu_blocks_per_file, tensors=tensors,

@@ -141,8 +141,9 @@ def realign_extra_features(engine_features, canonical_count: int):
             if ef is None:
                 continue
             if out[ci] is None:
-                out[ci] = ko.BlockExtraFeatures([])
-            out[ci].mm_hashes = list(out[ci].mm_hashes) + list(ef.mm_hashes)
+                out[ci] = ko.BlockExtraFeatures(None)  # &BlockExtraFeatures{}: MMHashes is a nil slice (pool.go:240-242)
+            if ef.mm_hashes:  # append(nil, <no elements>...) stays nil -> CBOR null, not an empty array
+                out[ci].mm_hashes = list(out[ci].mm_hashes or []) + list(ef.mm_hashes)
     return out
 
 
