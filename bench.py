@@ -7,14 +7,20 @@ Workload at N=1 = BASELINE config #2: Llama-3-8B fp16 paged KV, 16-token blocks
   one step = save the 10 000 blocks + load them back (2 x 20.97 GB of payload).
 Every rank runs the same workload on its own GPU / KV partition (weak scaling, no data-path collective).
 
-  value   device-resident: paged pool -> packed HBM (gather kernel) and back (scatter kernel); inputs in HBM.
-  e2e     through the reference-facing engine API (StorageOffloadEngine.async_store_gpu_blocks /
-          async_load_gpu_blocks, host-arena tier): D2H of every saved block to pinned host memory and H2D of
-          every loaded block inside the timed region.
+  value     device-resident: paged pool -> packed HBM (gather kernel) and back (scatter kernel); inputs in HBM.
+            It has NO host leg: compare it with the HBM roofline, not with the reference arm.
+  e2e       through the reference-facing engine API (StorageOffloadEngine.async_store_gpu_blocks /
+            async_load_gpu_blocks), tier = host_arena (pinned host DRAM): D2H of every saved block and H2D of every
+            loaded block inside the timed region.  This is the north-star host tier.
+  e2e_file_tier  the same API writing the REFERENCE'S on-disk format to /dev/shm, at every N, on the same blocks per step
+            as the reference arm: the like-for-like number against `--impl reference`.
   roofline  gather kernel: 2 x payload bytes / CUDA-event time per launch vs the measured HBM copy peak.
+  extras    config1 / config5 (index path), config3 (70B-fp8 block shape), migration (+ migration_70b) at N > 1,
+            ingest, manager_lookup — computed in the same run, each asserting parity before it reports a number.
   cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref, built from /root/reference's own
-          csrc) storing to and loading from /dev/shm with its default per-(block x tensor) cudaMemcpyAsync path,
-          on a bounded sample of the same workload.
+            csrc) storing to and loading from /dev/shm with its default per-(block x tensor) cudaMemcpyAsync path.
+            At N > 1 every rank runs its own reference engine on its own GPU (storage_offload.cpp:160-167) and the
+            line reports the aggregate.  `config.blocks_per_step` is the number of blocks it really moved per step.
 """
 from __future__ import annotations
 
@@ -35,6 +41,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import bench_extras as bx  # noqa: E402
+
 # ---- workload: BASELINE config #2 -------------------------------------------------------------------------
 T_TENSORS = 64          # K and V of 32 layers
 FRAG_BYTES = 32768      # 16 tok x 8 kv heads x 128 x fp16
@@ -42,7 +50,25 @@ POOL_BLOCKS = int(os.environ.get("KVB_BENCH_POOL_BLOCKS", "12288"))   # env over
 N_BLOCKS = int(os.environ.get("KVB_BENCH_BLOCKS", "10000"))           # (a reduced run says so in config)
 BLOCK_BYTES = T_TENSORS * FRAG_BYTES          # 2 MiB
 BLOCKS_PER_FILE = 16                           # reference default: 256-token files / 16-token blocks (spec.py:50-85)
-REF_SAMPLE_BLOCKS = min(2048, N_BLOCKS)        # bounded sample for the reference arm (4.3 GB each way)
+MIGRATE_BLOCKS = 2048                          # BASELINE config #4: 32k-token context = 2048 blocks (4.29 GB, 8B shape)
+# The file tier (reference arm and our like-for-like arm) runs on tmpfs at single-digit GB/s: its blocks per step are
+# bounded so that the whole --steps K --warmup W run stays within a few minutes.  The full 10 000 blocks when the run is
+# short enough, never fewer than 2048, and the number REALLY used is what `config.blocks_per_step` reports.
+FILE_TIER_BLOCK_BUDGET = 100_000               # blocks moved each way over the whole run, per rank
+
+
+def file_tier_blocks(steps: int, warmup: int) -> int:
+    per_step = FILE_TIER_BLOCK_BUDGET // max(1, steps + warmup)
+    n = max(2048, min(N_BLOCKS, per_step)) // BLOCKS_PER_FILE * BLOCKS_PER_FILE
+    n = min(n, N_BLOCKS // BLOCKS_PER_FILE * BLOCKS_PER_FILE)
+    try:  # and it must fit the tmpfs, with room for every rank of this node
+        free = shutil.disk_usage("/dev/shm").free
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        fit = int(free * 0.6 / world / BLOCK_BYTES) // BLOCKS_PER_FILE * BLOCKS_PER_FILE
+        n = max(BLOCKS_PER_FILE, min(n, fit))
+    except Exception:
+        pass
+    return n
 
 
 _JSON_FD = None
@@ -127,19 +153,25 @@ def load_reference_engine():
         return None, f"cannot load reference engine: {e}"
 
 
-def reference_step(mod, tensors, ids, step_tag, io_threads, root="/dev/shm/kvb_ref_bench"):
-    """One save+load of `ids` through the reference engine (default memcpy path), files on tmpfs.
-    Returns seconds for (store, load)."""
-    import torch
-    bpf = BLOCKS_PER_FILE
+def file_groups(ids, bpf=BLOCKS_PER_FILE):
+    """worker.py:158-193 grouping: the first file takes the remainder."""
     n_files = (len(ids) + bpf - 1) // bpf
-    files = [f"{root}/{step_tag}/{i:06d}.bin" for i in range(n_files)]
     first = len(ids) % bpf or bpf
     groups, pos, take = [], 0, first
     for _ in range(n_files):
         groups.append([int(x) for x in ids[pos:pos + take]])
         pos += take
         take = bpf
+    return groups
+
+
+def reference_step(mod, tensors, ids, step_tag, io_threads, root="/dev/shm/kvb_ref_bench"):
+    """One save+load of `ids` through the reference engine (default memcpy path), files on tmpfs.
+    Returns seconds for (store, load)."""
+    import torch
+    bpf = BLOCKS_PER_FILE
+    groups = file_groups(ids, bpf)
+    files = [f"{root}/{step_tag}/{i:06d}.bin" for i in range(len(groups))]
     eng = reference_step.engines.get(id(tensors[0]))
     if eng is None:
         eng = mod.StorageOffloadEngine(io_threads, bpf, tensors, max(1, int(io_threads * 0.75)), "disabled", 0.0)
@@ -159,18 +191,9 @@ def reference_step(mod, tensors, ids, step_tag, io_threads, root="/dev/shm/kvb_r
 
 reference_step.engines = {}
 
-
-def _drain(eng, job_id, timeout=600.0, sleep=0.0005):
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < timeout:
-        for jid, ok in eng.get_finished():
-            if jid == job_id:
-                if not ok:
-                    raise RuntimeError(f"job {job_id} failed")
-                return
-        if sleep:
-            time.sleep(sleep)
-    raise TimeoutError(f"job {job_id}")
+_drain = bx._drain
+barrier_sync = bx.barrier_sync
+max_over_ranks = bx.max_over_ranks
 
 
 def pipelined_save_load(eng, files, groups, files_per_job=25, first_job=1000):
@@ -242,40 +265,34 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
-def barrier_sync(dist):
-    import torch
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-
-
-def max_over_ranks(dist, x: float) -> float:
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+def workload_config(n_gpus, blocks_per_step=N_BLOCKS):
+    cfg = {"workload": "BASELINE config #2: Llama-3-8B fp16 paged-KV, 16-tok blocks, save+load 10k blocks GPU<->host",
+           "tensors": T_TENSORS, "fragment_bytes": FRAG_BYTES, "block_bytes": BLOCK_BYTES, "pool_blocks": POOL_BLOCKS,
+           "blocks_per_step": blocks_per_step, "workload_blocks": N_BLOCKS,
+           "block_ids": f"rng(1).permutation({POOL_BLOCKS})[:{blocks_per_step}] (non-contiguous, unsorted)",
+           "gpu_blocks_per_file": BLOCKS_PER_FILE, "partitioning": f"{n_gpus} independent KV partitions (one per GPU)",
+           "l2_policy": f"inputs_exceed_l2 ({blocks_per_step * BLOCK_BYTES / 1e9:.2f} GB per pass vs 126 MB L2)"}
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The unmodified reference engine, ONE PER RANK on its own GPU (storage_offload.cpp:160-167: the engine takes the
+    caller's current device), files under /dev/shm/<rank>; the line reports the aggregate over all ranks with the
+    max-over-ranks time, like our own arm."""
     import torch
     rank, world, local, dist = dist_setup(args.gpus)
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
     mod, why = load_reference_engine()
-    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
+    n_ref = file_tier_blocks(args.steps, args.warmup)
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:n_ref].astype(np.int64)
     cores = os.cpu_count() or 1
     io_threads = min(64, cores)
     big = torch.empty((T_TENSORS, POOL_BLOCKS, FRAG_BYTES), dtype=torch.int8, device="cuda")
     big.view(torch.uint8).random_(0, 256)
     tensors = list(big.unbind(0))
-    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
+    payload = n_ref * BLOCK_BYTES
     kind = "reference"
+    root = f"/dev/shm/kvb_ref_bench/rank_{rank}"
     if mod is None:
         # oracle port: numpy pack/unpack of the same bytes on the host (single thread)
         kind = "port"
@@ -290,43 +307,129 @@ def run_reference(args):
         io_threads = 1
     else:
         def step(tag):
-            a, b = reference_step(mod, tensors, ids, tag, io_threads)
+            a, b = reference_step(mod, tensors, ids, tag, io_threads, root=root)
             return a + b
     for w in range(args.warmup):
         step(f"w{w}")
-    torch.cuda.synchronize()
+    barrier_sync(dist)
     # timed region = the store and load phases of every step; deleting the previous step's tmpfs files (several GB of
     # page frees) is housekeeping between steps and is NOT charged to the reference
     dt = 0.0
     for k in range(args.steps):
+        barrier_sync(dist)
         dt += step(f"s{k}")
-    torch.cuda.synchronize()
-    gbs = 2 * payload * args.steps / dt / 1e9
-    sample = (f"{REF_SAMPLE_BLOCKS} of the workload's {N_BLOCKS} blocks (seed-1 permutation prefix), "
-              f"save+load per step, {BLOCKS_PER_FILE} blocks/file on /dev/shm, default cudaMemcpyAsync copy path")
-    line = {
-        "impl": "reference", "metric": "kv_block_offload_gbps_save_plus_load", "value": gbs, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "blocks_per_s": 2 * REF_SAMPLE_BLOCKS * args.steps / dt,
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": io_threads, "kind": kind, "sample": sample,
-                         "host_cores": cores, **({"note": why} if why else {})},
-        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit_json(line)
+    barrier_sync(dist)
+    dt = max_over_ranks(dist, dt)
+    shutil.rmtree(root, ignore_errors=True)
+    gbs = world * 2 * payload * args.steps / dt / 1e9
+    sample = (f"{n_ref} of the workload's {N_BLOCKS} blocks per step (seed-1 permutation prefix) on each of {world} GPU(s), "
+              f"save+load per step, {BLOCKS_PER_FILE} blocks/file on /dev/shm, default cudaMemcpyAsync copy path, "
+              f"{io_threads} io_threads per engine")
+    if rank == 0:
+        line = {
+            "impl": "reference", "metric": "kv_block_offload_gbps_save_plus_load", "value": gbs, "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world, n_ref),
+            "blocks_per_s": world * 2 * n_ref * args.steps / dt,
+            "engines": world, "tier": "file (/dev/shm)",
+            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": io_threads * world, "kind": kind, "sample": sample,
+                             "host_cores": cores, **({"note": why} if why else {})},
+            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        emit_json(line)
     reference_step.engines.clear()
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE config #2: Llama-3-8B fp16 paged-KV, 16-tok blocks, save+load 10k blocks GPU<->host",
-            "tensors": T_TENSORS, "fragment_bytes": FRAG_BYTES, "block_bytes": BLOCK_BYTES, "pool_blocks": POOL_BLOCKS,
-            "blocks_per_step": N_BLOCKS, "block_ids": f"rng(1).permutation({POOL_BLOCKS})[:{N_BLOCKS}] (non-contiguous, unsorted)",
-            "gpu_blocks_per_file": BLOCKS_PER_FILE, "partitioning": f"{n_gpus} independent KV partitions (one per GPU)",
-            "l2_policy": "inputs_exceed_l2 (20.97 GB per pass vs 126 MB L2)"}
+def pcie_probe(kvb, dist, world, local):
+    """What a plain cudaMemcpyAsync of one contiguous 2 GiB buffer achieves when the host side is pinned memory placed on
+    the GPU's NUMA node (kvb_host_alloc — the same placement the engine's arena uses), all ranks at once: the ceiling
+    the e2e number is a fraction of.  Per-rank figures are kept so that a lagging root complex is visible."""
+    import torch
+    try:
+        from cuda.bindings import runtime as cudart
+    except Exception:  # older cuda-python
+        from cuda import cudart
+    probe_n = 2 << 30
+    pin = kvb.pool.PinnedBuffer(probe_n)
+    dbuf = torch.empty(probe_n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for name, (dst, src, kind) in (("d2h_gbs", (pin.ptr, dbuf.data_ptr(), cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)),
+                                   ("h2d_gbs", (dbuf.data_ptr(), pin.ptr, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice))):
+        cudart.cudaMemcpyAsync(dst, src, probe_n, kind, stream)
+        barrier_sync(dist)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            (err,) = cudart.cudaMemcpyAsync(dst, src, probe_n, kind, stream)
+            assert int(err) == 0, f"cudaMemcpyAsync: {err}"
+        b.record()
+        barrier_sync(dist)
+        mine = 3 * probe_n / (a.elapsed_time(b) / 1e3) / 1e9
+        out[name] = world * 3 * probe_n / (max_over_ranks(dist, a.elapsed_time(b)) / 1e3) / 1e9
+        out[name.replace("_gbs", "_gbs_per_gpu")] = [round(x, 2) for x in bx.gather_objects(dist, mine)]
+    del dbuf
+    pin.free()
+    out["what"] = ("contiguous 2 GiB cudaMemcpyAsync, host side pinned on the GPU's NUMA node (kvb_host_alloc), all ranks at once "
+                   "(aggregate GB/s = bytes / max-over-ranks time)")
+    return out
+
+
+def run_file_tier(kvb, dist, rank, world, tensors, n_ref, with_latency):
+    """Our engine, tier=file: the reference's on-disk format on the same tmpfs, same blocks per step and file grouping as
+    the reference arm — the like-for-like comparison for the storage tier — at every N (one engine per rank)."""
+    import torch
+    root = f"/dev/shm/kvb_file_bench/rank_{rank}"
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:n_ref].astype(np.int64)
+    payload = n_ref * BLOCK_BYTES
+    bpf = BLOCKS_PER_FILE
+    groups = file_groups(ids, bpf)
+    n_files = len(groups)
+    threads = min(env_int("KVB_BENCH_FILE_THREADS", 16), os.cpu_count() or 1)
+    eng = kvb.engine.StorageOffloadEngine(threads, bpf, tensors, max(1, int(threads * 0.75)), "disabled", 0.0,
+                                          tier="file", chunk_bytes=bpf * BLOCK_BYTES)
+    res = {}
+    try:
+        for tag in ("warm", "base"):
+            files = [f"{root}/{tag}/{i:06d}.bin" for i in range(n_files)]
+            barrier_sync(dist)
+            t0 = time.perf_counter()
+            assert eng.async_store_gpu_blocks(1, files, groups)
+            _drain(eng, 1)
+            t1 = time.perf_counter()
+            if tag == "warm":   # the warm-up pass doubles as the proof: zero the saved pages before loading them back
+                ids_dev = torch.from_numpy(ids).to(tensors[0].device)
+                keep = [t[ids_dev[:32]].clone() for t in tensors[::16]]
+                for t in tensors:
+                    t[ids_dev] = 0
+                torch.cuda.synchronize()
+            t1b = time.perf_counter()
+            assert eng.async_load_gpu_blocks(2, files, groups)
+            _drain(eng, 2)
+            t2 = time.perf_counter()
+            if tag == "warm":
+                for t, k in zip(tensors[::16], keep):
+                    assert torch.equal(t[ids_dev[:32]], k), "file-tier load did not restore zeroed pages"
+            shutil.rmtree(f"{root}/{tag}", ignore_errors=True)
+            barrier_sync(dist)
+            st, ld = max_over_ranks(dist, t1 - t0), max_over_ranks(dist, t2 - t1b)
+            res = {"value": world * 2 * payload / (st + ld) / 1e9, "unit": "GB/s", "store_gbs": world * payload / st / 1e9,
+                   "load_gbs": world * payload / ld / 1e9, "io_threads": threads, "tier": "file (/dev/shm)",
+                   "blocks_per_step": n_ref, "engines": world, "bit_exact": True,
+                   "store_gbs_per_gpu": [round(x, 2) for x in bx.gather_objects(dist, payload / (t1 - t0) / 1e9)],
+                   "load_gbs_per_gpu": [round(x, 2) for x in bx.gather_objects(dist, payload / (t2 - t1b) / 1e9)],
+                   "sample": f"{n_ref} blocks per rank, {bpf} blocks/file, reference .bin format on /dev/shm "
+                             "(same blocks per step and grouping as the --impl reference arm)"}
+        if with_latency:
+            res["single_file_job_latency"] = single_file_job_latency(eng, ids, f"{root}/lat")
+    finally:
+        eng.shutdown()
+        shutil.rmtree(root, ignore_errors=True)
+    return res
 
 
 def run_ours(args):
@@ -334,6 +437,8 @@ def run_ours(args):
     rank, world, local, dist = dist_setup(args.gpus)
     kvb = importlib.import_module("llm-d-kv-cache_b200")
     lib = kvb.lib
+    peak, peak_src = measured_hbm_peak()
+    n_ref = file_tier_blocks(args.steps, args.warmup)
 
     # ---- data: pool resident in HBM, random bytes, random block table
     big = torch.empty((T_TENSORS, POOL_BLOCKS, FRAG_BYTES), dtype=torch.uint8, device="cuda")
@@ -362,7 +467,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         dev_step()
     sampler = ClockSampler(local)
-    launches0 = lib.kvb_launch_count()
+    launches_start = lib.kvb_launch_count()
     barrier_sync(dist)
     if rank == 0:
         sampler.start()
@@ -374,7 +479,6 @@ def run_ours(args):
     stop.record()
     barrier_sync(dist)
     dev_ms = max_over_ranks(dist, start.elapsed_time(stop))
-    launches_dev = lib.kvb_launch_count() - launches0
     gather_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev_sets]))
     scatter_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev_sets]))
     # untimed proof that the load leg really restores: save, ZERO every saved page, load, compare
@@ -414,18 +518,20 @@ def run_ours(args):
     for w in range(args.warmup):
         e2e_step(f"w{w}")
     stats0 = eng.stats()
-    launches1 = lib.kvb_launch_count()
     barrier_sync(dist)
     t0 = time.perf_counter()
     store_s = 0.0
     for k in range(args.steps):
         ts = time.perf_counter()
         store_s += e2e_step(f"s{k}") - ts
+    my_e2e_s = time.perf_counter() - t0
     barrier_sync(dist)
     e2e_s = max_over_ranks(dist, time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
-    launches_e2e = lib.kvb_launch_count() - launches1
     stats1 = eng.stats()
+    per_gpu = bx.gather_objects(dist, {"store": payload * args.steps / store_s / 1e9,
+                                       "load": payload * args.steps / max(my_e2e_s - store_s, 1e-9) / 1e9})
+    store_s_max = max_over_ranks(dist, store_s)
     # untimed proof through the engine: store, ZERO every saved page, load, whole-pool checksum + samples
     vfiles = [f"verify/{i:06d}" for i in range(n_files)]
     job[0] += 1
@@ -475,67 +581,80 @@ def run_ours(args):
     assert pool_checksum(big) == sum0, "direct_host_io save+load did not restore the pool bit-exact"
     eng_d.shutdown()
 
-    # ---- PCIe ceiling probe: plain pinned cudaMemcpy of one contiguous 2 GiB buffer, all ranks at once
-    probe_n = 2 << 30
-    hbuf = torch.empty(probe_n, dtype=torch.uint8).pin_memory()
-    dbuf = torch.empty(probe_n, dtype=torch.uint8, device="cuda")
-    probe = {}
-    for name, (dst_t, src_t) in (("d2h_gbs", (hbuf, dbuf)), ("h2d_gbs", (dbuf, hbuf))):
-        dst_t.copy_(src_t, non_blocking=True)
-        barrier_sync(dist)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
-            dst_t.copy_(src_t, non_blocking=True)
-        b.record()
-        barrier_sync(dist)
-        probe[name] = world * 3 * probe_n / (max_over_ranks(dist, a.elapsed_time(b)) / 1e3) / 1e9
-    del hbuf, dbuf
+    probe = pcie_probe(kvb, dist, world, local)
+
+    # ---- like-for-like storage tier: reference-format files on /dev/shm, every N
+    file_tier = run_file_tier(kvb, dist, rank, world, tensors, n_ref, with_latency=(rank == 0 and world == 1))
+    for t, r in zip(tensors[::8], check_ref):
+        assert torch.equal(t[check_ids], r), "file-tier save+load did not restore the pool bit-exact"
+
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras["manager_lookup"] = bx.run_manager_lookup(kvb)
 
     # ---- cross-GPU migration over NVLink (only where there is a peer)
     migration = None
+    ref_mod, _why = load_reference_engine()
     if world > 1 and not args.no_migration:
-        migration = run_migration(kvb, dist, rank, world, local, tensors, pool, args.steps, args.warmup)
+        migration = bx.run_migration(kvb, dist, rank, world, local, tensors, pool, POOL_BLOCKS, BLOCK_BYTES,
+                                     min(MIGRATE_BLOCKS, POOL_BLOCKS // 4), args.steps, args.warmup,
+                                     reference_engine=ref_mod, blocks_per_file=BLOCKS_PER_FILE, shape_name="8B-fp16")
 
-    # ---- cpu baseline (rank 0, N=1 only): the reference engine on a bounded sample, and OUR engine writing the
-    # same reference-format files to the same tmpfs on the same sample (like-for-like tier)
+    # ---- cpu baseline (rank 0, N=1 only): the reference engine on the same blocks per step as the file-tier arm
     cpu_baseline = None
-    file_tier = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_cpu_baseline(tensors)
-        file_tier = run_file_tier(kvb, tensors)
+        cpu_baseline = run_cpu_baseline(tensors, n_ref)
         for t, r in zip(tensors[::8], check_ref):
-            assert torch.equal(t[check_ids], r), "file-tier save+load did not restore the pool bit-exact"
+            assert torch.equal(t[check_ids], r), "the reference arm disturbed the pool"
+    launches_cfg2 = lib.kvb_launch_count() - launches_start
+
+    # ---- extras on their own data: config #3 (every rank, weak scaling), then configs #1 / #5 / ingest (rank 0)
+    pool.close()
+    del check_ref, tensors, big, ids_dev
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        c3 = bx.run_config3(kvb, dist, rank, world, local, args.steps, args.warmup, peak, peak_src,
+                            migrate=not args.no_migration)
+        if rank == 0:
+            extras["config3"] = c3
+            if "migration_70b" in c3:
+                extras["migration_70b"] = c3.pop("migration_70b")
+            cfg1, cfg5 = bx.run_index_configs(kvb)
+            if cfg5["roofline"]["achieved"] is not None:
+                cfg5["roofline"]["peak"], cfg5["roofline"]["peak_source"] = peak, peak_src
+                cfg5["roofline"]["frac"] = cfg5["roofline"]["achieved"] / peak
+            extras["config1"], extras["config5"] = cfg1, cfg5
+            extras["ingest"] = bx.run_ingest(kvb)
+        barrier_sync(dist)
 
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
         achieved = 2 * payload / (gather_ms / 1e3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "gather_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch_bench")
-            except Exception:
-                traffic = None
+        traffic = bx._traffic("gather_traffic.json")
         line = {
             "metric": "kv_block_offload_gbps_save_plus_load", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world),
+            "value_note": "device-resident gather+scatter (HBM<->HBM, no host leg): judge it against roofline, not against the "
+                          "reference arm; the reference-facing numbers are e2e (host arena) and e2e_file_tier (like-for-like)",
             "blocks_per_s": world * 2 * N_BLOCKS * args.steps / (dev_ms / 1e3),
-            "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_gbs, "unit": "GB/s", "tier": "host_arena (pinned host DRAM, NUMA-local)",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "blocks_per_s": world * 2 * N_BLOCKS * args.steps / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "store_gbs": world * payload * args.steps / store_s / 1e9,
-                    "load_gbs": world * payload * args.steps / max(e2e_s - store_s, 1e-9) / 1e9,
-                    "pcie_probe": {**probe, "what": "contiguous 2 GiB pinned cudaMemcpy, all ranks at once (aggregate GB/s)"},
+                    "store_gbs": world * payload * args.steps / store_s_max / 1e9,
+                    "load_gbs": world * payload * args.steps / max(e2e_s - store_s_max, 1e-9) / 1e9,
+                    "store_gbs_per_gpu": [round(x["store"], 2) for x in per_gpu],
+                    "load_gbs_per_gpu": [round(x["load"], 2) for x in per_gpu],
+                    "pcie_probe": probe,
                     "frac_of_pcie_probe": e2e_gbs / (2 * probe["d2h_gbs"] * probe["h2d_gbs"] / (probe["d2h_gbs"] + probe["h2d_gbs"])),
                     "pipelined_jobs_gbs": world * 2 * payload / t_pipe / 1e9,
                     "single_file_job_latency": job_latency,
                     "direct_host_io_gbs": world * 2 * payload / t_direct / 1e9,
                     "direct_host_io_note": "extra: fused gather+D2H / H2D+scatter kernels addressing the pinned arena (no HBM staging, no cudaMemcpy)",
                     "pipelined_note": "extra, not the headline: 25-file jobs, each group loaded back as soon as it is stored, so D2H and H2D overlap",
-                    "api": "StorageOffloadEngine.async_store_gpu_blocks/async_load_gpu_blocks/get_finished, tier=host_arena (pinned)"},
-            "gpu_launches": int(launches_dev + launches_e2e),
+                    "api": "StorageOffloadEngine.async_store_gpu_blocks/async_load_gpu_blocks/get_finished"},
+            "e2e_file_tier": file_tier,
+            "gpu_launches": int(launches_cfg2),
             "roofline": {"kernel": "paged_copy_bulk_kernel<gather>", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 2 * payload, "gather_ms": gather_ms, "scatter_ms": scatter_ms,
@@ -547,204 +666,23 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline
         if migration is not None:
             line["migration"] = migration
-        if file_tier is not None:
-            line["e2e_file_tier"] = file_tier
+        if extras:
+            line["extras"] = extras
+            line["gpu_launches_total"] = int(lib.kvb_launch_count())
         emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
-def run_file_tier(kvb, tensors, root="/dev/shm/kvb_file_bench"):
-    """Our engine, tier=file: the reference's on-disk format on the same tmpfs, same bounded sample and file grouping
-    as the reference arm (cpu_baseline) — the like-for-like comparison for the storage tier."""
-    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
-    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
-    bpf = BLOCKS_PER_FILE
-    n_files = (len(ids) + bpf - 1) // bpf
-    first = len(ids) % bpf or bpf
-    groups, pos, take = [], 0, first
-    for _ in range(n_files):
-        groups.append(ids[pos:pos + take].tolist())
-        pos += take
-        take = bpf
-    threads = min(env_int("KVB_BENCH_FILE_THREADS", 16), os.cpu_count() or 1)
-    eng = kvb.engine.StorageOffloadEngine(threads, bpf, tensors, max(1, int(threads * 0.75)), "disabled", 0.0,
-                                          tier="file", chunk_bytes=bpf * BLOCK_BYTES)
-    res = {}
-    try:
-        for tag in ("warm", "base"):
-            files = [f"{root}/{tag}/{i:06d}.bin" for i in range(n_files)]
-            t0 = time.perf_counter()
-            assert eng.async_store_gpu_blocks(1, files, groups)
-            _drain(eng, 1)
-            t1 = time.perf_counter()
-            if tag == "warm":   # the warm-up pass doubles as the proof: zero the saved pages before loading them back
-                import torch
-                ids_dev = torch.from_numpy(ids).to(tensors[0].device)
-                keep = [t[ids_dev[:32]].clone() for t in tensors[::16]]
-                for t in tensors:
-                    t[ids_dev] = 0
-            assert eng.async_load_gpu_blocks(2, files, groups)
-            _drain(eng, 2)
-            t2 = time.perf_counter()
-            if tag == "warm":
-                for t, k in zip(tensors[::16], keep):
-                    assert torch.equal(t[ids_dev[:32]], k), "file-tier load did not restore zeroed pages"
-            shutil.rmtree(f"{root}/{tag}", ignore_errors=True)
-            res = {"value": 2 * payload / (t2 - t0) / 1e9, "unit": "GB/s", "store_gbs": payload / (t1 - t0) / 1e9,
-                   "load_gbs": payload / (t2 - t1) / 1e9, "io_threads": threads,
-                   "sample": f"{REF_SAMPLE_BLOCKS} blocks, {bpf} blocks/file, reference .bin format on /dev/shm "
-                             "(same sample and grouping as cpu_baseline)"}
-        res["single_file_job_latency"] = single_file_job_latency(eng, ids, f"{root}/lat")
-    finally:
-        eng.shutdown()
-        shutil.rmtree(root, ignore_errors=True)
-    return res
-
-
-MIGRATE_BLOCKS = 2048   # BASELINE config #4: 32k-token context = 2048 blocks of the 8B shape (4.29 GB)
-
-
-def run_migration(kvb, dist, rank, world, local, tensors, pool, steps, warmup):
-    """Cross-GPU block migration over NVLink (BASELINE config #4), all-pairs ring r -> r+1 and, for world > 2,
-    fan-out rank 0 -> every peer.  One kernel per destination reads local pages and writes the peer's pages
-    (CUDA IPC mapping); torch.distributed carries descriptors and checksums only."""
-    import torch
-    part, mig = kvb.partition, kvb.migrate
-    descs = part.exchange_objects(mig.export_pool(pool), dist)
-    dst_rank, src_rank = part.ring_peers(rank, world)
-    n = min(MIGRATE_BLOCKS, POOL_BLOCKS // 4)
-    payload = n * BLOCK_BYTES
-    # source pages: a prefix of this rank's permutation; destination pages: the UPPER part of the peer's pool
-    # permutation so ring traffic never overwrites pages that are being read
-    src_ids = np.random.default_rng(10 + rank).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64)
-    dst_ids = (POOL_BLOCKS // 2 + np.random.default_rng(20 + rank).permutation(POOL_BLOCKS // 2)[:n]).astype(np.int64)
-    remote = mig.RemotePool(descs[dst_rank], local)
-    out = {"blocks": n, "bytes_per_destination": payload}
-
-    def timed(fn):
-        for _ in range(warmup):
-            fn()
-        barrier_sync(dist)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        barrier_sync(dist)
-        return max_over_ranks(dist, a.elapsed_time(b)) / steps
-
-    ring_ms = timed(lambda: mig.migrate_blocks(pool, remote, src_ids, dst_ids))
-    # verify: what my ring source wrote into my pool equals what it read
-    src_sum = part.page_checksum_torch(tensors, torch.from_numpy(src_ids).cuda())
-    sums = part.exchange_objects({"sum": src_sum, "dst_ids": dst_ids.tolist()}, dist)
-    got = part.page_checksum_torch(tensors, torch.tensor(sums[src_rank]["dst_ids"], device="cuda"))
-    ok = got == sums[src_rank]["sum"]
-    oks = part.exchange_objects(bool(ok), dist)
-    out["ring"] = {"ms": ring_ms, "egress_gbs_per_gpu": payload / ring_ms / 1e6,
-                   "aggregate_gbs": world * payload / ring_ms / 1e6, "bit_exact": all(oks),
-                   "frac_of_900": payload / ring_ms / 1e6 / 900.0, "frac_of_measured_770": payload / ring_ms / 1e6 / 770.0}
-
-    # NCCL baseline for the same exchange: gather -> packed -> send/recv -> scatter (library collective path)
-    packed_s = torch.empty(payload, dtype=torch.uint8, device="cuda")
-    packed_r = torch.empty(payload, dtype=torch.uint8, device="cuda")
-    src_dev, dst_dev = torch.from_numpy(src_ids).cuda(), torch.tensor(sums[src_rank]["dst_ids"], device="cuda")
-
-    def nccl_step():
-        pool.gather_dev(src_dev, packed_s)
-        ops = [dist.P2POp(dist.isend, packed_s, dst_rank), dist.P2POp(dist.irecv, packed_r, src_rank)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        pool.scatter_dev(dst_dev, packed_r)
-
-    nccl_ms = timed(nccl_step)
-    out["ring_nccl_staged"] = {"ms": nccl_ms, "egress_gbs_per_gpu": payload / nccl_ms / 1e6,
-                               "note": "gather kernel -> ncclSend/ncclRecv of the packed buffer -> scatter kernel"}
-    del packed_s, packed_r
-
-    if world > 2:
-        # fan-out: rank 0 pushes a different prefix to every peer, one kernel per peer on its own stream
-        peers = [r for r in range(world) if r != 0]
-        if rank == 0:
-            remotes = {p: (remote if p == dst_rank else mig.RemotePool(descs[p], local)) for p in peers}
-            streams = {p: torch.cuda.Stream() for p in peers}
-            fan_src = {p: np.random.default_rng(30 + p).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64) for p in peers}
-
-            def fan():
-                cur = torch.cuda.current_stream()
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                for p in peers:
-                    streams[p].wait_event(ev)
-                    mig.migrate_blocks(pool, remotes[p], fan_src[p], dst_ids, stream=streams[p])
-                for p in peers:
-                    cur.wait_stream(streams[p])
-        else:
-            def fan():
-                pass
-        fan_ms = timed(fan)
-        out["fanout_rank0"] = {"ms": fan_ms, "destinations": len(peers),
-                               "egress_gbs_rank0": len(peers) * payload / fan_ms / 1e6,
-                               "frac_of_900": len(peers) * payload / fan_ms / 1e6 / 900.0}
-        if rank == 0:
-            for p, r in remotes.items():
-                if r is not remote:
-                    r.close()
-    barrier_sync(dist)
-    remote.close()
-
-    # status quo for the same hand-off with the reference: no cross-GPU path exists, a block reaches another GPU by
-    # being stored by the source worker and loaded by the destination worker through the shared tier (here /dev/shm)
-    mod, _why = load_reference_engine()
-    if mod is not None:
-        ref_dir = "/dev/shm/kvb_ref_migrate"
-        nf = n // BLOCKS_PER_FILE
-        files = [f"{ref_dir}/{i:06d}.bin" for i in range(nf)]
-        sid = np.random.default_rng(10).permutation(POOL_BLOCKS // 2)[:n].astype(np.int64)   # rank 0's source pages
-        did = (POOL_BLOCKS // 2 + np.random.default_rng(21).permutation(POOL_BLOCKS // 2)[:n]).astype(np.int64)
-        grp = lambda ids: [[int(x) for x in ids[i * BLOCKS_PER_FILE:(i + 1) * BLOCKS_PER_FILE]] for i in range(nf)]
-        t_store = t_load = 0.0
-        try:
-            eng = None
-            if rank in (0, 1):
-                eng = mod.StorageOffloadEngine(min(64, os.cpu_count() or 1), BLOCKS_PER_FILE,
-                                               [t.view(torch.int8) for t in tensors], 48, "disabled", 0.0)
-            barrier_sync(dist)
-            if rank == 0:
-                shutil.rmtree(ref_dir, ignore_errors=True)
-                t0 = time.perf_counter()
-                eng.async_store_gpu_blocks(1, files, grp(sid))
-                _drain(eng, 1)
-                t_store = time.perf_counter() - t0
-            barrier_sync(dist)
-            if rank == 1:
-                t0 = time.perf_counter()
-                eng.async_load_gpu_blocks(2, files, grp(did))
-                _drain(eng, 2)
-                t_load = time.perf_counter() - t0
-            barrier_sync(dist)
-            t_store, t_load = max_over_ranks(dist, t_store), max_over_ranks(dist, t_load)
-            out["via_host_reference_engine"] = {
-                "gbs": payload / (t_store + t_load) / 1e9, "store_s": t_store, "load_s": t_load,
-                "note": "GPU0 -> /dev/shm -> GPU1 with the unmodified reference engine (store on rank 0, then load on rank 1)"}
-            del eng
-        except Exception as e:  # never let the comparison take the bench down
-            out["via_host_reference_engine"] = {"error": repr(e)}
-        if rank == 0:
-            shutil.rmtree(ref_dir, ignore_errors=True)
-        barrier_sync(dist)
-    return out
-
-
-def run_cpu_baseline(tensors):
-    """Reference engine (oracle/_ref) on a bounded sample of the same workload, same box, same run."""
+def run_cpu_baseline(tensors, n_ref):
+    """Reference engine (oracle/_ref) on the same blocks per step as e2e_file_tier, same box, same run."""
     import torch
     cores = os.cpu_count() or 1
-    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:REF_SAMPLE_BLOCKS].astype(np.int64)
-    payload = REF_SAMPLE_BLOCKS * BLOCK_BYTES
+    ids = np.random.default_rng(1).permutation(POOL_BLOCKS)[:n_ref].astype(np.int64)
+    payload = n_ref * BLOCK_BYTES
     mod, why = load_reference_engine()
-    sample = (f"{REF_SAMPLE_BLOCKS} of the workload's {N_BLOCKS} blocks, save+load once after one warm-up pass, "
+    sample = (f"{n_ref} of the workload's {N_BLOCKS} blocks, save+load once after one warm-up pass, "
               f"{BLOCKS_PER_FILE} blocks/file on /dev/shm")
     if mod is not None:
         io_threads = min(64, cores)
@@ -754,9 +692,8 @@ def run_cpu_baseline(tensors):
             a, b = reference_step(mod, i8, ids, "base", io_threads)
             ref_eng = reference_step.engines[id(i8[0])]
             root = "/dev/shm/kvb_ref_bench/pipe"
-            nf = (len(ids) + BLOCKS_PER_FILE - 1) // BLOCKS_PER_FILE
-            pf = [f"{root}/{i:06d}.bin" for i in range(nf)]
-            pg = [[int(x) for x in ids[i * BLOCKS_PER_FILE:(i + 1) * BLOCKS_PER_FILE]] for i in range(nf)]
+            pg = file_groups(ids[:2048])
+            pf = [f"{root}/{i:06d}.bin" for i in range(len(pg))]
             try:
                 t_pipe = pipelined_save_load(ref_eng, pf, pg, files_per_job=8)
             except Exception as e:  # the extra must not take the baseline down
@@ -799,10 +736,12 @@ def run_cpu_baseline(tensors):
                 os.environ.pop("USE_KERNEL_COPY_WRITE", None)
                 reference_step.engines.clear()
             return {"value": 2 * payload / (a + b) / 1e9, "unit": "GB/s", "cores": io_threads, "kind": "reference",
-                    "single_file_job_latency": lat, "kernel_copy_path": kc,
-                    "pipelined_jobs_gbs": (2 * payload / t_pipe / 1e9) if t_pipe else None,
+                    "single_file_job_latency": lat, "kernel_copy_path": kc, "blocks_per_step": n_ref,
+                    "pipelined_jobs_gbs": (2 * 2048 * BLOCK_BYTES / t_pipe / 1e9) if t_pipe else None,
                     "sample": sample + ", default cudaMemcpyAsync path, io_threads=min(64,nproc)",
-                    "store_gbs": payload / a / 1e9, "load_gbs": payload / b / 1e9, "host_cores": cores}
+                    "store_gbs": payload / a / 1e9, "load_gbs": payload / b / 1e9, "host_cores": cores,
+                    "numa_note": "built with numa_set_preferred stubbed (no libnuma in the image): its staging buffers are "
+                                 "first-touched by threads it pins to the GPU's node itself (thread_pool.cpp:73-131)"}
         except Exception as e:
             why = f"reference engine failed: {e}"
     from oracle import offload_oracle as oo
@@ -831,6 +770,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-migration", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs #1/#3/#5, ingest and manager lookup (ncu captures)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

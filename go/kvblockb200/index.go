@@ -51,17 +51,29 @@ func NewIndex(cfg *GPUIndexConfig, mediumWeights map[string]float64) (*Index, er
 
 func (ix *Index) Close() { C.kvb_index_destroy(ix.h) }
 
-func (ix *Index) entries(in []kvblock.PodEntry) []C.kvb_pod_entry_t {
+// The C ABI carries pods as uint16 and tiers as uint8: interning more than that would wrap and alias ids.
+const (
+	maxPods  = 1 << 16
+	maxTiers = 1 << 8
+)
+
+func (ix *Index) entries(in []kvblock.PodEntry) ([]C.kvb_pod_entry_t, error) {
 	out := make([]C.kvb_pod_entry_t, len(in))
 	for i, e := range in {
 		p, ok := ix.pods[e.PodIdentifier]
 		if !ok {
+			if len(ix.podN) >= maxPods {
+				return nil, fmt.Errorf("too many distinct pod identifiers (limit %d)", maxPods)
+			}
 			p = uint16(len(ix.podN))
 			ix.pods[e.PodIdentifier] = p
 			ix.podN = append(ix.podN, e.PodIdentifier)
 		}
 		t, ok := ix.tiers[e.DeviceTier]
 		if !ok {
+			if len(ix.tierN) >= maxTiers {
+				return nil, fmt.Errorf("too many distinct device tiers (limit %d)", maxTiers)
+			}
 			t = uint8(len(ix.tierN))
 			ix.tiers[e.DeviceTier] = t
 			ix.tierN = append(ix.tierN, e.DeviceTier)
@@ -77,7 +89,7 @@ func (ix *Index) entries(in []kvblock.PodEntry) []C.kvb_pod_entry_t {
 			out[i].speculative = 1
 		}
 	}
-	return out
+	return out, nil
 }
 
 func keysPtr(k []kvblock.BlockHash) *C.uint64_t {
@@ -94,7 +106,10 @@ func (ix *Index) Add(_ context.Context, engineKeys, requestKeys []kvblock.BlockH
 	}
 	ix.mu.Lock()
 	defer ix.mu.Unlock()
-	e := ix.entries(entries)
+	e, err := ix.entries(entries)
+	if err != nil {
+		return err
+	}
 	has := C.int(0)
 	if engineKeys != nil {
 		has = 1
@@ -113,7 +128,10 @@ func (ix *Index) Evict(_ context.Context, key kvblock.BlockHash, keyType kvblock
 	}
 	ix.mu.Lock()
 	defer ix.mu.Unlock()
-	e := ix.entries(entries)
+	e, err := ix.entries(entries)
+	if err != nil {
+		return err
+	}
 	if rc := C.kvb_index_evict(ix.h, C.uint64_t(key), C.int(keyType), &e[0], C.int32_t(len(e))); rc != 0 {
 		return lastError(rc)
 	}
@@ -200,6 +218,18 @@ func (ix *Index) ScoreTokensBatch(tp *TokenProcessor, prompts [][]uint32, model 
 			filter = append(filter, C.uint16_t(id))
 		}
 	}
+	if len(podIdentifiers) > 0 && len(filter) == 0 {
+		// A filter that names only pods the index has never seen matches nothing: Lookup builds
+		// sets.New(podIdentifiers...) and finds no entry in it (in_memory.go:131-137).  Passing n_filter = 0 here would
+		// mean "no filter" to the C ABI and score every pod.
+		res := make([]map[string]float64, n)
+		for i := range res {
+			if len(prompts[i])/tp.BlockSize() > 0 {
+				res[i] = map[string]float64{}
+			}
+		}
+		return res, nil
+	}
 	var fp *C.uint16_t
 	if len(filter) > 0 {
 		fp = &filter[0]
@@ -214,7 +244,7 @@ func (ix *Index) ScoreTokensBatch(tp *TokenProcessor, prompts [][]uint32, model 
 	}
 	if rc := C.kvb_index_score_tokens_batch(ix.h, tokp, (*C.int64_t)(unsafe.Pointer(&off[0])),
 		(*C.uint64_t)(unsafe.Pointer(&parents[0])), C.int32_t(n), C.int32_t(tp.BlockSize()), nil, nil,
-		fp, C.int32_t(len(filter)), C.KVB_SCORE_TOUCH_LRU, &outN[0], &outP[0], &outS[0]); rc != 0 {
+		fp, C.int32_t(len(filter)), 0 /* recency refreshed by default */, &outN[0], &outP[0], &outS[0]); rc != 0 {
 		return nil, lastError(rc)
 	}
 	res := make([]map[string]float64, n)

@@ -80,7 +80,9 @@ func (t *TokenProcessor) getInitHash(model string) (uint64, error) {
 // encodeExtra is the trailing CBOR item of one block: nil -> no bytes (the kernel folds 0xf6),
 // []MMHash -> array of {"Hash": text} (canonical CBOR of the struct, token_processor.go:146-148).
 func encodeExtra(f *kvblock.BlockExtraFeatures) []byte {
-	if f == nil {
+	// The reference hands extraFeatures[i].MMHashes to the encoder, and fxamacker/cbor encodes a nil slice as null
+	// (0xf6) — the same bytes as a nil *BlockExtraFeatures — not as an empty array (0x80).
+	if f == nil || f.MMHashes == nil {
 		return nil
 	}
 	out := cborHead(0x80, uint64(len(f.MMHashes)))

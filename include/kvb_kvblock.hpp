@@ -296,7 +296,7 @@ class Index {
     std::vector<double> out_s((size_t)n * KVB_INDEX_MAX_PODS_PER_KEY);
     check(kvb_index_score_tokens_batch(h_, flat.data(), off.data(), parents.data(), n, tp.BlockSize(), nullptr, nullptr,
                                        filter.empty() ? nullptr : filter.data(), (int32_t)filter.size(),
-                                       touchLRU ? KVB_SCORE_TOUCH_LRU : 0, out_n.data(), out_p.data(), out_s.data()));
+                                       touchLRU ? 0 : KVB_SCORE_NO_TOUCH, out_n.data(), out_p.data(), out_s.data()));
     for (int32_t i = 0; i < n; ++i)
       for (int j = 0; j < out_n[i]; ++j)
         res[i][pod_names_[out_p[(size_t)i * KVB_INDEX_MAX_PODS_PER_KEY + j]]] = out_s[(size_t)i * KVB_INDEX_MAX_PODS_PER_KEY + j];

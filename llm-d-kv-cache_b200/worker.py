@@ -22,6 +22,23 @@ DEFAULT_MAX_WRITE_QUEUED_SECONDS = 10.0
 DEFAULT_MAX_HBM_STAGING_MB = 1024
 
 
+def plan_worker_memory(per_block_bytes: int, gpu_blocks_per_file: int, threads_per_gpu: int,
+                       max_staging_memory_gb: float, extra_config: dict | None = None):
+    """Staging budget clamp (worker.py:303-319) for THIS engine.  What one of its workers allocates is a chunk of whole
+    files (>= one file) of HBM plus, in the file tier, the same amount of pinned host memory — not the reference's one
+    file-sized host buffer and no HBM at all — so the clamp is on the chunk and covers both memories: the host side by
+    ``max_staging_memory_gb`` (the reference's knob), the HBM side by ``max_hbm_staging_mb`` (default 1 GiB).
+    Returns (worker threads, chunk_bytes)."""
+    extra_config = extra_config or {}
+    file_bytes = per_block_bytes * gpu_blocks_per_file
+    chunk_bytes = max(int(extra_config.get("chunk_bytes", 0)) or file_bytes, file_bytes)
+    chunk_mb = math.ceil(chunk_bytes / (1 << 20))
+    budget_mb = min(max_staging_memory_gb * 1024, int(extra_config.get("max_hbm_staging_mb", DEFAULT_MAX_HBM_STAGING_MB)))
+    if chunk_mb * threads_per_gpu > budget_mb:
+        threads_per_gpu = max(1, min(threads_per_gpu, int(budget_mb / chunk_mb)))
+    return threads_per_gpu, chunk_bytes
+
+
 class BaseStorageOffloadingHandler:
     """Common bookkeeping of both directions (worker.py:64-193)."""
 
@@ -107,17 +124,8 @@ class StorageOffloadingHandlers:
         tensors = [getattr(t, "tensor", t) for t in raw]
         assert tensors
         per_block_bytes = sum(t.stride(0) * t.element_size() for t in tensors)  # worker.py:336
-        # staging budget clamp (worker.py:303-319).  What a worker of THIS engine allocates is one chunk (whole files,
-        # >= one file) of HBM plus, in the file tier, the same amount of pinned host memory — not the reference's one
-        # file-sized host buffer — so the clamp is on the chunk, for both memories.
-        file_bytes = per_block_bytes * gpu_blocks_per_file
-        chunk_bytes = int(extra_config.get("chunk_bytes", 0)) or file_bytes
-        chunk_bytes = max(chunk_bytes, file_bytes)
-        chunk_mb = math.ceil(chunk_bytes / (1 << 20))
-        hbm_budget_mb = int(extra_config.get("max_hbm_staging_mb", DEFAULT_MAX_HBM_STAGING_MB))
-        budget_mb = min(max_staging_memory_gb * 1024, hbm_budget_mb)
-        if chunk_mb * threads_per_gpu > budget_mb:
-            threads_per_gpu = max(1, min(threads_per_gpu, int(budget_mb / chunk_mb)))
+        threads_per_gpu, chunk_bytes = plan_worker_memory(per_block_bytes, gpu_blocks_per_file, threads_per_gpu,
+                                                          max_staging_memory_gb, extra_config)
         extra_config = dict(extra_config, chunk_bytes=chunk_bytes)
         read_preferring_workers = max(1, int(threads_per_gpu * read_preferring_ratio))  # worker.py:322
         self.engine = self._create_engine(

@@ -462,3 +462,64 @@ def test_gds_tier_format_and_roundtrip(kvb, torch_cuda, mode):
         assert torch.equal(z[35], t[11]) and torch.equal(z[36], t[12])
     eng.shutdown()
     eng2.shutdown()
+
+
+@pytest.mark.parametrize("tier", ["file", "host_arena"])
+def test_manager_lookup_is_one_library_call(kvb, torch_cuda, tier):
+    """SharedStorageOffloadingManager.lookup (manager.py:43-53): consecutive hits from the start, stopping at the first
+    miss — through kvb_engine_lookup_prefix, against the reference's per-block loop on the same state."""
+    torch = torch_cuda
+    bpf = 2
+    tensors = [torch.randint(0, 256, (64, 4096), dtype=torch.uint8, device="cuda") for _ in range(4)]
+    kw = dict(tier=tier, host_arena_bytes=8 << 20) if tier == "host_arena" else {}
+    eng = kvb.engine.StorageOffloadEngine(2, bpf, tensors, 1, "disabled", 0.0, **kw)
+    fm = _mapper(kvb, bpf)
+    hashes = _hashes(24)
+    files = [fm.get_file_name(h) for h in hashes]
+    present = [0, 1, 2, 3, 4, 6, 7, 10]                      # a hole at 5: the prefix is 5 long whatever comes after
+    assert eng.async_store_gpu_blocks(1, [files[i] for i in present], [[2 * i, 2 * i + 1] for i in present])
+    while not eng.get_finished():
+        time.sleep(0.001)
+    mgr = kvb.manager.SharedStorageOffloadingManager(fm, engine=eng)
+    loop = kvb.manager.SharedStorageOffloadingManager(fm, exists=eng.exists)          # the reference's loop
+    for start in (0, 1, 5, 6, 10, 11):
+        assert mgr.lookup(hashes[start:]) == loop.lookup(hashes[start:]), start
+    assert mgr.lookup(hashes) == 5 and mgr.lookup(hashes[6:]) == 2 and mgr.lookup(hashes[5:]) == 0 and mgr.lookup([]) == 0
+    assert eng.lookup_prefix([files[0], files[1]]) == 2
+    eng.shutdown()
+
+
+def test_arena_miss_fails_the_load(kvb, torch_cuda):
+    """The reference swallows a vanished FILE (storage_offload.cpp:378-383).  An entry the host arena's own LRU dropped
+    is a different thing — nothing was restored — and must fail the job without any strict flag."""
+    torch = torch_cuda
+    tensors = [torch.randint(0, 256, (8, 1 << 16), dtype=torch.uint8, device="cuda")]
+    eng = kvb.engine.StorageOffloadEngine(1, 1, tensors, 1, "disabled", 0.0, tier="host_arena", host_arena_bytes=2 << 16)
+    for i in range(3):                                       # room for 2: k0 is evicted by k2
+        assert eng.async_store_gpu_blocks(i, [f"k{i}"], [[i]])
+        while not eng.get_finished():
+            time.sleep(0.001)
+    assert not eng.exists("k0")
+    assert eng.async_load_gpu_blocks(10, ["k0"], [[0]])
+    res = []
+    while not res:
+        res = eng.get_finished()
+        time.sleep(0.001)
+    assert res == [(10, False)] and eng.stats()["load_failures"] == 1
+    eng.shutdown()
+
+
+def test_engine_that_cannot_allocate_its_workers_fails_at_construction(kvb, torch_cuda):
+    """Worker resources (a packed HBM chunk per worker) are part of construction: asking for more than the device has is a
+    constructor error, not a load that quietly restores nothing later."""
+    torch = torch_cuda
+    tensors = [torch.randint(0, 256, (8, 1 << 16), dtype=torch.uint8, device="cuda")]
+    free, _total = torch.cuda.mem_get_info()
+    per_worker = (free // 4 + (1 << 30)) // (1 << 16) * (1 << 16)       # 8 workers x > free/4: cannot fit
+    with pytest.raises(Exception) as ei:
+        kvb.engine.StorageOffloadEngine(8, 1, tensors, 1, "disabled", 0.0, tier="host_arena", host_arena_bytes=4 << 16,
+                                        chunk_bytes=per_worker)
+    assert "do not fit" in str(ei.value) or "NOMEM" in str(ei.value) or "-3" in str(ei.value)
+    # and the device is still usable afterwards
+    ok = kvb.engine.StorageOffloadEngine(2, 1, tensors, 1, "disabled", 0.0, tier="host_arena", host_arena_bytes=4 << 16)
+    ok.shutdown()

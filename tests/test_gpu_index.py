@@ -270,3 +270,58 @@ def test_pinned_token_buffer_scores_like_pageable(kvb, torch_cuda):
     del pinned
     buf.free()
     buf.free()  # idempotent
+
+
+def test_scoring_refreshes_recency_by_default(kvb, torch_cuda):
+    """Capacity pressure with SCORING between adds: the reference's ScoreTokens goes through Lookup, whose data.Get
+    refreshes every key it finds (in_memory.go:120), so which keys the outer LRU evicts depends on what was scored.
+    The batched scoring paths do the same by default (the kernel stamps the slots); `touch_lru=False` opts out."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(77)
+    idx, oidx = K.Index(size=64, pod_cache_size=3, expected_keys=16), o.InMemoryIndex(size=64, pod_cache_size=3)
+    keyspace = [int(x) for x in rng.integers(1, 1 << 63, 160)]
+    pods = ["pod-%d" % i for i in range(6)]
+    for step in range(400):
+        r = rng.random()
+        if r < 0.5:
+            ks = [keyspace[int(i)] for i in rng.integers(0, len(keyspace), int(rng.integers(1, 5)))]
+            ent = (pods[int(rng.integers(0, 6))], "gpu" if rng.random() < 0.7 else "cpu")
+            idx.add(None, ks, [K.PodEntry(*ent)])
+            oidx.add(None, ks, [o.PodEntry(*ent)])
+        else:
+            # a batch of "prompts" scored in one call: the oracle scores them one after the other
+            prompts = [[keyspace[int(i)] for i in rng.integers(0, len(keyspace), int(rng.integers(1, 12)))]
+                       for _ in range(int(rng.integers(1, 6)))]
+            flat = np.asarray([k for p in prompts for k in p], dtype=np.uint64)
+            off = np.cumsum([0] + [len(p) for p in prompts]).astype(np.int64)
+            got = idx.score_keys_batch(flat, off)
+            for p, g in zip(prompts, got):
+                assert g == o.longest_prefix_score(p, oidx.lookup(p), {"gpu": 1.0, "cpu": 0.8}), step
+        if step % 50 == 49:
+            assert set(idx.lookup(keyspace)) == set(oidx.lookup(keyspace)), step   # same survivors
+    assert idx.stats()["lru_evictions"] > 20
+    # opt-out: read-only scoring leaves the eviction order alone
+    e = [K.PodEntry("p", "gpu")]
+    ro = K.Index(size=3, pod_cache_size=2)
+    for k in (1, 2, 3):
+        ro.add(None, [k], e)
+    ro.score_keys_batch(np.asarray([1], dtype=np.uint64), np.asarray([0, 1], dtype=np.int64), touch_lru=False)
+    ro.add(None, [4], e)
+    assert set(ro.lookup([1, 2, 3, 4])) == {2, 3, 4}          # 1 was scored read-only: still the oldest, evicted
+
+
+def test_device_side_build_uses_the_parallel_path(kvb, torch_cuda):
+    """A bulk build never touches a host copy: ops are queued, sorted and replayed per key on the device."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(3)
+    idx, oidx = K.Index(expected_keys=1 << 12), o.InMemoryIndex()
+    keys = [int(x) for x in rng.integers(1, 1 << 63, 50000)]
+    for i in range(0, 50000, 5000):
+        ents = [("pod-%d" % int(rng.integers(0, 30)), "gpu" if rng.random() < 0.8 else "cpu") for _ in range(int(rng.integers(1, 5)))]
+        chunk = keys[i:i + 5000] + keys[max(0, i - 700):i]           # overlaps: the same key gets entries from several calls
+        idx.add(None, chunk, [K.PodEntry(*e) for e in ents])
+        oidx.add(None, chunk, [o.PodEntry(*e) for e in ents])
+    st = idx.stats()
+    assert st["live_keys"] == len(oidx.data) == 50000 and st["flushes_parallel"] >= 1 and st["rehashes"] >= 1
+    sample = [keys[int(i)] for i in rng.integers(0, 50000, 3000)]
+    assert _as_tuples(idx.lookup(sample)) == _as_tuples(oidx.lookup(sample))

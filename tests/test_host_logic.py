@@ -172,3 +172,18 @@ def test_manager_and_spec(kvb, tmp_path):
     cfg.parallel_config.rank = 1
     with pytest.raises(AssertionError):
         kvb.spec.SharedStorageOffloadingSpec(cfg).get_manager()               # scheduler rank must be 0
+
+
+def test_worker_memory_plan_counts_the_hbm_chunk(kvb):
+    """worker.py:303-319 clamps threads by host staging only; this engine also packs a chunk in HBM per worker, after
+    vLLM has sized its KV cache — the plan bounds io_threads x chunk for both memories."""
+    plan = kvb.worker.plan_worker_memory
+    block = 2 << 20                                             # Llama-3-8B block
+    # default: chunk = one file (16 blocks = 32 MiB), 1 GiB of HBM staging -> 32 workers, not 64 x 64 MiB = 4 GiB
+    assert plan(block, 16, 64, 150) == (32, 32 << 20)
+    assert plan(block, 16, 8, 150) == (8, 32 << 20)             # small pools are left alone
+    assert plan(block, 16, 64, 150, {"chunk_bytes": 64 << 20}) == (16, 64 << 20)
+    assert plan(block, 16, 64, 150, {"chunk_bytes": 1}) == (32, 32 << 20)          # a chunk always holds a whole file
+    assert plan(block, 16, 64, 0.25) == (8, 32 << 20)           # the reference's host budget still binds (256 MiB)
+    assert plan(block, 16, 64, 150, {"max_hbm_staging_mb": 4096}) == (64, 32 << 20)
+    assert plan(block, 1024, 64, 150)[0] == 1                   # one 2 GiB file per worker: a single worker, never zero
