@@ -124,3 +124,139 @@ def test_round_without_the_shift():
         for i, byte in enumerate(stream):
             assert z[i // 3][i % 3] == (h & 0xFF) ^ byte
             h = ((h ^ byte) * P) & M
+
+
+# ---- round 2 formulation (chain_kernel): merged first round for bits 0 and 1, per-block table constants, 3 REDUX -------
+def _ballot(preds):
+    return sum((1 << L) for L in range(32) if preds[L])
+
+
+def _par(x):
+    return bin(x).count("1") & 1
+
+
+def resolve_z_merged(b):
+    """z bytes (running low byte xor stream byte) for all 96 positions; bits 0 and 1 come from SIX independent ballots
+    (bit 0 / bit 1 of each lane's three bytes) — mod 4, x -> 0xb3 * x is the GF(2)-linear map (z1,z0) -> (z1^z0, z0), so the
+    prefix is a plain XOR prefix with position-parity masks — bits 2..7 from the usual dependent vote rounds."""
+    l00, l01 = H0 & 1, (H0 >> 1) & 1
+    V0 = [_ballot([(b[L][j] >> 0) & 1 for L in range(32)]) for j in range(3)]
+    V1 = [_ballot([(b[L][j] >> 1) & 1 for L in range(32)]) for j in range(3)]
+    EVEN, ODD = 0x55555555, 0xAAAAAAAA
+    z = [[0, 0, 0] for _ in range(32)]
+    for L in range(32):
+        lt = (1 << L) - 1
+        for j in range(3):
+            i = 3 * L + j
+            # lanes whose slot-j' position is <= i (le) / < i (ls): all earlier lanes, plus my own lane when j' <= j / j' < j
+            le = [lt | ((1 << L) if jp <= j else 0) for jp in range(3)]
+            ls = [lt | ((1 << L) if jp < j else 0) for jp in range(3)]
+            # positions of the OPPOSITE parity to i among slot j': lane parity must differ from (i + j') parity ...
+            opp = [(EVEN if ((i + jp) & 1) else ODD) for jp in range(3)]      # position 3L'+j' has parity (L'+j')&1
+            z0 = l00 ^ _par((V0[0] & le[0]) ^ (V0[1] & le[1]) ^ (V0[2] & le[2]))
+            a = _par((V0[0] & ls[0] & opp[0]) ^ (V0[1] & ls[1] & opp[1]) ^ (V0[2] & ls[2] & opp[2]))
+            z1 = l01 ^ _par((V1[0] & le[0]) ^ (V1[1] & le[1]) ^ (V1[2] & le[2])) ^ ((i & 1) * l00) ^ a
+            z[L][j] = (b[L][j] & 0xFC) | (z1 << 1) | z0
+    for k in range(2, 8):                       # the dependent rounds, unchanged
+        mask = 1 << k
+        p = [[(z[L][j] * 0xB3) & 0xFFFFFFFF for j in range(3)] for L in range(32)]
+        votes = _ballot([((p[L][0] ^ p[L][1] ^ p[L][2]) >> k) & 1 for L in range(32)])
+        for L in range(32):
+            before = _par(votes & ((1 << L) - 1))
+            m0 = mask if (H0 & 0xFF) & mask else 0
+            zc = [z[L][0] ^ m0, z[L][1] ^ m0 ^ (p[L][0] & mask), z[L][2] ^ m0 ^ ((p[L][0] ^ p[L][1]) & mask)]
+            z[L] = [zc[j] ^ ((before << k) & mask) for j in range(3)]
+    return z
+
+
+def chain2(stream):
+    m = len(stream)
+    assert m <= 96
+    b = [[stream[3 * L + j] if 3 * L + j < m else 0 for j in range(3)] for L in range(32)]
+    z = resolve_z_merged(b)
+    # key = P^m * H0 + sum_i e_i * P^(m - i): the per-lane constants come from a table indexed by m - position, so no
+    # multiply follows the reduction
+    terms = []
+    for L in range(32):
+        t = (pow(P, m, 1 << 64) * H0) & M if L == 0 else 0
+        for j in range(3):
+            i = 3 * L + j
+            c = pow(P, max(m - i, 0), 1 << 64)
+            clo = c & 0xFFFFFFFF
+            clo_s = clo - (1 << 32) if clo >= 1 << 31 else clo
+            chi = ((c >> 32) + (1 if clo_s < 0 else 0)) & 0xFFFFFFFF
+            e = z[L][j] - (z[L][j] ^ b[L][j])
+            t = (t + e * clo_s + ((e * chi & 0xFFFFFFFF) << 32)) & M
+        terms.append(t)
+    # three REDUX: sum of low words mod 2^32, EXACT sum of their upper halves (21 bits), sum of high words mod 2^32
+    r1 = sum(t & 0xFFFFFFFF for t in terms) & 0xFFFFFFFF
+    r2 = sum((t & 0xFFFFFFFF) >> 16 for t in terms)
+    r3 = sum(t >> 32 for t in terms) & 0xFFFFFFFF
+    low_part = (r1 - (r2 << 16)) & 0xFFFFFFFF            # = exact sum of the lower halves (< 2^21)
+    carry = ((r2 << 16) + low_part) >> 32
+    return ((((r3 + carry) & 0xFFFFFFFF) << 32) | r1)
+
+
+def test_merged_first_round_resolves_the_same_low_bytes():
+    rng = random.Random(7)
+    for _ in range(300):
+        m = rng.randrange(0, 97)
+        stream = [rng.randrange(256) for _ in range(m)]
+        b = [[stream[3 * L + j] if 3 * L + j < m else 0 for j in range(3)] for L in range(32)]
+        z = resolve_z_merged(b)
+        h = H0
+        for i, byte in enumerate(stream):
+            assert z[i // 3][i % 3] == (h & 0xFF) ^ byte, (m, i)
+            h = ((h ^ byte) * P) & M
+
+
+def test_chain2_equals_fnv1a():
+    rng = random.Random(8)
+    for _ in range(400):
+        stream = [rng.randrange(256) for _ in range(rng.randrange(0, 97))]
+        assert chain2(stream) == fnv(stream)
+    for _ in range(100):                                   # adversarial for the carry logic: all-ones bytes
+        stream = [rng.choice([0xFF, 0x00, 0x80]) for _ in range(rng.randrange(60, 97))]
+        assert chain2(stream) == fnv(stream)
+
+
+def test_static_plus_parent_masks_decomposition():
+    """What chain_kernel ships: the stager resolves bits 0/1 of z for the stream with the parent bytes ZEROED (six ballots,
+    off the chain); the folder adds the parent's contribution with two 64-bit masks per position and a popcount each —
+    no warp vote on the chain for the first two bits.  Stream = 83 1b P7..P0 (80+bs) tokens.. f6, parent at positions 2..9."""
+    rng = random.Random(9)
+    for _ in range(300):
+        key = rng.getrandbits(64) | (1 << 32)
+        body = [rng.randrange(256) for _ in range(rng.randrange(1, 83))]
+        stream = [0x83, 0x1B] + list(key.to_bytes(8, "big")) + [0x90] + body
+        m = len(stream)
+        zeroed = stream[:2] + [0] * 8 + stream[10:]
+        bz = [[zeroed[3 * L + j] if 3 * L + j < m else 0 for j in range(3)] for L in range(32)]
+        bs = [[stream[3 * L + j] if 3 * L + j < m else 0 for j in range(3)] for L in range(32)]
+        # static part: bits 0/1 of z with parent bytes zero (the merged round on the zeroed stream)
+        l00, l01 = H0 & 1, (H0 >> 1) & 1
+        V0 = [_ballot([(bz[L][j] >> 0) & 1 for L in range(32)]) for j in range(3)]
+        V1 = [_ballot([(bz[L][j] >> 1) & 1 for L in range(32)]) for j in range(3)]
+        EVEN, ODD = 0x55555555, 0xAAAAAAAA
+        h = H0
+        want = []
+        for byte in stream:
+            want.append((h & 0xFF) ^ byte)
+            h = ((h ^ byte) * P) & M
+        for L in range(32):
+            lt = (1 << L) - 1
+            for j in range(3):
+                i = 3 * L + j
+                if i >= m:
+                    continue
+                le = [lt | ((1 << L) if jp <= j else 0) for jp in range(3)]
+                lso = [(lt | ((1 << L) if jp < j else 0)) & (EVEN if ((i + jp) & 1) else ODD) for jp in range(3)]
+                st0 = l00 ^ _par((V0[0] & le[0]) ^ (V0[1] & le[1]) ^ (V0[2] & le[2]))
+                st1 = (l01 ^ ((i & 1) * l00) ^ _par((V1[0] & le[0]) ^ (V1[1] & le[1]) ^ (V1[2] & le[2]))
+                       ^ _par((V0[0] & lso[0]) ^ (V0[1] & lso[1]) ^ (V0[2] & lso[2])))
+                # dynamic part: masks over the parent key; the parent byte at stream position p is byte (9 - p) of the key
+                mle = sum(1 << (8 * (9 - p)) for p in range(2, min(i, 9) + 1))
+                mopp = sum(1 << (8 * (9 - p)) for p in range(2, min(i - 1, 9) + 1) if (i - p) & 1)
+                z0 = st0 ^ _par(key & mle)
+                z1 = st1 ^ _par(key & ((mle << 1) | mopp))
+                assert (z0, z1) == (want[i] & 1, (want[i] >> 1) & 1), (i, m)
