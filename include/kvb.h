@@ -16,6 +16,7 @@
  *     when no sm_100 device is usable.
  *   - environment switches (diagnostics and A/B runs, never needed for correctness):
  *       KVB_HASH_KERNEL=lanes   hash with the lane-per-prompt kernels at every batch size (read per call)
+ *       KVB_HASH_KERNEL=wpc     hash with round 1's warp-per-prompt kernel instead of the current chain kernel
  *       KVB_HASH_ONE_WARP=1     hash with the one-warp lane kernel (read once)
  *       KVB_NO_NUMA_BIND=1      do not bind engine threads / arena to the GPU's NUMA node
  */

@@ -641,6 +641,305 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_wpc(const uint32_t* __re
 #undef WPROF
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// chain kernel, second formulation (round 2).  Same idea as hash_chain_kernel_wpc — one warp folds one block's byte
+// stream with the T-function rounds — with three changes that shorten the serial part of a block:
+//   (a) bits 0 and 1 of every z byte need NO vote on the chain.  Mod 4, x -> 0xb3 * x is the GF(2)-linear map
+//       (z1, z0) -> (z1 ^ z0, z0), so bits 0/1 of the running low byte are plain XOR prefixes of bits 0/1 of the stream
+//       (with a position-parity mask for the cross term).  The stream's only unknown bytes are the eight parent bytes at
+//       positions 2..9, and every lane holds the parent: the stager resolves bits 0/1 for the stream with the parent
+//       ZEROED (six ballots, off the chain) and the folder adds the parent's contribution with two 64-bit masks per
+//       position and one popcount each.  Six dependent vote rounds per block remain instead of eight;
+//   (b) key = P^m * H0 + sum_i e_i * P^(m - i): the per-lane constants are table entries indexed by (stream length -
+//       position), looked up by the stager, so nothing is multiplied after the warp reduction;
+//   (c) the 64-bit warp sum is three REDUX instead of four: low words mod 2^32, the EXACT sum of their upper halves
+//       (21 bits) which recovers the carry, high words mod 2^32;
+// and the stager and the folder no longer meet at a CTA barrier every block: staged blocks sit in a four-slot ring, the
+// two warps exchange progress counters in shared memory (release / acquire), and tokens are fetched seven blocks ahead.
+// The arithmetic is restated on the CPU in tests/test_wpc_math.py (chain2, static + parent-mask decomposition).
+constexpr int kV2Slots = 4;    // staged blocks the stager may run ahead
+constexpr int kV2TokRing = 8;  // token blocks in flight (cp.async commit groups), power of two
+
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+template <int BS>
+__global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __restrict__ tokens,
+                                                           const int64_t* __restrict__ prompt_off,
+                                                           const uint64_t* __restrict__ parents,
+                                                           const uint8_t* __restrict__ extra,
+                                                           const int64_t* __restrict__ extra_off,
+                                                           uint64_t* __restrict__ out_keys,
+                                                           const int64_t* __restrict__ key_off) {
+  static_assert(BS > 0 && BS < 24 && kWpcPrefix + 5 * BS + 1 <= kWpcPositions, "stream must fit 96 positions");
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int S = kV2Slots, TR = kV2TokRing;
+  // per staged block: bw = the lane's 3 stream bytes (parent bytes zero) with the static z bits 0/1 of the three positions
+  // in bits 24..29; cq = {lo, hi'} of P^(m - position) for the lane's three positions; meta = {P^m * H0, bytes after
+  // the prefix, nil-extra flag}; raw = the token bytes for the byte-serial fallback
+  __shared__ uint32_t bw[S][32];
+  __shared__ uint2 cq[S][3][32];
+  __shared__ uint8_t raw[S][kWpcPositions];
+  __shared__ uint4 meta[S];
+  __shared__ uint32_t tring[TR][BS];
+  __shared__ uint64_t pw[kWpcPositions + 1];  // P^t
+  __shared__ uint32_t slot_id[2];
+  __shared__ int staged, folded;  // blocks published by the stager / consumed by the folder
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x;
+  const int64_t t0 = prompt_off[p];
+  const int nblk = (int)((prompt_off[p + 1] - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
+  if (nblk == 0) return;
+  const int64_t k0 = key_off[p];
+  for (int t = threadIdx.x; t <= kWpcPositions; t += 64) pw[t] = pow_u64(kFnvPrime, (uint32_t)t);
+  if (threadIdx.x == 0) {
+    staged = 0;
+    folded = 0;
+  }
+  if (lane == 0) {  // which warp folds: see hash_chain_kernel_wpc
+    uint32_t wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    slot_id[threadIdx.x >> 5] = wid;
+  }
+  __syncthreads();  // the only CTA barrier: publishes pw[], the counters and the slot ids
+  const uint32_t sa = slot_id[0], sb = slot_id[1];
+  const bool fa = ((sa >> 2) & 1u) == (sa & 1u), fb = ((sb >> 2) & 1u) == (sb & 1u);
+  const int folder_warp = (fa != fb) ? (fa ? 0 : 1) : 1;
+  const bool stager = (int)(threadIdx.x >> 5) != folder_warp;
+  const uint32_t lt = (1u << lane) - 1u, self = 1u << lane;
+
+  if (stager) {
+    // lanes whose slot-j' position is <= / < this lane's position j, the latter restricted to the opposite position
+    // parity (position 3L + j has parity (L + j) & 1): masks over the six ballots
+    uint32_t le[3][3], lso[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int jp = 0; jp < 3; ++jp) {
+        le[j][jp] = lt | (jp <= j ? self : 0u);
+        const uint32_t opp = ((3 * lane + j + jp) & 1) ? 0x55555555u : 0xaaaaaaaau;
+        lso[j][jp] = (lt | (jp < j ? self : 0u)) & opp;
+      }
+    constexpr uint32_t l00 = (uint32_t)(kFnvOffset & 1u), l01 = (uint32_t)((kFnvOffset >> 1) & 1u);
+    auto fetch_tokens = [&](int i) {  // one commit group per block, empty past the end so the group count stays uniform
+      if (lane < BS && i < nblk) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[i & (TR - 1)][lane]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(tokens + t0 + (int64_t)i * BS + lane));
+      }
+      asm volatile("cp.async.commit_group;");
+    };
+#pragma unroll
+    for (int i = 0; i < TR - 1; ++i) fetch_tokens(i);
+    int buf = 0;
+    for (int i = 0; i < nblk; ++i) {
+      fetch_tokens(i + TR - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(TR - 1) : "memory");  // all but the newest TR-1 groups: block i landed
+      if (i >= S)
+        while (ld_acquire_cta(&folded) < i - S + 1) {
+        }  // the slot's previous block has been consumed
+      const uint32_t t = lane < BS ? tring[i & (TR - 1)][lane] : 0u;  // each lane reads back its own copy
+      const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
+      const uint32_t head = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
+      const uint32_t pay = ge64k ? t : (ge256 ? (t << 16) : (t << 24));  // payload, left-aligned big-endian
+      const uint32_t v24 = __ballot_sync(kFull, ge24), v256 = __ballot_sync(kFull, ge256),
+                     v64k = __ballot_sync(kFull, ge64k);
+      const int w = 1 + (ge24 ? 1 : 0) + (ge256 ? 1 : 0) + (ge64k ? 2 : 0);
+      const int off = lane + __popc(v24 & lt) + __popc(v256 & lt) + 2 * __popc(v64k & lt);
+      const int n_tok = BS + __popc(v24) + __popc(v256) + 2 * __popc(v64k);
+      bool text = true;
+      if (extra_off != nullptr) text = extra_off[k0 + i + 1] <= extra_off[k0 + i];
+      {  // exactly w bytes per token; lane BS appends f6 for a nil extra; predicated stores, no divergent branches
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(raw[buf]) + (lane < BS ? off : n_tok);
+        const uint32_t first = lane < BS ? head : 0xf6u;
+        const int nst = lane < BS ? w : ((lane == BS && text) ? 1 : 0);
+        asm volatile(
+            "{\n\t.reg .pred p1, p2, p3, p4;\n\t"
+            "setp.gt.s32 p1, %2, 0;\n\tsetp.gt.s32 p2, %2, 1;\n\tsetp.gt.s32 p3, %2, 2;\n\tsetp.gt.s32 p4, %2, 3;\n\t"
+            "@p1 st.shared.u8 [%0], %1;\n\t@p2 st.shared.u8 [%0+1], %3;\n\t@p3 st.shared.u8 [%0+2], %4;\n\t"
+            "@p4 st.shared.u8 [%0+3], %5;\n\t@p4 st.shared.u8 [%0+4], %6;\n\t}"
+            :
+            : "r"(d), "r"(first), "r"(nst), "r"(pay >> 24), "r"((pay >> 16) & 0xffu), "r"((pay >> 8) & 0xffu), "r"(pay & 0xffu)
+            : "memory");
+      }
+      __syncwarp();
+      const int n_tot = n_tok + (text ? 1 : 0);
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {  // unconditional loads from a clamped index, then selects
+        const int pos = 3 * lane + j, idx = pos - kWpcPrefix;
+        const uint32_t ld = raw[buf][idx < 0 ? 0 : idx];
+        const uint32_t fixed = pos == 0 ? 0x83u : (pos == 1 ? 0x1bu : (pos == kWpcPrefix - 1 ? (0x80u | BS) : 0u));
+        const uint32_t byte = (idx >= 0 && idx < n_tot) ? ld : fixed;
+        word |= byte << (8 * j);
+      }
+      // (a) static bits 0/1 of z at this lane's three positions, parent bytes taken as zero
+      uint32_t v0[3], v1[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        v0[j] = __ballot_sync(kFull, (word >> (8 * j)) & 1u);
+        v1[j] = __ballot_sync(kFull, (word >> (8 * j + 1)) & 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t x0 = (v0[0] & le[j][0]) ^ (v0[1] & le[j][1]) ^ (v0[2] & le[j][2]);
+        const uint32_t x1 = (v1[0] & le[j][0]) ^ (v1[1] & le[j][1]) ^ (v1[2] & le[j][2]);
+        const uint32_t xa = (v0[0] & lso[j][0]) ^ (v0[1] & lso[j][1]) ^ (v0[2] & lso[j][2]);
+        const uint32_t z0 = (l00 ^ (uint32_t)__popc(x0)) & 1u;
+        const uint32_t z1 = (l01 ^ (((3 * lane + j) & 1) ? l00 : 0u) ^ (uint32_t)(__popc(x1) + __popc(xa))) & 1u;
+        word |= (z0 | (z1 << 1)) << (24 + 2 * j);
+      }
+      bw[buf][lane] = word;
+      // (b) per-position constants P^(m - position), split for the signed 32 x 32 products of the folder
+      const int m = kWpcPrefix + n_tot;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int d = m - (3 * lane + j);
+        const uint64_t c = pw[d < 0 ? 0 : d];
+        const int32_t clo = (int32_t)(uint32_t)c;  // c = (chi + [clo < 0]) * 2^32 + (signed) clo
+        cq[buf][j][lane] = make_uint2((uint32_t)clo, (uint32_t)(c >> 32) + (clo < 0 ? 1u : 0u));
+      }
+      if (lane == 0) {
+        const uint64_t pmh = pw[m] * kFnvOffset;
+        meta[buf] = make_uint4((uint32_t)pmh, (uint32_t)(pmh >> 32), (uint32_t)n_tot, text ? 1u : 0u);
+      }
+      __syncwarp();
+      if (lane == 0) st_release_cta(&staged, i + 1);
+      buf = buf == S - 1 ? 0 : buf + 1;
+    }
+    return;
+  }
+
+  // ---- folder
+  // where the parent's bytes land in this lane's word (stream position 2 + k carries parent byte 7 - k), and the masks
+  // that give the parent's contribution to bits 0/1 of z at the lane's three positions:
+  //   z0 ^= parity(parent & mle),  z1 ^= parity(parent & ((mle << 1) | mopp))
+  // mle = bit 0 of the parent bytes at positions <= i, mopp = bit 0 of those at positions < i of the opposite parity
+  uint32_t psel = 0, pmask = 0;
+  uint32_t m0lo[3], m0hi[3], m1lo[3], m1hi[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int pos = 3 * lane + j;
+    if (pos >= 2 && pos <= 9) {
+      psel |= (uint32_t)(9 - pos) << (4 * j);
+      pmask |= 0xffu << (8 * j);
+    }
+    uint64_t mle = 0, mopp = 0;
+    for (int q = 2; q <= 9; ++q) {
+      if (q <= pos) mle |= 1ull << (8 * (9 - q));
+      if (q < pos && ((pos - q) & 1)) mopp |= 1ull << (8 * (9 - q));
+    }
+    const uint64_t m1 = (mle << 1) | mopp;
+    m0lo[j] = (uint32_t)mle;
+    m0hi[j] = (uint32_t)(mle >> 32);
+    m1lo[j] = (uint32_t)m1;
+    m1hi[j] = (uint32_t)(m1 >> 32);
+  }
+  uint64_t parent = parents[p];
+  while (ld_acquire_cta(&staged) < 1) {
+  }
+  uint32_t w_cur = bw[0][lane];
+  uint2 c_cur[3] = {cq[0][0][lane], cq[0][1][lane], cq[0][2][lane]};
+  uint4 m_cur = meta[0];
+  int cbuf = 0, nbuf = 1;
+  for (int i = 0; i < nblk; ++i) {
+    uint32_t w_nxt = 0;
+    uint2 c_nxt[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+    uint4 m_nxt = make_uint4(0, 0, 0, 1);
+    if (i + 1 < nblk) {  // normally published long ago: the stager runs up to S blocks ahead
+      while (ld_acquire_cta(&staged) < i + 2) {
+      }
+      w_nxt = bw[nbuf][lane];
+      c_nxt[0] = cq[nbuf][0][lane];
+      c_nxt[1] = cq[nbuf][1][lane];
+      c_nxt[2] = cq[nbuf][2][lane];
+      m_nxt = meta[nbuf];
+    }
+    uint64_t key;
+    if (parent >= 0x100000000ull) {
+      const uint32_t klo = (uint32_t)parent, khi = (uint32_t)(parent >> 32);
+      const uint32_t w = (w_cur & 0x00ffffffu) | (__byte_perm(klo, khi, psel) & pmask);
+      const uint32_t b0 = __byte_perm(w, 0u, 0x4440u), b1 = __byte_perm(w, 0u, 0x4441u), b2 = __byte_perm(w, 0u, 0x4442u);
+      // bits 0/1: static part from the stager, parent part from two masked popcounts per position — no vote
+      const uint32_t q00 = (uint32_t)__popc((klo & m0lo[0]) ^ (khi & m0hi[0])), q10 = (uint32_t)__popc((klo & m1lo[0]) ^ (khi & m1hi[0]));
+      const uint32_t q01 = (uint32_t)__popc((klo & m0lo[1]) ^ (khi & m0hi[1])), q11 = (uint32_t)__popc((klo & m1lo[1]) ^ (khi & m1hi[1]));
+      const uint32_t q02 = (uint32_t)__popc((klo & m0lo[2]) ^ (khi & m0hi[2])), q12 = (uint32_t)__popc((klo & m1lo[2]) ^ (khi & m1hi[2]));
+      const uint32_t s0 = w_cur >> 24, s1 = w_cur >> 26, s2 = w_cur >> 28;
+      uint32_t z0 = (b0 & 0xfcu) | ((s0 ^ (q00 & 1u) ^ ((q10 & 1u) << 1)) & 3u);
+      uint32_t z1 = (b1 & 0xfcu) | ((s1 ^ (q01 & 1u) ^ ((q11 & 1u) << 1)) & 3u);
+      uint32_t z2 = (b2 & 0xfcu) | ((s2 ^ (q02 & 1u) ^ ((q12 & 1u) << 1)) & 3u);
+      // bits 2..7: the dependent rounds (IMAD -> LOP3 -> LOP3.P -> VOTE -> LOP3 -> POPC -> SHL -> LOP3 each)
+#pragma unroll
+      for (int k = 2; k < 8; ++k) {
+        constexpr uint32_t kL0 = (uint32_t)(kFnvOffset & 0xffu);
+        const uint32_t mask = 1u << k;
+        const uint32_t p0 = z0 * 0xb3u, p1 = z1 * 0xb3u, p2 = z2 * 0xb3u;
+        uint32_t votes;
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t.reg .b32 g;\n\tlop3.b32 g, %1, %2, %3, 0x96;\n\tand.b32 g, g, %4;\n\t"
+            "setp.ne.u32 q, g, 0;\n\tvote.sync.ballot.b32 %0, q, 0xffffffff;\n\t}"
+            : "=r"(votes)
+            : "r"(p0), "r"(p1), "r"(p2), "r"(mask));
+        const uint32_t mm = (kL0 & mask) ? mask : 0u;
+        uint32_t zc0 = z0 ^ mm, zc1 = z1 ^ mm ^ (p0 & mask), zc2 = z2 ^ mm ^ ((p0 ^ p1) & mask);
+        asm volatile("" : "+r"(zc0), "+r"(zc1), "+r"(zc2));  // keep them off the vote -> popc chain (no re-association)
+        const uint32_t sh = (uint32_t)__popc(votes & lt) << k;  // parity of all earlier positions' toggles -> bit k
+        asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z0) : "r"(zc0), "r"(sh), "r"(mask));
+        asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z1) : "r"(zc1), "r"(sh), "r"(mask));
+        asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z2) : "r"(zc2), "r"(sh), "r"(mask));
+      }
+      // e = z - l with l = z ^ b;  key = P^m * H0 + sum_i e_i * P^(m - i)
+      const int32_t e0 = (int32_t)z0 - (int32_t)(z0 ^ b0), e1 = (int32_t)z1 - (int32_t)(z1 ^ b1),
+                    e2 = (int32_t)z2 - (int32_t)(z2 ^ b2);
+      int64_t acc;  // three signed IMAD.WIDE
+      asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %1, %2;\n\tmad.wide.s32 t, %3, %4, t;\n\tmad.wide.s32 %0, %5, %6, t;\n\t}"
+          : "=l"(acc)
+          : "r"(e0), "r"((int32_t)c_cur[0].x), "r"(e1), "r"((int32_t)c_cur[1].x), "r"(e2), "r"((int32_t)c_cur[2].x));
+      const uint32_t hi = (uint32_t)e0 * c_cur[0].y + (uint32_t)e1 * c_cur[1].y + (uint32_t)e2 * c_cur[2].y;
+      const uint64_t pmh = ((uint64_t)m_cur.y << 32) | m_cur.x;
+      const uint64_t tl = (uint64_t)acc + ((uint64_t)hi << 32) + (lane == 0 ? pmh : 0ull);
+      const uint32_t tlo = (uint32_t)tl, thi = (uint32_t)(tl >> 32);
+      const uint32_t r1 = __reduce_add_sync(kFull, tlo), r2 = __reduce_add_sync(kFull, tlo >> 16),
+                     r3 = __reduce_add_sync(kFull, thi);
+      const uint32_t a = r2 << 16;  // exact low sum = (r2 << 16) + B with B < 2^21, and its low word is r1
+      const uint32_t carry = (r2 >> 16) + (r1 < a ? 1u : 0u);
+      key = ((uint64_t)(r3 + carry) << 32) | r1;
+    } else {  // short parent head (a caller-supplied root below 2^32): byte-serial fold, every lane the same
+      Fnv h = fnv_init();
+      fold_prefix(h, parent, (uint32_t)BS);
+      const uint8_t* src = raw[cbuf];
+      const int n_cur = (int)m_cur.z;
+      for (int k = 0; k < n_cur; ++k) fold(h, src[k]);
+      key = fnv_value(h);
+    }
+    if (!m_cur.w) {  // pre-encoded X(extra_i) follows the tokens (extra_keys.go)
+      Fnv h{(uint32_t)key, (uint32_t)(key >> 32)};
+      for (int64_t e = extra_off[k0 + i]; e < extra_off[k0 + i + 1]; ++e) fold(h, extra[e]);
+      key = fnv_value(h);
+    }
+    if (lane == 0) {
+      // slot i may be restaged: its words are in registers and raw[] has been read — every value the key depends on has
+      // arrived, so a relaxed store is enough (a release here would put a MEMBAR, and the wait for the global store
+      // below, on the chain)
+      *reinterpret_cast<volatile int*>(&folded) = i + 1;
+      out_keys[k0 + i] = key;
+    }
+    parent = key;
+    w_cur = w_nxt;
+    c_cur[0] = c_nxt[0];
+    c_cur[1] = c_nxt[1];
+    c_cur[2] = c_nxt[2];
+    m_cur = m_nxt;
+    cbuf = nbuf;
+    nbuf = nbuf == S - 1 ? 0 : nbuf + 1;
+  }
+}
+
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
 __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__ name, uint32_t len,
                                  uint64_t* __restrict__ out) {
@@ -665,6 +964,23 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   // KVB_HASH_KERNEL=lanes forces the lane-per-prompt kernels (A/B and parity tests of both families); read per call
   const char* force = std::getenv("KVB_HASH_KERNEL");
   const bool lanes_only = force != nullptr && std::strcmp(force, "lanes") == 0;
+  const bool wpc_v1 = force != nullptr && std::strcmp(force, "wpc") == 0;  // round-1 warp kernel, kept for A/B
+  if (!one_warp && !lanes_only && !wpc_v1 && n_prompts <= kWpcMaxPrompts &&
+      (block_size == 16 || block_size == 8 || block_size == 4)) {
+    if (block_size == 16)
+      hash_chain_kernel_v2<16><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    else if (block_size == 8)
+      hash_chain_kernel_v2<8><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    else
+      hash_chain_kernel_v2<4><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("hash kernel launch failed: %s", cudaGetErrorString(e));
+      return KVB_ERR_CUDA;
+    }
+    count_launch();
+    return KVB_OK;
+  }
   if (!one_warp && !lanes_only && n_prompts <= kWpcMaxPrompts && (block_size == 16 || block_size == 8 || block_size == 4)) {
     if (block_size == 16)
       hash_chain_kernel_wpc<16><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);

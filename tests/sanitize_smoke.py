@@ -48,7 +48,7 @@ while not eng.get_finished():
     pass
 eng.shutdown()
 rng = np.random.default_rng(0)
-for family, bs in [(f, b) for f in ("", "lanes") for b in (4, 16, 17, 64)]:  # warp-per-prompt and lane-per-prompt kernels
+for family, bs in [(f, b) for f in ("", "lanes", "wpc") for b in (4, 16, 17, 64)]:  # warp-per-prompt and lane-per-prompt kernels
     if family:
         os.environ["KVB_HASH_KERNEL"] = family
     else:

@@ -7,12 +7,12 @@ from oracle import kvblock_oracle as o
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "lanes"])
+@pytest.fixture(autouse=True, params=["auto", "lanes", "wpc"])
 def hash_kernel_family(request, monkeypatch):
     """Every test runs twice: default dispatch (warp-per-chain kernel for small batches of block size 4/8/16) and with
     the lane-per-prompt kernels forced (KVB_HASH_KERNEL is read on every launch)."""
-    if request.param == "lanes":
-        monkeypatch.setenv("KVB_HASH_KERNEL", "lanes")
+    if request.param in ("lanes", "wpc"):   # "wpc": the round-1 warp-per-prompt kernel, kept for A/B
+        monkeypatch.setenv("KVB_HASH_KERNEL", request.param)
     else:
         monkeypatch.delenv("KVB_HASH_KERNEL", raising=False)
     return request.param
