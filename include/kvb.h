@@ -247,6 +247,8 @@ int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const ui
 #define KVB_SCORE_TOUCH_LRU 1    /* accepted for source compatibility; this is the default now */
 #define KVB_SCORE_NO_TOUCH 2     /* opt out: read-only scoring (e.g. what-if queries that must not disturb eviction order) */
 #define KVB_SCORE_TIME_KERNELS 4 /* record CUDA events around the kernels; read them with kvb_index_get_stats */
+#define KVB_SCORE_COPY_TOKENS 8  /* A/B: copy pinned token buffers to HBM first instead of reading them in place */
+#define KVB_SCORE_TWO_KERNELS 16 /* A/B: hash kernel + score kernel instead of the fused tokens -> scores launch */
 int kvb_index_score_batch(kvb_index_t* idx, const uint64_t* keys, const int64_t* key_off, int32_t n_prompts,
                           const uint16_t* pod_filter, int32_t n_filter, int32_t flags, int32_t* out_n,
                           uint16_t* out_pods, double* out_scores);

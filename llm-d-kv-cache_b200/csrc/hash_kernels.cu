@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "kvb_internal.h"
+#include "index_device.cuh"
 
 namespace kvb {
 
@@ -375,6 +376,7 @@ static_assert(kFnvPrimeInv * kFnvPrime == 1ull, "P^-1 mod 2^64");
 constexpr int kWpcPositions = 96;  // 32 lanes x 3 stream positions
 constexpr int kWpcPrefix = 11;     // 83 1b P7..P0 (80+BS)
 constexpr int kWpcMaxPrompts = 1536;  // beyond ~2000 prompts the lane-per-prompt kernels (flat ~66 us to 19k) win
+constexpr int kChainMaxPrompts = 1536; // round-2 chain kernel; the round-1 warp kernel stays available (KVB_HASH_KERNEL=wpc)
 
 __device__ __forceinline__ uint64_t pow_u64(uint64_t base, uint32_t e) {  // e < 128
   uint64_t r = 1;
@@ -642,23 +644,32 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_wpc(const uint32_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// chain kernel, second formulation (round 2).  Same idea as hash_chain_kernel_wpc — one warp folds one block's byte
-// stream with the T-function rounds — with three changes that shorten the serial part of a block:
-//   (a) bits 0 and 1 of every z byte need NO vote on the chain.  Mod 4, x -> 0xb3 * x is the GF(2)-linear map
-//       (z1, z0) -> (z1 ^ z0, z0), so bits 0/1 of the running low byte are plain XOR prefixes of bits 0/1 of the stream
-//       (with a position-parity mask for the cross term).  The stream's only unknown bytes are the eight parent bytes at
-//       positions 2..9, and every lane holds the parent: the stager resolves bits 0/1 for the stream with the parent
-//       ZEROED (six ballots, off the chain) and the folder adds the parent's contribution with two 64-bit masks per
-//       position and one popcount each.  Six dependent vote rounds per block remain instead of eight;
-//   (b) key = P^m * H0 + sum_i e_i * P^(m - i): the per-lane constants are table entries indexed by (stream length -
-//       position), looked up by the stager, so nothing is multiplied after the warp reduction;
-//   (c) the 64-bit warp sum is three REDUX instead of four: low words mod 2^32, the EXACT sum of their upper halves
-//       (21 bits) which recovers the carry, high words mod 2^32;
-// and the stager and the folder no longer meet at a CTA barrier every block: staged blocks sit in a four-slot ring, the
-// two warps exchange progress counters in shared memory (release / acquire), and tokens are fetched seven blocks ahead.
-// The arithmetic is restated on the CPU in tests/test_wpc_math.py (chain2, static + parent-mask decomposition).
-constexpr int kV2Slots = 4;    // staged blocks the stager may run ahead
+// chain kernel (round 2): one CTA per prompt, warp 0 FOLDS the chain, warps 1..NST STAGE blocks ahead of it, and — in
+// the fused tokens -> scores form — one more warp SCORES the keys as they appear (probes and the longest-prefix walk run
+// under the hash chain; only the last tile of keys is left when the chain ends).  Same T-function rounds as
+// hash_chain_kernel_wpc, with these differences:
+//   * no CTA barrier per block: staged blocks sit in a ring of S slots, the warps exchange progress counters in shared
+//     memory (stagers publish with release, the folder reads the counter one block ahead of its use, so no memory
+//     latency sits on the chain), tokens are fetched TR blocks ahead with cp.async;
+//   * key = sum_i e_i * P^(m - i) + P^m * H0: the per-position constants are table entries indexed by (stream length -
+//     position), looked up by the stager; the offset-basis term rides on position 0, whose byte (0x83) and therefore
+//     e_0 = 129 are constant: c_0' = P^m * (1 + H0 * 129^-1).  Nothing is multiplied after the warp reduction;
+//   * the 64-bit warp sum is three REDUX instead of four: low words mod 2^32, the EXACT sum of their upper halves
+//     (21 bits, which recovers the carry), high words mod 2^32;
+//   * one staged block is ONE 32 B record per lane (two 128-bit shared loads for the folder);
+//   * MERGED (A/B): bits 0 and 1 of every z byte without a vote.  Mod 4, x -> 0xb3 * x is the GF(2)-linear map
+//     (z1, z0) -> (z1 ^ z0, z0), so bits 0/1 of the running low byte are XOR prefixes of bits 0/1 of the stream; the
+//     stager resolves them for the stream with the parent bytes ZEROED (six ballots, off the chain) and the folder adds
+//     the parent's contribution with two 64-bit masks per position and one popcount each: six vote rounds instead of
+//     eight, at the price of more instructions in both warps.
+// A lone in-order warp retires about one instruction per three cycles (profiles/r02_hash_phase_v2.txt), so the
+// folder's INSTRUCTION COUNT is on the chain as much as its dependency depth: everything that does not depend on the
+// parent key is done by the stagers.  The arithmetic is restated on the CPU in tests/test_wpc_math.py.
+constexpr int kV2Slots = 4;    // staged blocks the stagers may run ahead
 constexpr int kV2TokRing = 8;  // token blocks in flight (cp.async commit groups), power of two
+constexpr uint64_t kInv129 = inv_mod_2_64(129);
+static_assert(kInv129 * 129ull == 1ull, "129^-1 mod 2^64");
+constexpr uint64_t kBasisOnPos0 = 1ull + kFnvOffset * kInv129;  // c_0' = P^m * kBasisOnPos0
 
 __device__ __forceinline__ int ld_acquire_cta(const int* p) {
   int v;
@@ -669,77 +680,71 @@ __device__ __forceinline__ void st_release_cta(int* p, int v) {
   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-template <int BS>
-__global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __restrict__ tokens,
-                                                           const int64_t* __restrict__ prompt_off,
-                                                           const uint64_t* __restrict__ parents,
-                                                           const uint8_t* __restrict__ extra,
-                                                           const int64_t* __restrict__ extra_off,
-                                                           uint64_t* __restrict__ out_keys,
-                                                           const int64_t* __restrict__ key_off) {
+template <int BS, int NST, bool MERGED, bool SCORE>
+__global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel(const ChainArgs A) {
   static_assert(BS > 0 && BS < 24 && kWpcPrefix + 5 * BS + 1 <= kWpcPositions, "stream must fit 96 positions");
+  static_assert(NST == 1 || NST == 2, "one or two stager warps");
   constexpr uint32_t kFull = 0xffffffffu;
-  constexpr int S = kV2Slots, TR = kV2TokRing;
-  // per staged block: bw = the lane's 3 stream bytes (parent bytes zero) with the static z bits 0/1 of the three positions
-  // in bits 24..29; cq = {lo, hi'} of P^(m - position) for the lane's three positions; meta = {P^m * H0, bytes after
-  // the prefix, nil-extra flag}; raw = the token bytes for the byte-serial fallback
-  __shared__ uint32_t bw[S][32];
-  __shared__ uint2 cq[S][3][32];
+  constexpr int S = kV2Slots, TR = kV2TokRing, NT = 32 * (1 + NST + (SCORE ? 1 : 0));
+  constexpr int kKeyRing = 64;
+  // per staged block and lane: {w, c0.lo, c0.hi', c1.lo} {c1.hi', c2.lo, c2.hi', n_tot | text << 31}; w = the lane's 3
+  // stream bytes (parent bytes zero) [+ static z bits 0/1 in bits 24..29 when MERGED]; c_j = P^(m - position), split for
+  // signed 32 x 32 products; raw = the token bytes for the byte-serial fallback
+  __shared__ uint4 rec[S][2][32];
   __shared__ uint8_t raw[S][kWpcPositions];
-  __shared__ uint4 meta[S];
   __shared__ uint32_t tring[TR][BS];
   __shared__ uint64_t pw[kWpcPositions + 1];  // P^t
-  __shared__ uint32_t slot_id[2];
-  __shared__ int staged, folded;  // blocks published by the stager / consumed by the folder
-  const int lane = threadIdx.x & 31;
+  __shared__ int staged, folded, scored;      // blocks published by the stagers / folded / consumed by the scorer
+  __shared__ uint64_t skeys[SCORE ? kKeyRing : 1];
+  __shared__ Bucket tile[SCORE ? 32 : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x;
-  const int64_t t0 = prompt_off[p];
-  const int nblk = (int)((prompt_off[p + 1] - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
-  if (nblk == 0) return;
-  const int64_t k0 = key_off[p];
-  for (int t = threadIdx.x; t <= kWpcPositions; t += 64) pw[t] = pow_u64(kFnvPrime, (uint32_t)t);
+  const int64_t t0 = A.prompt_off[p];
+  const int nblk = (int)((A.prompt_off[p + 1] - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
+  if (nblk == 0) {
+    if (SCORE && threadIdx.x == 0) A.out_n[p] = 0;
+    return;
+  }
+  const int64_t k0 = A.key_off[p];
+  for (int t = threadIdx.x; t <= kWpcPositions; t += NT) pw[t] = pow_u64(kFnvPrime, (uint32_t)t);
   if (threadIdx.x == 0) {
     staged = 0;
     folded = 0;
+    scored = 0;
   }
-  if (lane == 0) {  // which warp folds: see hash_chain_kernel_wpc
-    uint32_t wid;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-    slot_id[threadIdx.x >> 5] = wid;
-  }
-  __syncthreads();  // the only CTA barrier: publishes pw[], the counters and the slot ids
-  const uint32_t sa = slot_id[0], sb = slot_id[1];
-  const bool fa = ((sa >> 2) & 1u) == (sa & 1u), fb = ((sb >> 2) & 1u) == (sb & 1u);
-  const int folder_warp = (fa != fb) ? (fa ? 0 : 1) : 1;
-  const bool stager = (int)(threadIdx.x >> 5) != folder_warp;
+  __syncthreads();  // the only CTA barrier: publishes pw[] and the counters
   const uint32_t lt = (1u << lane) - 1u, self = 1u << lane;
 
-  if (stager) {
-    // lanes whose slot-j' position is <= / < this lane's position j, the latter restricted to the opposite position
-    // parity (position 3L + j has parity (L + j) & 1): masks over the six ballots
-    uint32_t le[3][3], lso[3][3];
+  if (warp >= 1 && warp <= NST) {
+    // ------------------------------------------------------------------------------------------------ stager
+    uint32_t le[3][3], lso[3][3];  // MERGED: lanes whose slot-j' position is <= / < (opposite parity) position j
+    if (MERGED) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
-      for (int jp = 0; jp < 3; ++jp) {
-        le[j][jp] = lt | (jp <= j ? self : 0u);
-        const uint32_t opp = ((3 * lane + j + jp) & 1) ? 0x55555555u : 0xaaaaaaaau;
-        lso[j][jp] = (lt | (jp < j ? self : 0u)) & opp;
-      }
+        for (int jp = 0; jp < 3; ++jp) {
+          le[j][jp] = lt | (jp <= j ? self : 0u);
+          const uint32_t opp = ((3 * lane + j + jp) & 1) ? 0x55555555u : 0xaaaaaaaau;  // position 3L+j has parity (L+j)&1
+          lso[j][jp] = (lt | (jp < j ? self : 0u)) & opp;
+        }
+    }
     constexpr uint32_t l00 = (uint32_t)(kFnvOffset & 1u), l01 = (uint32_t)((kFnvOffset >> 1) & 1u);
+    const uint32_t* tk = A.tokens + t0;
     auto fetch_tokens = [&](int i) {  // one commit group per block, empty past the end so the group count stays uniform
       if (lane < BS && i < nblk) {
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[i & (TR - 1)][lane]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(tokens + t0 + (int64_t)i * BS + lane));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(tk + (int64_t)i * BS + lane));
       }
       asm volatile("cp.async.commit_group;");
     };
+    constexpr int TRW = TR / NST;  // token blocks this stager keeps in flight
+    const int first = warp - 1;
 #pragma unroll
-    for (int i = 0; i < TR - 1; ++i) fetch_tokens(i);
-    int buf = 0;
-    for (int i = 0; i < nblk; ++i) {
-      fetch_tokens(i + TR - 1);
-      asm volatile("cp.async.wait_group %0;" ::"n"(TR - 1) : "memory");  // all but the newest TR-1 groups: block i landed
+    for (int q = 0; q < TRW - 1; ++q) fetch_tokens(first + q * NST);
+    for (int i = first; i < nblk; i += NST) {
+      const int buf = i % S;
+      fetch_tokens(i + (TRW - 1) * NST);
+      asm volatile("cp.async.wait_group %0;" ::"n"(TRW - 1) : "memory");  // all but the newest TRW-1 groups: block i landed
       if (i >= S)
         while (ld_acquire_cta(&folded) < i - S + 1) {
         }  // the slot's previous block has been consumed
@@ -753,10 +758,10 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
       const int off = lane + __popc(v24 & lt) + __popc(v256 & lt) + 2 * __popc(v64k & lt);
       const int n_tok = BS + __popc(v24) + __popc(v256) + 2 * __popc(v64k);
       bool text = true;
-      if (extra_off != nullptr) text = extra_off[k0 + i + 1] <= extra_off[k0 + i];
+      if (A.extra_off != nullptr) text = A.extra_off[k0 + i + 1] <= A.extra_off[k0 + i];
       {  // exactly w bytes per token; lane BS appends f6 for a nil extra; predicated stores, no divergent branches
         const uint32_t d = (uint32_t)__cvta_generic_to_shared(raw[buf]) + (lane < BS ? off : n_tok);
-        const uint32_t first = lane < BS ? head : 0xf6u;
+        const uint32_t first_b = lane < BS ? head : 0xf6u;
         const int nst = lane < BS ? w : ((lane == BS && text) ? 1 : 0);
         asm volatile(
             "{\n\t.reg .pred p1, p2, p3, p4;\n\t"
@@ -764,7 +769,7 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
             "@p1 st.shared.u8 [%0], %1;\n\t@p2 st.shared.u8 [%0+1], %3;\n\t@p3 st.shared.u8 [%0+2], %4;\n\t"
             "@p4 st.shared.u8 [%0+3], %5;\n\t@p4 st.shared.u8 [%0+4], %6;\n\t}"
             :
-            : "r"(d), "r"(first), "r"(nst), "r"(pay >> 24), "r"((pay >> 16) & 0xffu), "r"((pay >> 8) & 0xffu), "r"(pay & 0xffu)
+            : "r"(d), "r"(first_b), "r"(nst), "r"(pay >> 24), "r"((pay >> 16) & 0xffu), "r"((pay >> 8) & 0xffu), "r"(pay & 0xffu)
             : "memory");
       }
       __syncwarp();
@@ -778,50 +783,68 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
         const uint32_t byte = (idx >= 0 && idx < n_tot) ? ld : fixed;
         word |= byte << (8 * j);
       }
-      // (a) static bits 0/1 of z at this lane's three positions, parent bytes taken as zero
-      uint32_t v0[3], v1[3];
+      if (MERGED) {  // static bits 0/1 of z at this lane's three positions, parent bytes taken as zero
+        uint32_t v0[3], v1[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        v0[j] = __ballot_sync(kFull, (word >> (8 * j)) & 1u);
-        v1[j] = __ballot_sync(kFull, (word >> (8 * j + 1)) & 1u);
-      }
+        for (int j = 0; j < 3; ++j) {
+          v0[j] = __ballot_sync(kFull, (word >> (8 * j)) & 1u);
+          v1[j] = __ballot_sync(kFull, (word >> (8 * j + 1)) & 1u);
+        }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const uint32_t x0 = (v0[0] & le[j][0]) ^ (v0[1] & le[j][1]) ^ (v0[2] & le[j][2]);
-        const uint32_t x1 = (v1[0] & le[j][0]) ^ (v1[1] & le[j][1]) ^ (v1[2] & le[j][2]);
-        const uint32_t xa = (v0[0] & lso[j][0]) ^ (v0[1] & lso[j][1]) ^ (v0[2] & lso[j][2]);
-        const uint32_t z0 = (l00 ^ (uint32_t)__popc(x0)) & 1u;
-        const uint32_t z1 = (l01 ^ (((3 * lane + j) & 1) ? l00 : 0u) ^ (uint32_t)(__popc(x1) + __popc(xa))) & 1u;
-        word |= (z0 | (z1 << 1)) << (24 + 2 * j);
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t x0 = (v0[0] & le[j][0]) ^ (v0[1] & le[j][1]) ^ (v0[2] & le[j][2]);
+          const uint32_t x1 = (v1[0] & le[j][0]) ^ (v1[1] & le[j][1]) ^ (v1[2] & le[j][2]);
+          const uint32_t xa = (v0[0] & lso[j][0]) ^ (v0[1] & lso[j][1]) ^ (v0[2] & lso[j][2]);
+          const uint32_t z0 = (l00 ^ (uint32_t)__popc(x0)) & 1u;
+          const uint32_t z1 = (l01 ^ (((3 * lane + j) & 1) ? l00 : 0u) ^ (uint32_t)(__popc(x1) + __popc(xa))) & 1u;
+          word |= (z0 | (z1 << 1)) << (24 + 2 * j);
+        }
       }
-      bw[buf][lane] = word;
-      // (b) per-position constants P^(m - position), split for the signed 32 x 32 products of the folder
+      // per-position constants P^(m - position); position 0 also carries the offset-basis term
       const int m = kWpcPrefix + n_tot;
+      uint32_t clo[3], chi[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int d = m - (3 * lane + j);
-        const uint64_t c = pw[d < 0 ? 0 : d];
-        const int32_t clo = (int32_t)(uint32_t)c;  // c = (chi + [clo < 0]) * 2^32 + (signed) clo
-        cq[buf][j][lane] = make_uint2((uint32_t)clo, (uint32_t)(c >> 32) + (clo < 0 ? 1u : 0u));
+        uint64_t c = pw[d < 0 ? 0 : d];
+        if (j == 0 && lane == 0) c *= kBasisOnPos0;
+        const int32_t lo = (int32_t)(uint32_t)c;  // c = (hi' ) * 2^32 + (signed) lo with hi' = hi + [lo < 0]
+        clo[j] = (uint32_t)lo;
+        chi[j] = (uint32_t)(c >> 32) + (lo < 0 ? 1u : 0u);
       }
-      if (lane == 0) {
-        const uint64_t pmh = pw[m] * kFnvOffset;
-        meta[buf] = make_uint4((uint32_t)pmh, (uint32_t)(pmh >> 32), (uint32_t)n_tot, text ? 1u : 0u);
-      }
+      rec[buf][0][lane] = make_uint4(word, clo[0], chi[0], clo[1]);
+      rec[buf][1][lane] = make_uint4(chi[1], clo[2], chi[2], (uint32_t)n_tot | (text ? 0x80000000u : 0u));
       __syncwarp();
+      if (NST > 1)
+        while (ld_acquire_cta(&staged) < i) {
+        }  // blocks are published in order
       if (lane == 0) st_release_cta(&staged, i + 1);
-      buf = buf == S - 1 ? 0 : buf + 1;
     }
     return;
   }
 
-  // ---- folder
-  // where the parent's bytes land in this lane's word (stream position 2 + k carries parent byte 7 - k), and the masks
-  // that give the parent's contribution to bits 0/1 of z at the lane's three positions:
-  //   z0 ^= parity(parent & mle),  z1 ^= parity(parent & ((mle << 1) | mopp))
-  // mle = bit 0 of the parent bytes at positions <= i, mopp = bit 0 of those at positions < i of the opposite parity
+  if (SCORE && warp == 1 + NST) {
+    // ------------------------------------------------------------------------------------------------ scorer
+    ScoreWalker wk;
+    for (int base = 0; base < nblk; base += 32) {
+      const int in_tile = min(32, nblk - base);
+      while (ld_acquire_cta(&folded) < base + in_tile) {
+      }
+      const uint64_t key = lane < in_tile ? skeys[(base + lane) & (kKeyRing - 1)] : 0ull;
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(&scored) = base + in_tile;  // the ring slots may be reused
+      if (!wk.chain_alive && A.ts == nullptr) continue;  // nothing left to add and nothing to stamp
+      wk.tile(A.table, A.mask, tile, key, lane < in_tile, base, in_tile, A.filter_bits, A.tier_w, A.ts,
+              A.stamp_base + (unsigned long long)(k0 + base + lane));
+    }
+    wk.finish(p, A.out_n, A.out_pods, A.out_scores);
+    return;
+  }
+
+  // -------------------------------------------------------------------------------------------------- folder
+  // where the parent's bytes land in this lane's word (stream position 2 + k carries parent byte 7 - k)
   uint32_t psel = 0, pmask = 0;
-  uint32_t m0lo[3], m0hi[3], m1lo[3], m1hi[3];
+  uint32_t m0lo[3], m0hi[3], m1lo[3], m1hi[3];  // MERGED: z0 ^= parity(parent & m0), z1 ^= parity(parent & m1)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int pos = 3 * lane + j;
@@ -829,6 +852,8 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
       psel |= (uint32_t)(9 - pos) << (4 * j);
       pmask |= 0xffu << (8 * j);
     }
+    // m0 = bit 0 of the parent bytes at positions <= pos; m1 = their bit 1, plus bit 0 of those at positions < pos of
+    // the opposite position parity (the cross term of the mod-4 map)
     uint64_t mle = 0, mopp = 0;
     for (int q = 2; q <= 9; ++q) {
       if (q <= pos) mle |= 1ull << (8 * (9 - q));
@@ -840,42 +865,68 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
     m1lo[j] = (uint32_t)m1;
     m1hi[j] = (uint32_t)(m1 >> 32);
   }
-  uint64_t parent = parents[p];
-  while (ld_acquire_cta(&staged) < 1) {
+#ifdef KVB_HASH_PROFILE
+  // clock reads that cannot issue before `dep` is ready: they sit ON the dependent chain, like the next real instruction
+  long long vp[6] = {0, 0, 0, 0, 0, 0};  // top (check + loads) | prefix / bits 0,1 | rounds | reduce | tail
+  auto clk = [](uint32_t dep) {
+    long long t;
+    asm volatile("{\n\t.reg .b32 d;\n\tmov.b32 d, %1;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+  };
+#define VPROF(slot, t_begin, dep)  \
+  {                                \
+    const long long _n = clk(dep); \
+    vp[slot] += _n - (t_begin);    \
+    (t_begin) = _n;                \
   }
-  uint32_t w_cur = bw[0][lane];
-  uint2 c_cur[3] = {cq[0][0][lane], cq[0][1][lane], cq[0][2][lane]};
-  uint4 m_cur = meta[0];
-  int cbuf = 0, nbuf = 1;
+#else
+#define VPROF(slot, t_begin, dep)
+#endif
+  uint64_t parent = A.parents[p];
+  int seen = 0;  // last value read from `staged`: the stagers run ahead, so the check below rarely has to look again
+  while ((seen = ld_acquire_cta(&staged)) < 1) {
+  }
+  uint4 ra = rec[0][0][lane], rb = rec[0][1][lane];
+  int cbuf = 0, nbuf = 1, scored_seen = 0;
+#ifdef KVB_HASH_PROFILE
+  long long tb = clk((uint32_t)parent);
+#endif
   for (int i = 0; i < nblk; ++i) {
-    uint32_t w_nxt = 0;
-    uint2 c_nxt[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
-    uint4 m_nxt = make_uint4(0, 0, 0, 1);
-    if (i + 1 < nblk) {  // normally published long ago: the stager runs up to S blocks ahead
-      while (ld_acquire_cta(&staged) < i + 2) {
-      }
-      w_nxt = bw[nbuf][lane];
-      c_nxt[0] = cq[nbuf][0][lane];
-      c_nxt[1] = cq[nbuf][1][lane];
-      c_nxt[2] = cq[nbuf][2][lane];
-      m_nxt = meta[nbuf];
+    uint4 ra_n = make_uint4(0, 0, 0, 0), rb_n = make_uint4(0, 0, 0, 0x80000000u);
+    int seen_nxt = seen;
+    if (i + 1 < nblk) {
+      // block i + 1 was normally published long ago and `seen` (read an iteration ago) already says so: the compare is
+      // on a register, the loads are issued at once and consumed only when the next block starts
+      while (seen < i + 2) seen = ld_acquire_cta(&staged);
+      ra_n = rec[nbuf][0][lane];
+      rb_n = rec[nbuf][1][lane];
+      seen_nxt = *reinterpret_cast<volatile int*>(&staged);  // for the next iteration's check; not waited for here
     }
+    VPROF(0, tb, (uint32_t)parent);
+    const uint32_t w_cur = ra.x;
     uint64_t key;
     if (parent >= 0x100000000ull) {
       const uint32_t klo = (uint32_t)parent, khi = (uint32_t)(parent >> 32);
       const uint32_t w = (w_cur & 0x00ffffffu) | (__byte_perm(klo, khi, psel) & pmask);
       const uint32_t b0 = __byte_perm(w, 0u, 0x4440u), b1 = __byte_perm(w, 0u, 0x4441u), b2 = __byte_perm(w, 0u, 0x4442u);
-      // bits 0/1: static part from the stager, parent part from two masked popcounts per position — no vote
-      const uint32_t q00 = (uint32_t)__popc((klo & m0lo[0]) ^ (khi & m0hi[0])), q10 = (uint32_t)__popc((klo & m1lo[0]) ^ (khi & m1hi[0]));
-      const uint32_t q01 = (uint32_t)__popc((klo & m0lo[1]) ^ (khi & m0hi[1])), q11 = (uint32_t)__popc((klo & m1lo[1]) ^ (khi & m1hi[1]));
-      const uint32_t q02 = (uint32_t)__popc((klo & m0lo[2]) ^ (khi & m0hi[2])), q12 = (uint32_t)__popc((klo & m1lo[2]) ^ (khi & m1hi[2]));
-      const uint32_t s0 = w_cur >> 24, s1 = w_cur >> 26, s2 = w_cur >> 28;
-      uint32_t z0 = (b0 & 0xfcu) | ((s0 ^ (q00 & 1u) ^ ((q10 & 1u) << 1)) & 3u);
-      uint32_t z1 = (b1 & 0xfcu) | ((s1 ^ (q01 & 1u) ^ ((q11 & 1u) << 1)) & 3u);
-      uint32_t z2 = (b2 & 0xfcu) | ((s2 ^ (q02 & 1u) ^ ((q12 & 1u) << 1)) & 3u);
-      // bits 2..7: the dependent rounds (IMAD -> LOP3 -> LOP3.P -> VOTE -> LOP3 -> POPC -> SHL -> LOP3 each)
+      uint32_t z0, z1, z2;
+      if (MERGED) {  // bits 0/1: static part from the stager, parent part from two masked popcounts per position
+        const uint32_t q00 = (uint32_t)__popc((klo & m0lo[0]) ^ (khi & m0hi[0])), q10 = (uint32_t)__popc((klo & m1lo[0]) ^ (khi & m1hi[0]));
+        const uint32_t q01 = (uint32_t)__popc((klo & m0lo[1]) ^ (khi & m0hi[1])), q11 = (uint32_t)__popc((klo & m1lo[1]) ^ (khi & m1hi[1]));
+        const uint32_t q02 = (uint32_t)__popc((klo & m0lo[2]) ^ (khi & m0hi[2])), q12 = (uint32_t)__popc((klo & m1lo[2]) ^ (khi & m1hi[2]));
+        const uint32_t s0 = w_cur >> 24, s1 = w_cur >> 26, s2 = w_cur >> 28;
+        z0 = (b0 & 0xfcu) | ((s0 ^ (q00 & 1u) ^ ((q10 & 1u) << 1)) & 3u);
+        z1 = (b1 & 0xfcu) | ((s1 ^ (q01 & 1u) ^ ((q11 & 1u) << 1)) & 3u);
+        z2 = (b2 & 0xfcu) | ((s2 ^ (q02 & 1u) ^ ((q12 & 1u) << 1)) & 3u);
+      } else {  // z starts as b: bit k of z * 0xb3 is then exactly b_k ^ c_k
+        z0 = b0;
+        z1 = b1;
+        z2 = b2;
+      }
+      VPROF(1, tb, z0 ^ z1 ^ z2);
+      // the dependent rounds (IMAD -> LOP3 -> LOP3.P -> VOTE -> LOP3 -> POPC -> SHL -> LOP3 each)
 #pragma unroll
-      for (int k = 2; k < 8; ++k) {
+      for (int k = MERGED ? 2 : 0; k < 8; ++k) {
         constexpr uint32_t kL0 = (uint32_t)(kFnvOffset & 0xffu);
         const uint32_t mask = 1u << k;
         const uint32_t p0 = z0 * 0xb3u, p1 = z1 * 0xb3u, p2 = z2 * 0xb3u;
@@ -893,17 +944,16 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
         asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z1) : "r"(zc1), "r"(sh), "r"(mask));
         asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(z2) : "r"(zc2), "r"(sh), "r"(mask));
       }
-      // e = z - l with l = z ^ b;  key = P^m * H0 + sum_i e_i * P^(m - i)
+      VPROF(2, tb, z0 ^ z1 ^ z2);
+      // e = z - l with l = z ^ b;  key = sum_i e_i * c_i (the offset-basis term rides on position 0)
       const int32_t e0 = (int32_t)z0 - (int32_t)(z0 ^ b0), e1 = (int32_t)z1 - (int32_t)(z1 ^ b1),
                     e2 = (int32_t)z2 - (int32_t)(z2 ^ b2);
       int64_t acc;  // three signed IMAD.WIDE
       asm("{\n\t.reg .s64 t;\n\tmul.wide.s32 t, %1, %2;\n\tmad.wide.s32 t, %3, %4, t;\n\tmad.wide.s32 %0, %5, %6, t;\n\t}"
           : "=l"(acc)
-          : "r"(e0), "r"((int32_t)c_cur[0].x), "r"(e1), "r"((int32_t)c_cur[1].x), "r"(e2), "r"((int32_t)c_cur[2].x));
-      const uint32_t hi = (uint32_t)e0 * c_cur[0].y + (uint32_t)e1 * c_cur[1].y + (uint32_t)e2 * c_cur[2].y;
-      const uint64_t pmh = ((uint64_t)m_cur.y << 32) | m_cur.x;
-      const uint64_t tl = (uint64_t)acc + ((uint64_t)hi << 32) + (lane == 0 ? pmh : 0ull);
-      const uint32_t tlo = (uint32_t)tl, thi = (uint32_t)(tl >> 32);
+          : "r"(e0), "r"((int32_t)ra.y), "r"(e1), "r"((int32_t)ra.w), "r"(e2), "r"((int32_t)rb.y));
+      const uint32_t hi = (uint32_t)e0 * ra.z + (uint32_t)e1 * rb.x + (uint32_t)e2 * rb.z;
+      const uint32_t tlo = (uint32_t)acc, thi = (uint32_t)((uint64_t)acc >> 32) + hi;
       const uint32_t r1 = __reduce_add_sync(kFull, tlo), r2 = __reduce_add_sync(kFull, tlo >> 16),
                      r3 = __reduce_add_sync(kFull, thi);
       const uint32_t a = r2 << 16;  // exact low sum = (r2 << 16) + B with B < 2^21, and its low word is r1
@@ -913,31 +963,74 @@ __global__ void __launch_bounds__(64) hash_chain_kernel_v2(const uint32_t* __res
       Fnv h = fnv_init();
       fold_prefix(h, parent, (uint32_t)BS);
       const uint8_t* src = raw[cbuf];
-      const int n_cur = (int)m_cur.z;
+      const int n_cur = (int)(rb.w & 0x7fffffffu);
       for (int k = 0; k < n_cur; ++k) fold(h, src[k]);
       key = fnv_value(h);
     }
-    if (!m_cur.w) {  // pre-encoded X(extra_i) follows the tokens (extra_keys.go)
+    if (!(rb.w & 0x80000000u)) {  // pre-encoded X(extra_i) follows the tokens (extra_keys.go)
       Fnv h{(uint32_t)key, (uint32_t)(key >> 32)};
-      for (int64_t e = extra_off[k0 + i]; e < extra_off[k0 + i + 1]; ++e) fold(h, extra[e]);
+      for (int64_t e = A.extra_off[k0 + i]; e < A.extra_off[k0 + i + 1]; ++e) fold(h, A.extra[e]);
       key = fnv_value(h);
     }
+    VPROF(3, tb, (uint32_t)key ^ (uint32_t)(key >> 32));
+    if (SCORE) {  // the key ring is 64 deep and the scorer consumes 32 at a time: it is normally far ahead of this check
+      while (i - scored_seen >= kKeyRing) scored_seen = ld_acquire_cta(&scored);
+    }
     if (lane == 0) {
-      // slot i may be restaged: its words are in registers and raw[] has been read — every value the key depends on has
+      if (SCORE) skeys[i & (kKeyRing - 1)] = key;
+      // slot i may be restaged: its record is in registers and raw[] has been read — every value the key depends on has
       // arrived, so a relaxed store is enough (a release here would put a MEMBAR, and the wait for the global store
-      // below, on the chain)
+      // below, on the chain).  The scorer reads `folded` with acquire after the key store above (same thread, in order).
+      if (SCORE) __threadfence_block();
       *reinterpret_cast<volatile int*>(&folded) = i + 1;
-      out_keys[k0 + i] = key;
+      if (A.out_keys != nullptr) A.out_keys[k0 + i] = key;
     }
     parent = key;
-    w_cur = w_nxt;
-    c_cur[0] = c_nxt[0];
-    c_cur[1] = c_nxt[1];
-    c_cur[2] = c_nxt[2];
-    m_cur = m_nxt;
+    ra = ra_n;
+    rb = rb_n;
+    seen = seen_nxt > seen ? seen_nxt : seen;
+    if (SCORE) {
+      const int sc = *reinterpret_cast<volatile int*>(&scored);
+      scored_seen = sc > scored_seen ? sc : scored_seen;
+    }
     cbuf = nbuf;
     nbuf = nbuf == S - 1 ? 0 : nbuf + 1;
+    VPROF(4, tb, (uint32_t)parent);
   }
+#ifdef KVB_HASH_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    for (int q = 0; q < 5; ++q) g_hash_prof[5 + q] = vp[q];
+    g_hash_prof[10] = nblk;
+  }
+#endif
+#undef VPROF
+}
+
+template <int BS, bool SCORE>
+static void launch_chain_bs(const ChainArgs& a, int n_prompts, cudaStream_t s) {
+  // A/B switches (read per call): stager warps per chain, merged first two bits
+  const char* e1 = std::getenv("KVB_HASH_STAGERS");
+  const char* e2 = std::getenv("KVB_HASH_MERGED");
+  const int nst = e1 ? std::atoi(e1) : 1;
+  const bool merged = e2 ? std::atoi(e2) != 0 : false;
+  const int threads = 32 * (1 + nst + (SCORE ? 1 : 0));
+  if (nst == 2 && merged) chain_kernel<BS, 2, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  else if (nst == 2) chain_kernel<BS, 2, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  else if (merged) chain_kernel<BS, 1, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  else chain_kernel<BS, 1, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
+}
+
+static bool chain_kernel_supports(int32_t block_size) { return block_size == 16 || block_size == 8 || block_size == 4; }
+
+// fused tokens -> keys -> lookup -> scores, one launch (kvb_index_score_tokens_batch); false if this block size has no
+// chain kernel (the caller then hashes and scores with two launches)
+bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, cudaStream_t s) {
+  if (!chain_kernel_supports(block_size)) return false;
+  if (block_size == 16) launch_chain_bs<16, true>(a, n_prompts, s);
+  else if (block_size == 8) launch_chain_bs<8, true>(a, n_prompts, s);
+  else launch_chain_bs<4, true>(a, n_prompts, s);
+  count_launch();
+  return true;
 }
 
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
@@ -965,14 +1058,20 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   const char* force = std::getenv("KVB_HASH_KERNEL");
   const bool lanes_only = force != nullptr && std::strcmp(force, "lanes") == 0;
   const bool wpc_v1 = force != nullptr && std::strcmp(force, "wpc") == 0;  // round-1 warp kernel, kept for A/B
-  if (!one_warp && !lanes_only && !wpc_v1 && n_prompts <= kWpcMaxPrompts &&
-      (block_size == 16 || block_size == 8 || block_size == 4)) {
-    if (block_size == 16)
-      hash_chain_kernel_v2<16><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
-    else if (block_size == 8)
-      hash_chain_kernel_v2<8><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
-    else
-      hash_chain_kernel_v2<4><<<n_prompts, 64, 0, s>>>(tokens, prompt_off, parents, extra, extra_off, out_keys, key_off);
+  const char* want_chain = std::getenv("KVB_HASH_CHAIN_MAX");  // largest batch for the round-2 chain kernel (A/B)
+  const int chain_max = want_chain ? std::atoi(want_chain) : kChainMaxPrompts;
+  if (!one_warp && !lanes_only && !wpc_v1 && n_prompts <= chain_max && chain_kernel_supports(block_size)) {
+    ChainArgs a{};
+    a.tokens = tokens;
+    a.prompt_off = prompt_off;
+    a.parents = parents;
+    a.extra = extra;
+    a.extra_off = extra_off;
+    a.out_keys = out_keys;
+    a.key_off = key_off;
+    if (block_size == 16) launch_chain_bs<16, false>(a, n_prompts, s);
+    else if (block_size == 8) launch_chain_bs<8, false>(a, n_prompts, s);
+    else launch_chain_bs<4, false>(a, n_prompts, s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("hash kernel launch failed: %s", cudaGetErrorString(e));

@@ -49,18 +49,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include "index_device.cuh"
+
 namespace kvb {
-
-constexpr int kMaxEnt = KVB_INDEX_MAX_PODS_PER_KEY;  // 13
-constexpr uint32_t kEmpty = 0, kFull = 1, kTomb = 2, kBusy = 3;
-constexpr uint32_t kNoSlot = 0xffffffffu;
-
-struct __align__(64) Bucket {
-  uint64_t key;
-  uint32_t meta;  // bits 0-1 state, bits 8-15 entry count
-  uint32_t ent[kMaxEnt];
-};
-static_assert(sizeof(Bucket) == 64, "bucket must be one 64 B line");
 
 constexpr uint8_t kOpAdd = 0, kOpEvict = 1;
 struct OpRec {  // one queued mutation of one request key
@@ -84,17 +75,6 @@ struct TableRef {
   int ppk;
 };
 
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {  // murmur3 fmix64
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return k;
-}
-__host__ __device__ __forceinline__ uint32_t pack_entry(uint16_t pod, uint8_t tier, uint8_t spec) {
-  return (uint32_t)pod | ((uint32_t)tier << 16) | ((uint32_t)(spec ? 1 : 0) << 24);
-}
 KVB_DEV __forceinline__ uint32_t ld_meta(const Bucket* b) {
   return *reinterpret_cast<const volatile uint32_t*>(&b->meta);
 }
@@ -374,20 +354,6 @@ __global__ void index_collect_order_kernel(TableRef t, unsigned long long* __res
   }
 }
 
-__device__ __host__ __forceinline__ int64_t probe(const Bucket* __restrict__ table, uint64_t mask, uint64_t key) {
-  uint64_t slot = mix64(key) & mask;
-  for (uint64_t probes = 0; probes <= mask; ++probes, slot = (slot + 1) & mask) {
-    const uint32_t st = table[slot].meta & 3u;
-    if (st == kEmpty) return -1;
-    if (st == kFull && table[slot].key == key) return (int64_t)slot;
-  }
-  return -1;
-}
-
-__device__ __host__ __forceinline__ bool pod_allowed(const uint32_t* __restrict__ filter_bits, uint32_t pod) {
-  return filter_bits == nullptr || ((filter_bits[pod >> 5] >> (pod & 31)) & 1u);
-}
-
 // Lookup: one thread per key.  counts: -1 absent, -2 present but empty, else #entries after the pod filter.
 // stamp_base != 0: found keys are re-stamped (data.Get, in_memory.go:120) with stamp_base + position.
 __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t mask, const uint64_t* __restrict__ keys,
@@ -417,7 +383,8 @@ __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t m
 }
 
 #ifndef KVB_HOST_SIM
-// Score: one warp per prompt (4 warps per CTA).
+// Score: one warp per prompt (4 warps per CTA); the walk itself is ScoreWalker (index_device.cuh), shared with the
+// fused tokens -> scores kernel of hash_kernels.cu.
 constexpr int kScoreWarps = 4;
 
 __global__ void __launch_bounds__(kScoreWarps * 32)
@@ -433,108 +400,15 @@ __global__ void __launch_bounds__(kScoreWarps * 32)
   if (p >= n_prompts) return;
   const int64_t k0 = key_off[p];
   const int64_t nk = key_off[p + 1] - k0;
-  const unsigned FULL = 0xffffffffu;
-
-  bool active = false;  // this lane owns a pod that is still on the consecutive prefix
-  bool owner = false;   // this lane owns a pod that appeared at key 0 (it is reported)
-  uint32_t my_pod = 0xffffffffu;
-  double score = 0.0;
-  bool chain_alive = true;
-
+  ScoreWalker wk;
   for (int64_t base = 0; base < nk; base += 32) {
-    if (!chain_alive && ts == nullptr) break;
-    // ---- phase A: 32 independent probes, buckets staged in shared memory
+    if (!wk.chain_alive && ts == nullptr) break;
     const int64_t ki = base + lane;
-    int64_t slot = -1;
-    if (ki < nk) slot = probe(table, mask, keys[k0 + ki]);
-    // Lookup walks EVERY key and data.Get refreshes each one it finds (in_memory.go:119-120): stamp in key order
-    if (ts != nullptr && slot >= 0) atomicMax(&ts[slot], stamp_base + (unsigned long long)(k0 + ki));
-    if (slot >= 0) {
-      const uint4* src = reinterpret_cast<const uint4*>(&table[slot]);
-      uint4* dst = reinterpret_cast<uint4*>(&tile[warp][lane]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = src[q];
-    }
-    __syncwarp();
-    if (!chain_alive) continue;
-    const int in_tile = (int)min((int64_t)32, nk - base);
-    // ---- phase B: serial walk over the tile's keys
-    for (int j = 0; j < in_tile; ++j) {
-      const int64_t sj = __shfl_sync(FULL, slot, j);
-      // bucket entries sit on lanes 16..28, the reported pods (owners) on lanes 0..12 in the order they appeared at
-      // key 0: ONE match.any per key pairs every owner with the entries that carry its pod
-      bool valid = false;
-      uint32_t pod = 0x10000u + lane;  // unique sentinel for lanes without a valid entry
-      double w = 0.0;
-      if (sj >= 0) {
-        const Bucket& b = tile[warp][j];
-        const int cnt = (int)((b.meta >> 8) & 0xff);
-        const int e = lane - 16;
-        if (e >= 0 && e < cnt && e < kMaxEnt) {
-          const uint32_t v = b.ent[e];
-          if (pod_allowed(filter_bits, v & 0xffffu)) {
-            valid = true;
-            pod = v & 0xffffu;
-            w = tier_w[(v >> 16) & 0xffu];
-          }
-        }
-      }
-      if (base + j == 0) {
-        // key 0: active set = distinct pods, weight = max over that pod's tiers (fillMaxWeights)
-        const unsigned group = __match_any_sync(FULL, pod) & 0x1fff0000u;  // entry lanes with this lane's pod
-        const bool leader = valid && (group & ((1u << lane) - 1u)) == 0u;   // first entry of its pod
-        double wmax = w;
-        unsigned rest = valid ? (group & ~(1u << lane)) : 0u;
-        while (__any_sync(FULL, rest != 0u)) {  // usually zero or one round: a pod on two tiers
-          const int src = rest ? __ffs((int)rest) - 1 : lane;
-          const double we = __shfl_sync(FULL, w, src);
-          if (rest) {
-            if (we > wmax) wmax = we;
-            rest &= rest - 1u;
-          }
-        }
-        const bool l2 = __shfl_down_sync(FULL, leader ? 1 : 0, 16) != 0;
-        const uint32_t p2 = __shfl_down_sync(FULL, pod, 16);
-        const double w2 = __shfl_down_sync(FULL, wmax, 16);
-        owner = active = lane < kMaxEnt && l2;
-        my_pod = owner ? p2 : 0xffffffffu;
-        score = owner ? w2 : 0.0;
-      } else {
-        const uint32_t val = lane < 16 ? (active ? my_pod : 0x20000u + lane) : pod;
-        unsigned em = __match_any_sync(FULL, val) >> 16;  // entry lanes (as bits 0..12) that carry my_pod
-        if (!(lane < 16 && active)) em = 0u;
-        const bool hit = em != 0u;
-        double wm = 0.0;
-        bool first = true;
-        while (__any_sync(FULL, em != 0u)) {
-          const int src = em ? 16 + __ffs((int)em) - 1 : lane;
-          const double we = __shfl_sync(FULL, w, src);
-          if (em) {
-            if (first || we > wm) wm = we;
-            first = false;
-            em &= em - 1u;
-          }
-        }
-        if (active) {
-          if (hit) score += wm;  // float64, key order: same sum as the Go loop
-          else active = false;
-        }
-      }
-      if (!__any_sync(FULL, active)) {
-        chain_alive = false;
-        break;
-      }
-    }
-    __syncwarp();
+    const uint64_t key = ki < nk ? keys[k0 + ki] : 0ull;
+    wk.tile(table, mask, tile[warp], key, ki < nk, base, (int)min((int64_t)32, nk - base), filter_bits, tier_w, ts,
+            stamp_base + (unsigned long long)(k0 + ki));
   }
-  // compact (pod, score) pairs of the owner lanes
-  const unsigned om = __ballot_sync(FULL, owner);
-  if (owner) {
-    const int pos = __popc(om & ((1u << lane) - 1u));
-    out_pods[(int64_t)p * kMaxEnt + pos] = (uint16_t)my_pod;
-    out_scores[(int64_t)p * kMaxEnt + pos] = score;
-  }
-  if (lane == 0) out_n[p] = __popc(om);
+  wk.finish(p, out_n, out_pods, out_scores);
 }
 #endif  // !KVB_HOST_SIM
 
@@ -1418,35 +1292,18 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     for (int32_t p = 0; p <= n_prompts; ++p) h_koff[p] = key_off[p] - key_off[0];
     if (total_keys > 0) std::memcpy(H + o_hkeys, keys_host + key_off[0], (size_t)total_keys * 8);
   }
-  // the filter bitmap was copied by set_filter already (only when it changed); everything else in one copy
-  const size_t small_end = (n_filter > 0) ? o_filt : in_end;
-  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_a, s));
-  KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, small_end - o_koff, cudaMemcpyHostToDevice, s));
-  const uint64_t* d_keys = reinterpret_cast<const uint64_t*>(D + (from_tokens ? o_keys : o_hkeys));
-  if (from_tokens && total_keys > 0) {
-    // tokens: pinned buffers are read by the copy engine in place, pageable ones are staged by the driver (measured
-    // faster than staging them here, tools/ab_stage.py)
-    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
-    rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
-                            reinterpret_cast<uint64_t*>(D + o_par), n_prompts, block_size,
-                            extra_off ? D + o_ext : nullptr,
-                            extra_off ? reinterpret_cast<int64_t*>(D + o_eoff) : nullptr,
-                            reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
-    if (rc) return rc;
-  }
-  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_b, s));
   // results land where the caller wants them when that memory is pinned (no D2H copy, no memcpy); otherwise in the
   // pinned staging block through its device alias
+  uint8_t* Hd = static_cast<uint8_t*>(device_alias(H));
+  if (!Hd) {
+    set_error("index: the pinned staging block has no device alias");
+    return KVB_ERR_CUDA;
+  }
   int32_t* k_n = static_cast<int32_t*>(device_alias(out_n));
   uint16_t* k_pods = static_cast<uint16_t*>(device_alias(out_pods));
   double* k_sc = static_cast<double*>(device_alias(out_scores));
   const bool direct_out = k_n && k_pods && k_sc;
   if (!direct_out) {
-    uint8_t* Hd = static_cast<uint8_t*>(device_alias(H));
-    if (!Hd) {
-      set_error("index: the pinned staging block has no device alias");
-      return KVB_ERR_CUDA;
-    }
     k_n = reinterpret_cast<int32_t*>(Hd + o_n);
     k_pods = reinterpret_cast<uint16_t*>(Hd + o_pods);
     k_sc = reinterpret_cast<double*>(Hd + o_sc);
@@ -1456,12 +1313,59 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     stamp_base = idx->seq;
     idx->seq += (unsigned long long)total_keys;
   }
-  const int64_t grid = ((int64_t)n_prompts + kScoreWarps - 1) / kScoreWarps;
-  index_score_kernel<<<(unsigned)grid, kScoreWarps * 32, 0, s>>>(
-      idx->table, idx->slots - 1, d_keys, reinterpret_cast<const int64_t*>(D + o_koff), n_prompts, filt, idx->tier_w,
-      k_n, k_pods, k_sc, touch ? idx->ts : nullptr, stamp_base);
-  KVB_CUDA_TRY(cudaGetLastError());
-  count_launch();
+  // the small arrays: one copy — or none at all for a handful of prompts, where the kernel reads the pinned staging
+  // block in place (one PCIe round trip instead of a copy operation ahead of the launch)
+  const bool small_in_place = from_tokens && n_prompts <= 64 && !extra_off && (flags & KVB_SCORE_COPY_TOKENS) == 0;
+  const uint8_t* Din = small_in_place ? Hd : D;  // where the kernels read koff / poff / parents
+  const size_t small_end = (n_filter > 0) ? o_filt : in_end;  // the filter bitmap was copied by set_filter (if it changed)
+  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_a, s));
+  if (!small_in_place)
+    KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, small_end - o_koff, cudaMemcpyHostToDevice, s));
+  const uint64_t* d_keys = reinterpret_cast<const uint64_t*>(D + (from_tokens ? o_keys : o_hkeys));
+  bool scored = false;
+  if (from_tokens && total_keys > 0) {
+    // tokens: pinned buffers (kvb_host_alloc / cudaHostAlloc / registered) are read IN PLACE by the stager warps — the
+    // PCIe transfer overlaps the hash chains instead of preceding them; pageable buffers are copied (staged by the driver)
+    const uint32_t* tok_dev = static_cast<const uint32_t*>(device_alias(tokens + prompt_off[0]));
+    if (tok_dev == nullptr || (flags & KVB_SCORE_COPY_TOKENS) != 0) {
+      KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
+      tok_dev = reinterpret_cast<const uint32_t*>(D + o_tok);
+    }
+    ChainArgs a{};
+    a.tokens = tok_dev;
+    a.prompt_off = reinterpret_cast<const int64_t*>(Din + o_poff);
+    a.parents = reinterpret_cast<const uint64_t*>(Din + o_par);
+    a.extra = extra_off ? D + o_ext : nullptr;
+    a.extra_off = extra_off ? reinterpret_cast<const int64_t*>(D + o_eoff) : nullptr;
+    a.out_keys = nullptr;
+    a.key_off = reinterpret_cast<const int64_t*>(Din + o_koff);
+    a.table = idx->table;
+    a.mask = idx->slots - 1;
+    a.filter_bits = filt;
+    a.tier_w = idx->tier_w;
+    a.out_n = k_n;
+    a.out_pods = k_pods;
+    a.out_scores = k_sc;
+    a.ts = touch ? idx->ts : nullptr;
+    a.stamp_base = stamp_base;
+    if (n_prompts <= 1536 && (flags & KVB_SCORE_TWO_KERNELS) == 0 && launch_chain_score(a, n_prompts, block_size, s)) {
+      KVB_CUDA_TRY(cudaGetLastError());
+      scored = true;  // ONE launch did tokens -> keys -> lookup -> scores
+    } else {
+      rc = launch_hash_blocks(tok_dev, a.prompt_off, a.parents, n_prompts, block_size, a.extra, a.extra_off,
+                              reinterpret_cast<uint64_t*>(D + o_keys), a.key_off, s);
+      if (rc) return rc;
+    }
+  }
+  if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_b, s));
+  if (!scored) {
+    const int64_t grid = ((int64_t)n_prompts + kScoreWarps - 1) / kScoreWarps;
+    index_score_kernel<<<(unsigned)grid, kScoreWarps * 32, 0, s>>>(
+        idx->table, idx->slots - 1, d_keys, reinterpret_cast<const int64_t*>(Din + o_koff), n_prompts, filt, idx->tier_w,
+        k_n, k_pods, k_sc, touch ? idx->ts : nullptr, stamp_base);
+    KVB_CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
   if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_c, s));
   KVB_CUDA_TRY(cudaStreamSynchronize(s));
   if (!direct_out) {

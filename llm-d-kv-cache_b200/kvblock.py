@@ -394,9 +394,10 @@ class Index:
         return self._unpack_scores(n, out_n, out_pods, out_scores)
 
     def score_tokens_flat(self, block_size: int, tokens: np.ndarray, prompt_off: np.ndarray, parents: np.ndarray,
-                          pod_identifiers=None, touch_lru: bool = True, out=None):
+                          pod_identifiers=None, touch_lru: bool = True, out=None, flags: int = 0):
         """Same fused call on pre-flattened arrays (uint32 tokens, int64 offsets, uint64 parents); returns the raw
-        (n, pods, scores) arrays — the zero-copy form a host-language shim would use."""
+        (n, pods, scores) arrays — the zero-copy form a host-language shim would use: token and output buffers from
+        ``pool.PinnedBuffer`` are read and written by the kernel in place.  ``flags``: extra KVB_SCORE_* bits (A/B)."""
         n = len(prompt_off) - 1
         filt, nf = self._filter(pod_identifiers)
         if out is None:
@@ -404,7 +405,7 @@ class Index:
                    np.zeros(max(n, 1) * MAX_PODS_PER_KEY, dtype=np.float64))
         self._check(self._lib.kvb_index_score_tokens_batch(
             self._h, tokens.ctypes.data, prompt_off.ctypes.data, parents.ctypes.data, n, int(block_size), None, None,
-            None if filt is None else filt.ctypes.data, nf, 0 if touch_lru else _lib.SCORE_NO_TOUCH,
+            None if filt is None else filt.ctypes.data, nf, (0 if touch_lru else _lib.SCORE_NO_TOUCH) | int(flags),
             out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
         return out
 

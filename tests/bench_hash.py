@@ -37,11 +37,14 @@ def main():
             kvb._lib.check(lib.kvb_hash_token_blocks_dev(0, d_tok.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), n, bs, None, None,
                                                          d_keys.data_ptr(), d_koff.data_ptr(), st.cuda_stream))
         row = {}
-        for family in ("", "wpc", "lanes"):
-            if family:
-                os.environ["KVB_HASH_KERNEL"] = family
+        for family in ("chain_s1", "chain_s2", "chain_s1_merged", "chain_s2_merged", "wpc", "lanes"):
+            for k in ("KVB_HASH_STAGERS", "KVB_HASH_MERGED", "KVB_HASH_KERNEL"):
+                os.environ.pop(k, None)
+            if family.startswith("chain"):
+                os.environ["KVB_HASH_STAGERS"] = "2" if "_s2" in family else "1"
+                os.environ["KVB_HASH_MERGED"] = "1" if "merged" in family else "0"
             else:
-                os.environ.pop("KVB_HASH_KERNEL", None)
+                os.environ["KVB_HASH_KERNEL"] = family
             d_keys.zero_()
             for _ in range(50):
                 launch()
@@ -61,9 +64,10 @@ def main():
                 launch()
                 y.record(st)
             torch.cuda.synchronize()
-            row[family or "chain_v2"] = {"us_back_to_back": round(back_to_back, 2),
+            row[family] = {"us_back_to_back": round(back_to_back, 2),
                                          "us_median_single": round(float(np.median([x.elapsed_time(y) for x, y in evs])) * 1e3, 2)}
-        os.environ.pop("KVB_HASH_KERNEL", None)
+        for k in ("KVB_HASH_STAGERS", "KVB_HASH_MERGED", "KVB_HASH_KERNEL"):
+            os.environ.pop(k, None)
         out[str(n)] = row
     print(json.dumps({"block_size": bs, "tokens_per_prompt": ntok, "blocks_per_chain": ntok // bs, "bit_exact_vs_oracle": True,
                       "prompts": out}))

@@ -260,3 +260,26 @@ def test_static_plus_parent_masks_decomposition():
                 z0 = st0 ^ _par(key & mle)
                 z1 = st1 ^ _par(key & ((mle << 1) | mopp))
                 assert (z0, z1) == (want[i] & 1, (want[i] >> 1) & 1), (i, m)
+
+
+def test_offset_basis_rides_on_position_zero():
+    """Position 0 of every block stream is 0x83 and the running low byte there is the offset basis' (0x25), so
+    e_0 = (0x25 ^ 0x83) - 0x25 = 129 is a constant: the term P^m * H0 is folded into position 0's table constant,
+    c_0' = P^m * (1 + H0 * 129^-1), and nothing is added after the dot product."""
+    inv129 = pow(129, -1, 1 << 64)
+    g = (1 + H0 * inv129) & M
+    rng = random.Random(10)
+    for _ in range(200):
+        body = [rng.randrange(256) for _ in range(rng.randrange(1, 95))]
+        stream = [0x83] + body
+        m = len(stream)
+        h, es = H0, []
+        for byte in stream:
+            lo = h & 0xFF
+            es.append((lo ^ byte) - lo)
+            h = ((h ^ byte) * P) & M
+        assert es[0] == 129
+        total = (es[0] * ((pow(P, m, 1 << 64) * g) & M)) & M
+        for i in range(1, m):
+            total = (total + es[i] * pow(P, m - i, 1 << 64)) & M
+        assert total == fnv(stream)

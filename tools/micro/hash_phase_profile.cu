@@ -38,6 +38,9 @@ int main(int argc, char** argv) {
   const double nb = (double)h[10];
   printf("blocks per chain: %.0f\n", nb);
   if (n <= kvb::kWpcMaxPrompts && getenv("KVB_HASH_KERNEL") == nullptr) {
+    printf("chain v2 folder : wait+loads %.0f  bits-0/1 %.0f  rounds(6) %.0f  reduce %.0f  tail %.0f  cycles/block (sum %.0f)\n",
+           h[5] / nb, h[6] / nb, h[7] / nb, h[8] / nb, h[9] / nb, (h[5] + h[6] + h[7] + h[8] + h[9]) / nb);
+  } else if (n <= kvb::kWpcMaxPrompts && getenv("KVB_HASH_KERNEL") != nullptr && !strcmp(getenv("KVB_HASH_KERNEL"), "wpc")) {
     printf("warp-per-chain  stager : work %.0f  barrier-wait %.0f  cycles/block\n", h[0] / nb, h[4] / nb);
     printf("warp-per-chain  folder : rounds %.0f  reduce+combine %.0f  rest %.0f  barrier-wait %.0f  cycles/block\n", h[6] / nb, h[7] / nb, h[8] / nb, h[9] / nb);
   } else {
