@@ -146,6 +146,11 @@ int kvb_engine_exists(kvb_engine_t* eng, const char* file);
  * from the start that exist — the loop stops at the first miss, like the reference's.  Arena tier: hash-map probes
  * under one lock; file tier: one statx per file, nothing else (no Python, no per-block FFI crossing). */
 int kvb_engine_lookup_prefix(kvb_engine_t* eng, int32_t n_files, const char* const* files, int32_t* out_hits);
+/* the same with the file names built inside the library from the low 64 bits of the block hashes
+ * (FileMapper.get_file_name, file_mapper.py:69-87: <base_path>/<hhh>/<hh>/<016x>.bin): 8 bytes per block cross the
+ * boundary instead of a path string */
+int kvb_engine_lookup_prefix_hashes(kvb_engine_t* eng, const char* base_path, const uint64_t* hashes, int32_t n,
+                                    int32_t* out_hits);
 /* drop every host-arena entry (test / bench helper) */
 int kvb_engine_arena_clear(kvb_engine_t* eng);
 

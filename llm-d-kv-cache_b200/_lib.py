@@ -82,6 +82,7 @@ SIGNATURES = {
     "kvb_engine_wait": (C.c_int, [_vp, _i64]),
     "kvb_engine_exists": (C.c_int, [_vp, C.c_char_p]),
     "kvb_engine_lookup_prefix": (C.c_int, [_vp, _i32, _P(C.c_char_p), _P(_i32)]),
+    "kvb_engine_lookup_prefix_hashes": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _P(_i32)]),
     "kvb_engine_arena_clear": (C.c_int, [_vp]),
     "kvb_engine_get_stats": (C.c_int, [_vp, _P(EngineStats)]),
     "kvb_fnv64a": (_u64, [_vp, C.c_size_t]),

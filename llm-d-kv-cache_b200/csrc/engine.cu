@@ -20,6 +20,7 @@
 #include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -300,6 +301,45 @@ static bool file_rw(int fd, uint8_t* p, int64_t n, int64_t off, bool is_write, i
   return ok.load();
 }
 
+// A lone store has nothing to overlap with, so its one file should not be written by one thread: pwrite() calls on ONE
+// file serialise on the inode lock, but page faults on a shared mapping do not — map the (already sized) file and let a
+// few short-lived threads copy disjoint ranges into the page cache.  Used only when nothing else is queued (latency
+// regime) or when KVB_FILE_WRITE=mmap forces it for A/B; the throughput regime keeps one pwrite per worker.
+static bool mmap_write(int fd, const uint8_t* p, int64_t n, int64_t off, int64_t file_bytes, int parts) {
+  void* m = ::mmap(nullptr, (size_t)file_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (m == MAP_FAILED) return false;
+  uint8_t* dst = static_cast<uint8_t*>(m) + off;
+  if (parts <= 1) {
+    std::memcpy(dst, p, (size_t)n);
+  } else {
+    const int64_t chunk = ((n + parts - 1) / parts + 4095) & ~4095ll;
+    std::vector<std::thread> th;
+    for (int k = 0; k < parts; ++k) {
+      const int64_t lo = (int64_t)k * chunk, len = std::min(chunk, n - lo);
+      if (len <= 0) break;
+      th.emplace_back([=] { std::memcpy(dst + lo, p + lo, (size_t)len); });
+    }
+    for (auto& t : th) t.join();
+  }
+  return ::munmap(m, (size_t)file_bytes) == 0;
+}
+static int lone_io_parts() {  // helper threads of a lone file job (KVB_FILE_LONE_PARTS, default 8)
+  static const int parts = [] {
+    const char* e = std::getenv("KVB_FILE_LONE_PARTS");
+    const int v = e ? std::atoi(e) : 8;
+    return v < 1 ? 1 : (v > 32 ? 32 : v);
+  }();
+  return parts;
+}
+static int file_write_mode() {  // 0 = auto (mmap only for lone stores), 1 = always pwrite, 2 = always mmap
+  static const int mode = [] {
+    const char* e = std::getenv("KVB_FILE_WRITE");
+    if (!e) return 0;
+    return std::strcmp(e, "pwrite") == 0 ? 1 : (std::strcmp(e, "mmap") == 0 ? 2 : 0);
+  }();
+  return mode;
+}
+
 // ---------------------------------------------------------------------------------- cuFile (GDS tier)
 // libcufile is resolved with dlopen so that libkvb.so has no hard dependency on it; the driver is opened once per
 // process and left open.  Without the nvidia-fs kernel module cuFile runs in its compatibility mode (POSIX I/O through
@@ -564,13 +604,15 @@ bool kvb_engine::write_file(const FilePart& f, const uint8_t* payload, int parts
   size_t pos = target.find_last_of('/');
   if (pos != std::string::npos && !mkdirs(target.substr(0, pos))) return false;
   std::string tmp = target + tmp_suffix + std::to_string((uintptr_t)payload & 0xffffff);
-  int fd = ::open(tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  int fd = ::open(tmp.c_str(), O_CREAT | O_TRUNC | O_RDWR, 0644);  // O_RDWR: the lone-store path maps the file
   if (fd < 0) return false;
   const int64_t n = (int64_t)f.ids.size();
   const int64_t off = ((int64_t)opts.gpu_blocks_per_file - n) * block_bytes;
+  const int mode = file_write_mode();
+  const bool use_mmap = mode == 2 || (mode == 0 && parts > 1 && n * block_bytes >= (8ll << 20));
   bool ok = ::ftruncate(fd, file_bytes) == 0 &&
-            file_rw(fd, const_cast<uint8_t*>(payload), n * block_bytes, off, true, 1);
-  (void)parts;
+            (use_mmap ? mmap_write(fd, payload, n * block_bytes, off, file_bytes, parts)
+                      : file_rw(fd, const_cast<uint8_t*>(payload), n * block_bytes, off, true, 1));
   ok = (::close(fd) == 0) && ok;
   if (ok && ::rename(tmp.c_str(), target.c_str()) != 0) ok = false;
   if (!ok) ::unlink(tmp.c_str());
@@ -803,7 +845,7 @@ void kvb_engine::worker_loop(Worker* w) {
       auto& q = !first.empty() ? first : second;
       task = std::move(q.front());
       q.pop_front();
-      if (q_high.empty() && q_normal.empty() && opts.tier == KVB_TIER_FILE) task->io_parts = 4;
+      if (q_high.empty() && q_normal.empty() && opts.tier == KVB_TIER_FILE) task->io_parts = lone_io_parts();
     }
     bool ok = false;
     try {
@@ -1088,6 +1130,53 @@ int kvb_engine_lookup_prefix(kvb_engine_t* e, int32_t n_files, const char* const
       if (!files[hits]) break;
       struct statx sx;
       if (::statx(AT_FDCWD, files[hits], AT_STATX_DONT_SYNC, 0, &sx) != 0) break;  // existence only: no attributes asked
+    }
+    *out_hits = hits;
+    return KVB_OK;
+  });
+}
+
+int kvb_engine_lookup_prefix_hashes(kvb_engine_t* e, const char* base_path, const uint64_t* hashes, int32_t n,
+                                    int32_t* out_hits) {
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(e && out_hits && base_path, "NULL argument");
+    KVB_REQUIRE(n >= 0 && (n == 0 || hashes), "bad hash list");
+    *out_hits = 0;
+    // FileMapper.get_file_name (file_mapper.py:69-87): <base>/<hhh>/<hh>/<016x>.bin, built here so that the caller
+    // hands over 8 bytes per block instead of a path string
+    std::string path(base_path);
+    const size_t base_len = path.size();
+    path.resize(base_len + 1 + 3 + 1 + 2 + 1 + 16 + 4);
+    static const char* hex = "0123456789abcdef";
+    auto fill = [&](uint64_t h) {
+      char name[16];
+      for (int i = 0; i < 16; ++i) name[i] = hex[(h >> (60 - 4 * i)) & 0xf];
+      char* q = &path[base_len];
+      *q++ = '/';
+      std::memcpy(q, name, 3);
+      q += 3;
+      *q++ = '/';
+      std::memcpy(q, name + 3, 2);
+      q += 2;
+      *q++ = '/';
+      std::memcpy(q, name, 16);
+      q += 16;
+      std::memcpy(q, ".bin", 4);
+    };
+    int32_t hits = 0;
+    if (e->opts.tier == KVB_TIER_HOST_ARENA) {
+      std::lock_guard<std::mutex> lk(e->arena.mu);
+      for (; hits < n; ++hits) {
+        fill(hashes[hits]);
+        auto it = e->arena.entries.find(path);
+        if (it == e->arena.entries.end() || !it->second.valid) break;
+      }
+    } else {
+      for (; hits < n; ++hits) {  // manager.py:49-53: stop at the first block that is not offloaded
+        fill(hashes[hits]);
+        struct statx sx;
+        if (::statx(AT_FDCWD, path.c_str(), AT_STATX_DONT_SYNC, 0, &sx) != 0) break;
+      }
     }
     *out_hits = hits;
     return KVB_OK;

@@ -109,6 +109,17 @@ class StorageOffloadEngine:
         check(_lib.load().kvb_engine_lookup_prefix(self._h, n, paths, C.byref(hits)))
         return int(hits.value)
 
+    def lookup_prefix_hashes(self, base_path: str, hashes: np.ndarray) -> int:
+        """Same, from the low 64 bits of the block hashes (uint64 array): the library builds FileMapper's file names
+        itself, so nothing per block is done in Python."""
+        hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+        if hashes.size == 0:
+            return 0
+        hits = C.c_int32()
+        check(_lib.load().kvb_engine_lookup_prefix_hashes(self._h, base_path.encode(), hashes.ctypes.data, hashes.size,
+                                                          C.byref(hits)))
+        return int(hits.value)
+
     def arena_clear(self) -> None:
         check(_lib.load().kvb_engine_arena_clear(self._h))
 

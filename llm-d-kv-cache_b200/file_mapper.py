@@ -22,3 +22,25 @@ class FileMapper:
             raise TypeError("block_hash must be int or bytes")
         name = format(value & 0xFFFFFFFFFFFFFFFF, "016x")
         return "/".join((self.base_path, name[0:3], name[3:5], name + ".bin"))
+
+
+def hashes_low64(block_hashes) -> "np.ndarray":
+    """The low 64 bits of each block hash as a uint64 array — what get_file_name keeps of it (bytes hashes are
+    big-endian).  Equal-length bytes hashes (what vLLM hands over) are converted without a Python loop."""
+    import numpy as np
+    hs = block_hashes if isinstance(block_hashes, (list, tuple)) else list(block_hashes)
+    n = len(hs)
+    if n == 0:
+        return np.empty(0, dtype=np.uint64)
+    first = hs[0]
+    if isinstance(first, (bytes, bytearray)):
+        width = len(first)
+        raw = b"".join(hs)
+        if width >= 8 and len(raw) == n * width:  # all the same length (else fall through to the loop)
+            tail = np.frombuffer(raw, dtype=np.uint8).reshape(n, width)[:, width - 8:]
+            return np.ascontiguousarray(tail).view(">u8").reshape(n).astype(np.uint64)
+    out = np.empty(n, dtype=np.uint64)
+    for i, h in enumerate(hs):
+        v = int.from_bytes(h, "big") if isinstance(h, (bytes, bytearray)) else int(h)
+        out[i] = v & 0xFFFFFFFFFFFFFFFF
+    return out

@@ -7,7 +7,7 @@ import os
 from dataclasses import dataclass, field
 from typing import Callable, Iterable, Optional
 
-from .file_mapper import FileMapper
+from .file_mapper import FileMapper, hashes_low64
 from .mediums import SharedStorageLoadStoreSpec
 
 
@@ -32,8 +32,8 @@ class SharedStorageOffloadingManager:
 
     def lookup(self, block_hashes: Iterable) -> int:
         """How many consecutive blocks from the start are already offloaded (manager.py:43-53)."""
-        if self._engine is not None:
-            return self._engine.lookup_prefix([self.file_mapper.get_file_name(h) for h in block_hashes])
+        if self._engine is not None:  # ONE library call; the file names are built in C from 8 bytes per block
+            return self._engine.lookup_prefix_hashes(self.file_mapper.base_path, hashes_low64(block_hashes))
         hits = 0
         for h in block_hashes:
             if not self._exists(self.file_mapper.get_file_name(h)):
