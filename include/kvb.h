@@ -47,6 +47,12 @@ int kvb_device_count(void);
  * pageable buffers are staged through an internal pinned scratch first */
 int kvb_host_alloc(size_t bytes, void** out);
 int kvb_host_free(void* p);
+/* the same with the backing chosen: KVB_HOST_ALLOC_THP = anonymous memory advised to transparent huge pages, first-touched
+ * on the GPU's NUMA node and registered with CUDA (fewer, larger DMA translations; measured beside the default in the
+ * bench's PCIe probe) */
+#define KVB_HOST_ALLOC_DEFAULT 0
+#define KVB_HOST_ALLOC_THP 1
+int kvb_host_alloc_mode(size_t bytes, int mode, void** out);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Paged-KV pool + gather / scatter  (HBM <-> packed HBM)
@@ -254,6 +260,8 @@ int kvb_index_lookup(kvb_index_t* idx, const uint64_t* keys, int64_t n, const ui
 #define KVB_SCORE_TIME_KERNELS 4 /* record CUDA events around the kernels; read them with kvb_index_get_stats */
 #define KVB_SCORE_COPY_TOKENS 8  /* A/B: copy pinned token buffers to HBM first instead of reading them in place */
 #define KVB_SCORE_TWO_KERNELS 16 /* A/B: hash kernel + score kernel instead of the fused tokens -> scores launch */
+#define KVB_SCORE_PINNED_IO 32   /* the caller vouches that tokens AND the three output arrays are pinned host memory
+                                    (kvb_host_alloc): they are read / written in place without asking the driver */
 int kvb_index_score_batch(kvb_index_t* idx, const uint64_t* keys, const int64_t* key_off, int32_t n_prompts,
                           const uint16_t* pod_filter, int32_t n_filter, int32_t flags, int32_t* out_n,
                           uint16_t* out_pods, double* out_scores);

@@ -14,7 +14,7 @@ COPY_DEFAULT, COPY_LDG, COPY_BULK = 0, 1, 2
 TIER_FILE, TIER_HOST_ARENA = 0, 1
 MAX_PODS_PER_KEY = 13
 KEY_ENGINE, KEY_REQUEST = 0, 1
-SCORE_TOUCH_LRU, SCORE_NO_TOUCH, SCORE_TIME_KERNELS, SCORE_COPY_TOKENS, SCORE_TWO_KERNELS = 1, 2, 4, 8, 16
+SCORE_TOUCH_LRU, SCORE_NO_TOUCH, SCORE_TIME_KERNELS, SCORE_COPY_TOKENS, SCORE_TWO_KERNELS, SCORE_PINNED_IO = 1, 2, 4, 8, 16, 32
 
 
 class KvbError(RuntimeError):
@@ -64,6 +64,7 @@ SIGNATURES = {
     "kvb_device_count": (C.c_int, []),
     "kvb_host_alloc": (C.c_int, [C.c_size_t, _P(_vp)]),
     "kvb_host_free": (C.c_int, [_vp]),
+    "kvb_host_alloc_mode": (C.c_int, [C.c_size_t, C.c_int, _P(_vp)]),
     "kvb_pool_create": (C.c_int, [C.c_int, _P(_vp), _i32, _i64, _i64, _i64, _P(_vp)]),
     "kvb_pool_destroy": (None, [_vp]),
     "kvb_pool_block_bytes": (_i64, [_vp]),

@@ -680,32 +680,51 @@ __device__ __forceinline__ void st_release_cta(int* p, int v) {
   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-template <int BS, int NST, bool MERGED, bool SCORE>
-__global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel(const ChainArgs A) {
+// fused form: the last prompt to finish tells the host through a word in pinned memory, so the caller can watch that word
+// instead of paying a stream synchronisation after the kernel has already ended
+__device__ __forceinline__ void chain_signal_done(const ChainArgs& A) {
+  if (A.done_counter == nullptr) return;
+  __threadfence_system();  // this prompt's results (possibly written to pinned host memory) before the count
+  const unsigned prev = atomicAdd(A.done_counter, 1u);
+  if (prev + 1u == A.done_target) {
+    *A.done_counter = 0u;  // ready for the next call (stream order: no other launch touches it before this one ends)
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(A.done_flag_host) = A.done_value;
+  }
+}
+
+template <int BS, bool MERGED, bool SCORE>
+__global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const ChainArgs A) {
   static_assert(BS > 0 && BS < 24 && kWpcPrefix + 5 * BS + 1 <= kWpcPositions, "stream must fit 96 positions");
-  static_assert(NST == 1 || NST == 2, "one or two stager warps");
   constexpr uint32_t kFull = 0xffffffffu;
-  constexpr int S = kV2Slots, TR = kV2TokRing, NT = 32 * (1 + NST + (SCORE ? 1 : 0));
+  constexpr int NST = 1;  // one stager warp keeps up (two were measured: no gain, profiles/r02_hash_time_c.json)
+  constexpr int S = kV2Slots, NT = 32 * (1 + NST + (SCORE ? 1 : 0));
+  constexpr int kChunkTok = 128, kChunks = 4, kRingTok = kChunkTok * kChunks, kLookahead = 2;
   constexpr int kKeyRing = 64;
   // per staged block and lane: {w, c0.lo, c0.hi', c1.lo} {c1.hi', c2.lo, c2.hi', n_tot | text << 31}; w = the lane's 3
   // stream bytes (parent bytes zero) [+ static z bits 0/1 in bits 24..29 when MERGED]; c_j = P^(m - position), split for
   // signed 32 x 32 products; raw = the token bytes for the byte-serial fallback
   __shared__ uint4 rec[S][2][32];
   __shared__ uint8_t raw[S][kWpcPositions];
-  __shared__ uint32_t tring[TR][BS];
+  __shared__ __align__(16) uint32_t tring[kRingTok];  // token ring: chunks of 128 tokens, fetched 16 B per lane
   __shared__ uint64_t pw[kWpcPositions + 1];  // P^t
-  __shared__ int staged, folded, scored;      // blocks published by the stagers / folded / consumed by the scorer
+  __shared__ int staged, folded, scored;      // blocks published by the stager / folded / consumed by the scorer
   __shared__ uint64_t skeys[SCORE ? kKeyRing : 1];
   __shared__ Bucket tile[SCORE ? 32 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p = blockIdx.x;
-  const int64_t t0 = A.prompt_off[p];
-  const int nblk = (int)((A.prompt_off[p + 1] - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
+  // a single prompt travels in the kernel arguments: no array to read before the chain can start
+  const int64_t t0 = A.single ? 0 : A.prompt_off[p];
+  const int64_t t1 = A.single ? A.single_tokens : A.prompt_off[p + 1];
+  const int nblk = (int)((t1 - t0) / BS);  // tail tokens dropped (token_processor.go:166-168)
   if (nblk == 0) {
-    if (SCORE && threadIdx.x == 0) A.out_n[p] = 0;
+    if (SCORE && threadIdx.x == 0) {
+      A.out_n[p] = 0;
+      chain_signal_done(A);
+    }
     return;
   }
-  const int64_t k0 = A.key_off[p];
+  const int64_t k0 = A.single ? 0 : A.key_off[p];
   for (int t = threadIdx.x; t <= kWpcPositions; t += NT) pw[t] = pow_u64(kFnvPrime, (uint32_t)t);
   if (threadIdx.x == 0) {
     staged = 0;
@@ -729,26 +748,41 @@ __global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel
         }
     }
     constexpr uint32_t l00 = (uint32_t)(kFnvOffset & 1u), l01 = (uint32_t)((kFnvOffset >> 1) & 1u);
+    // tokens arrive in chunks of 128 (one 16 B granule per lane: a single warp instruction moves 512 B, which matters
+    // when the source is pinned HOST memory read in place over PCIe); the prompt need not start on a 16 B boundary —
+    // the granules are taken from the aligned superset, and granules that stick out of the caller's array fall back to
+    // 4 B copies of the tokens that are inside it
     const uint32_t* tk = A.tokens + t0;
-    auto fetch_tokens = [&](int i) {  // one commit group per block, empty past the end so the group count stays uniform
-      if (lane < BS && i < nblk) {
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[i & (TR - 1)][lane]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(tk + (int64_t)i * BS + lane));
+    const int mis = (int)((reinterpret_cast<uintptr_t>(tk) >> 2) & 3u);  // tokens between the 16 B boundary and tk
+    const uint32_t* tka = tk - mis;
+    const int need_hi = mis + nblk * BS;                                  // aligned token indices [mis, need_hi) are needed
+    auto fetch_chunk = [&](int c) {  // one commit group per chunk, empty past the end so the group count stays uniform
+      const int a0 = (c * 32 + lane) * 4;
+      if (a0 + 3 >= mis && a0 < need_hi) {
+        const uint32_t* src = tka + a0;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[a0 & (kRingTok - 1)]);
+        if (src >= A.tokens_lo && src + 4 <= A.tokens_hi) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (src + q >= A.tokens_lo && src + q < A.tokens_hi)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * q), "l"(src + q));
+        }
       }
       asm volatile("cp.async.commit_group;");
     };
-    constexpr int TRW = TR / NST;  // token blocks this stager keeps in flight
-    const int first = warp - 1;
-#pragma unroll
-    for (int q = 0; q < TRW - 1; ++q) fetch_tokens(first + q * NST);
-    for (int i = first; i < nblk; i += NST) {
+    int committed = 0;
+    for (int i = 0; i < nblk; ++i) {
       const int buf = i % S;
-      fetch_tokens(i + (TRW - 1) * NST);
-      asm volatile("cp.async.wait_group %0;" ::"n"(TRW - 1) : "memory");  // all but the newest TRW-1 groups: block i landed
+      const int c_need = (mis + i * BS + BS - 1) / kChunkTok;
+      while (committed <= c_need + kLookahead) fetch_chunk(committed++);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLookahead) : "memory");  // all but the newest chunks: block i landed
       if (i >= S)
         while (ld_acquire_cta(&folded) < i - S + 1) {
         }  // the slot's previous block has been consumed
-      const uint32_t t = lane < BS ? tring[i & (TR - 1)][lane] : 0u;  // each lane reads back its own copy
+      __syncwarp();  // a chunk is written by all lanes and read by others
+      const uint32_t t = lane < BS ? tring[(mis + i * BS + lane) & (kRingTok - 1)] : 0u;
       const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
       const uint32_t head = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
       const uint32_t pay = ge64k ? t : (ge256 ? (t << 16) : (t << 24));  // payload, left-aligned big-endian
@@ -815,9 +849,6 @@ __global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel
       rec[buf][0][lane] = make_uint4(word, clo[0], chi[0], clo[1]);
       rec[buf][1][lane] = make_uint4(chi[1], clo[2], chi[2], (uint32_t)n_tot | (text ? 0x80000000u : 0u));
       __syncwarp();
-      if (NST > 1)
-        while (ld_acquire_cta(&staged) < i) {
-        }  // blocks are published in order
       if (lane == 0) st_release_cta(&staged, i + 1);
     }
     return;
@@ -838,6 +869,8 @@ __global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel
               A.stamp_base + (unsigned long long)(k0 + base + lane));
     }
     wk.finish(p, A.out_n, A.out_pods, A.out_scores);
+    __syncwarp();
+    if (lane == 0) chain_signal_done(A);
     return;
   }
 
@@ -882,7 +915,7 @@ __global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel
 #else
 #define VPROF(slot, t_begin, dep)
 #endif
-  uint64_t parent = A.parents[p];
+  uint64_t parent = A.single ? A.single_parent : A.parents[p];
   int seen = 0;  // last value read from `staged`: the stagers run ahead, so the check below rarely has to look again
   while ((seen = ld_acquire_cta(&staged)) < 1) {
   }
@@ -1008,16 +1041,13 @@ __global__ void __launch_bounds__(32 * (1 + NST + (SCORE ? 1 : 0))) chain_kernel
 
 template <int BS, bool SCORE>
 static void launch_chain_bs(const ChainArgs& a, int n_prompts, cudaStream_t s) {
-  // A/B switches (read per call): stager warps per chain, merged first two bits
-  const char* e1 = std::getenv("KVB_HASH_STAGERS");
+  // MERGED (bits 0/1 without votes) shortens a lone chain by ~2 us but costs instructions in both warps: it pays while
+  // every folder has a scheduler to itself and loses when they share one (profiles/r02_hash_time_c.json).  A/B: KVB_HASH_MERGED
   const char* e2 = std::getenv("KVB_HASH_MERGED");
-  const int nst = e1 ? std::atoi(e1) : 1;
-  const bool merged = e2 ? std::atoi(e2) != 0 : false;
-  const int threads = 32 * (1 + nst + (SCORE ? 1 : 0));
-  if (nst == 2 && merged) chain_kernel<BS, 2, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
-  else if (nst == 2) chain_kernel<BS, 2, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
-  else if (merged) chain_kernel<BS, 1, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
-  else chain_kernel<BS, 1, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  const bool merged = e2 ? std::atoi(e2) != 0 : n_prompts <= 512;
+  const int threads = 32 * (2 + (SCORE ? 1 : 0));
+  if (merged) chain_kernel<BS, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  else chain_kernel<BS, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
 }
 
 static bool chain_kernel_supports(int32_t block_size) { return block_size == 16 || block_size == 8 || block_size == 4; }
@@ -1058,11 +1088,14 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
   const char* force = std::getenv("KVB_HASH_KERNEL");
   const bool lanes_only = force != nullptr && std::strcmp(force, "lanes") == 0;
   const bool wpc_v1 = force != nullptr && std::strcmp(force, "wpc") == 0;  // round-1 warp kernel, kept for A/B
-  const char* want_chain = std::getenv("KVB_HASH_CHAIN_MAX");  // largest batch for the round-2 chain kernel (A/B)
-  const int chain_max = want_chain ? std::atoi(want_chain) : kChainMaxPrompts;
-  if (!one_warp && !lanes_only && !wpc_v1 && n_prompts <= chain_max && chain_kernel_supports(block_size)) {
+  // the round-2 chain kernel in its hash-only form: measured no faster than round 1's warp kernel (36.9 vs 34.8 us for one
+  // prompt, 51 vs 47 us for 1024), so it hashes alone only on request; its value is the fused tokens -> scores launch
+  const bool chain_only = force != nullptr && std::strcmp(force, "chain") == 0;
+  if (chain_only && n_prompts <= kChainMaxPrompts && chain_kernel_supports(block_size)) {
     ChainArgs a{};
     a.tokens = tokens;
+    a.tokens_lo = tokens;
+    a.tokens_hi = tokens + (1ll << 40);  // device-resident tokens: the caller's array bounds are not known here
     a.prompt_off = prompt_off;
     a.parents = parents;
     a.extra = extra;

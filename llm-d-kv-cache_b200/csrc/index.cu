@@ -42,6 +42,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -596,8 +597,12 @@ struct kvb_index {
   uint8_t* d_scratch = nullptr;
   size_t d_scratch_cap = 0;
   uint8_t* h_scratch = nullptr;
+  uint8_t* h_scratch_dev = nullptr;  // device alias of the pinned staging block (taken once, when it is allocated)
   size_t h_scratch_cap = 0;
   uint32_t* d_filter = nullptr;  // 65536 bits
+  unsigned* d_done = nullptr;                 // prompts finished in the running fused launch (the kernel resets it)
+  unsigned long long* h_done = nullptr;       // pinned word the last prompt writes the call's sequence number to
+  unsigned long long done_seq = 0;
   std::vector<uint16_t> filter_cached;
   bool filter_valid = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
@@ -627,6 +632,12 @@ struct kvb_index {
       KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&h_scratch), cap,
                                    cudaHostAllocPortable | cudaHostAllocMapped));
       h_scratch_cap = cap;
+      h_scratch_dev = h_scratch;  // UVA: pinned host memory is addressable by kernels at the same address ...
+#ifndef KVB_HOST_SIM
+      void* alias = nullptr;    // ... and the runtime confirms it where it can
+      if (cudaHostGetDevicePointer(&alias, h_scratch, 0) == cudaSuccess && alias) h_scratch_dev = static_cast<uint8_t*>(alias);
+      else cudaGetLastError();
+#endif
     }
     return KVB_OK;
   }
@@ -912,6 +923,10 @@ int kvb_index_create(int device, int64_t max_keys, int32_t pods_per_key, int64_t
     KVB_CUDA_TRY(cudaMemcpy(idx->tier_w, idx->tier_w_host, 256 * sizeof(double), cudaMemcpyHostToDevice));
     KVB_CUDA_TRY(cudaMalloc(&idx->d_ctr, sizeof(Counters)));
     KVB_CUDA_TRY(cudaMemset(idx->d_ctr, 0, sizeof(Counters)));
+    KVB_CUDA_TRY(cudaMalloc(&idx->d_done, sizeof(unsigned)));
+    KVB_CUDA_TRY(cudaMemset(idx->d_done, 0, sizeof(unsigned)));
+    KVB_CUDA_TRY(host_alloc_near(device, reinterpret_cast<void**>(&idx->h_done), 64, cudaHostAllocPortable | cudaHostAllocMapped));
+    *idx->h_done = 0ull;
     int64_t exp_keys = std::max<int64_t>(expected_keys, 1024);
     exp_keys = std::min<int64_t>(exp_keys, max_keys);
     uint64_t slots = 2048;
@@ -951,9 +966,9 @@ void kvb_index_destroy(kvb_index_t* idx) {
                   (void*)idx->d_ents, (void*)idx->d_skey_in, (void*)idx->d_skey_out, (void*)idx->d_sidx_in,
                   (void*)idx->d_sidx_out, idx->d_sort_tmp, (void*)idx->order_ts, (void*)idx->order_slot,
                   (void*)idx->order_ts_in, (void*)idx->order_slot_in, (void*)idx->d_cursor, (void*)idx->d_scratch,
-                  (void*)idx->d_filter})
+                  (void*)idx->d_filter, (void*)idx->d_done})
     if (p) cudaFree(p);
-  for (void* p : {(void*)idx->h_ops, (void*)idx->h_ents, (void*)idx->h_scratch})
+  for (void* p : {(void*)idx->h_ops, (void*)idx->h_ents, (void*)idx->h_scratch, (void*)idx->h_done})
     if (p) cudaFreeHost(p);
   for (cudaEvent_t e : {idx->q_free, idx->ev_a, idx->ev_b, idx->ev_c})
     if (e) cudaEventDestroy(e);
@@ -1294,14 +1309,13 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
   }
   // results land where the caller wants them when that memory is pinned (no D2H copy, no memcpy); otherwise in the
   // pinned staging block through its device alias
-  uint8_t* Hd = static_cast<uint8_t*>(device_alias(H));
-  if (!Hd) {
-    set_error("index: the pinned staging block has no device alias");
-    return KVB_ERR_CUDA;
-  }
-  int32_t* k_n = static_cast<int32_t*>(device_alias(out_n));
-  uint16_t* k_pods = static_cast<uint16_t*>(device_alias(out_pods));
-  double* k_sc = static_cast<double*>(device_alias(out_scores));
+  uint8_t* Hd = idx->h_scratch_dev;
+  // KVB_SCORE_PINNED_IO: the caller vouches that tokens and outputs are pinned (kvb_host_alloc / cudaHostAlloc) — with
+  // unified addressing a kernel uses the same address, and four pointer queries (~1 us each) leave the call
+  const bool pinned_io = (flags & KVB_SCORE_PINNED_IO) != 0;
+  int32_t* k_n = pinned_io ? out_n : static_cast<int32_t*>(device_alias(out_n));
+  uint16_t* k_pods = pinned_io ? out_pods : static_cast<uint16_t*>(device_alias(out_pods));
+  double* k_sc = pinned_io ? out_scores : static_cast<double*>(device_alias(out_scores));
   const bool direct_out = k_n && k_pods && k_sc;
   if (!direct_out) {
     k_n = reinterpret_cast<int32_t*>(Hd + o_n);
@@ -1322,17 +1336,23 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
   if (!small_in_place)
     KVB_CUDA_TRY(cudaMemcpyAsync(D + o_koff, H + o_koff, small_end - o_koff, cudaMemcpyHostToDevice, s));
   const uint64_t* d_keys = reinterpret_cast<const uint64_t*>(D + (from_tokens ? o_keys : o_hkeys));
-  bool scored = false;
+  bool scored = false, watch_flag = false;
   if (from_tokens && total_keys > 0) {
     // tokens: pinned buffers (kvb_host_alloc / cudaHostAlloc / registered) are read IN PLACE by the stager warps — the
     // PCIe transfer overlaps the hash chains instead of preceding them; pageable buffers are copied (staged by the driver)
-    const uint32_t* tok_dev = static_cast<const uint32_t*>(device_alias(tokens + prompt_off[0]));
+    const uint32_t* tok_dev = pinned_io ? tokens + prompt_off[0]
+                                        : static_cast<const uint32_t*>(device_alias(tokens + prompt_off[0]));
     if (tok_dev == nullptr || (flags & KVB_SCORE_COPY_TOKENS) != 0) {
       KVB_CUDA_TRY(cudaMemcpyAsync(D + o_tok, tokens + prompt_off[0], (size_t)total_tok * 4, cudaMemcpyHostToDevice, s));
       tok_dev = reinterpret_cast<const uint32_t*>(D + o_tok);
     }
     ChainArgs a{};
     a.tokens = tok_dev;
+    a.tokens_lo = tok_dev;  // 16 B granules are read only inside [lo, hi): nothing outside the caller's array is touched
+    a.tokens_hi = tok_dev + total_tok;
+    a.single = (n_prompts == 1 && !extra_off) ? 1 : 0;
+    a.single_tokens = total_tok;
+    a.single_parent = parents[0];
     a.prompt_off = reinterpret_cast<const int64_t*>(Din + o_poff);
     a.parents = reinterpret_cast<const uint64_t*>(Din + o_par);
     a.extra = extra_off ? D + o_ext : nullptr;
@@ -1348,9 +1368,17 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     a.out_scores = k_sc;
     a.ts = touch ? idx->ts : nullptr;
     a.stamp_base = stamp_base;
-    if (n_prompts <= 1536 && (flags & KVB_SCORE_TWO_KERNELS) == 0 && launch_chain_score(a, n_prompts, block_size, s)) {
+    const bool fuse = n_prompts <= 1536 && (flags & KVB_SCORE_TWO_KERNELS) == 0;
+    if (fuse && !timing) {  // completion word: the last prompt to finish writes this call's number to pinned memory
+      a.done_counter = idx->d_done;
+      a.done_target = (unsigned)n_prompts;
+      a.done_flag_host = idx->h_done;
+      a.done_value = ++idx->done_seq;
+    }
+    if (fuse && launch_chain_score(a, n_prompts, block_size, s)) {
       KVB_CUDA_TRY(cudaGetLastError());
       scored = true;  // ONE launch did tokens -> keys -> lookup -> scores
+      watch_flag = a.done_counter != nullptr;
     } else {
       rc = launch_hash_blocks(tok_dev, a.prompt_off, a.parents, n_prompts, block_size, a.extra, a.extra_off,
                               reinterpret_cast<uint64_t*>(D + o_keys), a.key_off, s);
@@ -1367,7 +1395,23 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     count_launch();
   }
   if (timing) KVB_CUDA_TRY(cudaEventRecord(idx->ev_c, s));
-  KVB_CUDA_TRY(cudaStreamSynchronize(s));
+  bool finished = false;
+  if (watch_flag) {
+    // the kernel's last act is a store of done_seq to pinned memory (after a system fence behind every result): watching
+    // that word costs about a microsecond, a stream synchronisation several.  Bounded: a faulting kernel never writes it.
+    const volatile unsigned long long* flag = idx->h_done;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0;; ++spins) {
+      if (*flag == idx->done_seq) {
+        finished = true;
+        break;
+      }
+      if ((spins & 1023u) == 1023u &&
+          std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > 5000)
+        break;
+    }
+  }
+  if (!finished) KVB_CUDA_TRY(cudaStreamSynchronize(s));
   if (!direct_out) {
     std::memcpy(out_n, H + o_n, (size_t)n_prompts * 4);
     std::memcpy(out_pods, H + o_pods, (size_t)n_prompts * kMaxEnt * 2);

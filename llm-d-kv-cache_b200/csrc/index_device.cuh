@@ -157,6 +157,15 @@ struct ScoreWalker {
 // arguments of the chain kernel of hash_kernels.cu (hash only, or fused tokens -> keys -> lookup -> scores)
 struct ChainArgs {
   const uint32_t* tokens;     // device memory, or pinned host memory through its device alias (zero copy)
+  const uint32_t* tokens_lo;  // bounds of the caller's token array: 16 B granules are only read inside them
+  const uint32_t* tokens_hi;
+  int32_t single;             // one prompt: its offsets and parent travel in the arguments below
+  int64_t single_tokens;
+  uint64_t single_parent;
+  unsigned* done_counter;     // nullable: completion word (fused form), see chain_signal_done
+  unsigned done_target;
+  unsigned long long* done_flag_host;
+  unsigned long long done_value;
   const int64_t* prompt_off;
   const uint64_t* parents;
   const uint8_t* extra;

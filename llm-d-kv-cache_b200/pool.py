@@ -92,9 +92,9 @@ class PinnedBuffer:
     """Pinned host memory from kvb_host_alloc: page-locked and placed on the NUMA node of the current CUDA device, so
     the copy engine (and the engine's fused host I/O) reads it at full PCIe rate without a staging copy."""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, huge_pages: bool = False):
         p = C.c_void_p()
-        check(_lib.load().kvb_host_alloc(int(nbytes), C.byref(p)))
+        check(_lib.load().kvb_host_alloc_mode(int(nbytes), 1 if huge_pages else 0, C.byref(p)))
         self.ptr, self.nbytes = int(p.value), int(nbytes)
 
     def numpy(self, dtype=np.uint8) -> np.ndarray:

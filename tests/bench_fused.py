@@ -88,17 +88,33 @@ def main():
             "two_kernels": (tok_pin, o_pin, L.SCORE_TWO_KERNELS | L.SCORE_COPY_TOKENS),
             "fused_pageable_buffers": (tokens, o_pg, 0),
         }
-        for stagers in ("1", "2"):
-            os.environ["KVB_HASH_STAGERS"] = stagers
+        variants["fused_in_place_pinned_io"] = (tok_pin, o_pin, L.SCORE_PINNED_IO)
+        for merged in ("auto", "0", "1"):
+            if merged == "auto":
+                os.environ.pop("KVB_HASH_MERGED", None)
+            else:
+                os.environ["KVB_HASH_MERGED"] = merged
             for name, (tk, o, fl) in variants.items():
+                if merged != "auto" and not name.startswith("fused_in_place"):
+                    continue
                 for a in o:
                     a[:] = 0
                 idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl)
                 got = [{int(o[1][p * 13 + j]): float(o[2][p * 13 + j]) for j in range(int(o[0][p]))} for p in range(n)]
-                assert got == want, (n, name, stagers)
-                row[f"{name}_s{stagers}"] = round(med(lambda: idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl),
-                                                      iters=200 if n == 1 else 40, warm=20 if n == 1 else 8), 2)
-        os.environ.pop("KVB_HASH_STAGERS", None)
+                assert got == want, (n, name, merged)
+                row[f"{name}_merged_{merged}"] = round(med(lambda: idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl),
+                                                           iters=300 if n == 1 else 60, warm=30 if n == 1 else 10), 2)
+        os.environ.pop("KVB_HASH_MERGED", None)
+        # the same call as a host-language shim makes it: arguments bound once, no Python wrapper around the C entry point
+        fn = kvb.lib.kvb_index_score_tokens_batch
+        args = (idx._h, tok_pin.ctypes.data, off.ctypes.data, parents.ctypes.data, n, BS, None, None, None, 0, L.SCORE_PINNED_IO,
+                o_pin[0].ctypes.data, o_pin[1].ctypes.data, o_pin[2].ctypes.data)
+        for a in o_pin:
+            a[:] = 0
+        assert fn(*args) == 0
+        got = [{int(o_pin[1][p * 13 + j]): float(o_pin[2][p * 13 + j]) for j in range(int(o_pin[0][p]))} for p in range(n)]
+        assert got == want, (n, "raw abi")
+        row["raw_c_abi_pinned_io"] = round(med(lambda: fn(*args), iters=500 if n == 1 else 80, warm=50 if n == 1 else 10), 2)
         out[str(n)] = row
         idx.close()
         pin_t.free()
