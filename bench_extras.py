@@ -552,9 +552,14 @@ def run_index_configs(kvb):
         mism += g != c
     assert mism == 0, f"config #5: {mism} prompts differ from the oracle at full size"
 
+    # the call as a host-language shim makes it: arguments bound once, pinned buffers declared (KVB_SCORE_PINNED_IO)
+    raw5 = _raw_call(kvb, idx, tok_pin, off, parents, out_pinned, kvb._lib.SCORE_PINNED_IO)
     launches0 = lib.kvb_launch_count()
-    t_fused_pinned = _med(lambda: idx.score_tokens_flat(BS, tok_pin, off, parents, out=out_pinned), iters=15, warm=5)
-    launches = (lib.kvb_launch_count() - launches0) // 20
+    t_fused_pinned = _med(raw5, iters=25, warm=8)
+    launches = (lib.kvb_launch_count() - launches0) // 33
+    t_fused_py = _med(lambda: idx.score_tokens_flat(BS, tok_pin, off, parents, out=out_pinned), iters=15, warm=5)
+    t_two_kernels = _med(_raw_call(kvb, idx, tok_pin, off, parents, out_pinned,
+                                   kvb._lib.SCORE_PINNED_IO | kvb._lib.SCORE_TWO_KERNELS | kvb._lib.SCORE_COPY_TOKENS), iters=15, warm=5)
     pg_out = (np.zeros(N_PROMPTS, np.int32), np.zeros(N_PROMPTS * 13, np.uint16), np.zeros(N_PROMPTS * 13, np.float64))
     t_fused_pageable = _med(lambda: idx.score_tokens_flat(BS, tokens, off, parents, out=pg_out), iters=9, warm=3)
     # device time of the two kernels inside the fused call (CUDA events recorded by the library on its own stream)
@@ -601,8 +606,10 @@ def run_index_configs(kvb):
         "bit_exact_vs_oracle": True,
         "fused_tokens_to_scores_ms": t_fused_pinned * 1e3, "prompts_per_s": N_PROMPTS / t_fused_pinned,
         "keys_per_s": total_keys / t_fused_pinned, "kernels_per_call": int(launches),
-        "fused_pageable_buffers_ms": t_fused_pageable * 1e3,
-        "api": "kvb_index_score_tokens_batch: host tokens in, host (pod, score) pairs out, recency refreshed (default)",
+        "fused_pageable_buffers_ms": t_fused_pageable * 1e3, "fused_through_python_wrapper_ms": t_fused_py * 1e3,
+        "two_kernels_after_token_copy_ms": t_two_kernels * 1e3,
+        "api": "kvb_index_score_tokens_batch (C ABI, arguments bound once): pinned host tokens read in place by ONE fused launch, "
+               "(pod, score) pairs written to pinned host memory, recency refreshed (default), completion word instead of a stream sync",
         "h2d_bytes_per_call": int(tokens.nbytes + off.nbytes + parents.nbytes), "d2h_bytes_per_call": N_PROMPTS * (4 + 13 * 10),
         "hash_stage_us_in_call": hash_stage_us, "score_us_in_call": score_us,
         "hash_kernel": {"device_resident_us": t_hash_kernel * 1e6, "keys_per_s": total_keys / t_hash_kernel,
@@ -645,7 +652,12 @@ def run_index_configs(kvb):
     idx1.score_tokens_flat(BS, t1buf, off1, par1, out=o1)
     got = {idx1.pods.names[int(o1[1][j])]: float(o1[2][j]) for j in range(int(o1[0][0]))}
     assert got == {"pod-0": 15.0, "pod-1": 31.0, "pod-2": 46.0, "pod-3": 62.0}, got
-    t1 = _med(lambda: idx1.score_tokens_flat(BS, t1buf, off1, par1, out=o1), iters=300, warm=50)
+    raw1 = _raw_call(kvb, idx1, t1buf, off1, par1, o1, kvb._lib.SCORE_PINNED_IO)
+    raw1()
+    got_raw = {idx1.pods.names[int(o1[1][j])]: float(o1[2][j]) for j in range(int(o1[0][0]))}
+    assert got_raw == got, got_raw
+    t1 = _med(raw1, iters=500, warm=50)
+    t1_wrapped = _med(lambda: idx1.score_tokens_flat(BS, t1buf, off1, par1, out=o1), iters=300, warm=50)
     ix = kvb.indexer.Indexer(tp, idx1)
     t1_py = _med(lambda: ix.score_tokens(tok1, MODEL), iters=100, warm=10)
     cix1 = oc.load().kvo_index_new(1 << 10)
@@ -659,7 +671,10 @@ def run_index_configs(kvb):
                                   s1.ctypes.data, 1)
     t1_c = _med(c_one, iters=300, warm=50)
     cfg1 = {"workload": "BASELINE config #1: ScoreTokens, one 1000-token prompt, 16-token blocks, 4 pods",
-            "keys": 62, "us_per_call": t1 * 1e6, "calls_per_s": 1.0 / t1, "python_indexer_us_per_call": t1_py * 1e6,
+            "keys": 62, "us_per_call": t1 * 1e6, "calls_per_s": 1.0 / t1, "python_wrapper_us_per_call": t1_wrapped * 1e6,
+            "python_indexer_us_per_call": t1_py * 1e6,
+            "api": "kvb_index_score_tokens_batch through the C ABI with bound arguments and pinned buffers: one fused launch, the "
+                   "prompt's offsets and parent in the kernel arguments, tokens read in place, completion word",
             "known_answer": got, "bit_exact_vs_known_answer": True,
             "cpu_baseline": {"kind": "port", "cores": 1, "unit": "us", "value": t1_c * 1e6,
                              "sample": "the same call, C restatement on one core"},
@@ -669,6 +684,17 @@ def run_index_configs(kvb):
     idx.close()
     idx1.close()
     return cfg1, cfg5
+
+
+def _raw_call(kvb, idx, tokens, off, parents, out, flags):
+    fn = idx._lib.kvb_index_score_tokens_batch
+    args = (idx._h, tokens.ctypes.data, off.ctypes.data, parents.ctypes.data, len(off) - 1, BS, None, None, None, 0, int(flags),
+            out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+
+    def call():
+        rc = fn(*args)
+        assert rc == 0, rc
+    return call
 
 
 def _score_timed(kvb, idx, tokens, off, parents, out):
