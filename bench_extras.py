@@ -563,13 +563,16 @@ def run_index_configs(kvb):
     pg_out = (np.zeros(N_PROMPTS, np.int32), np.zeros(N_PROMPTS * 13, np.uint16), np.zeros(N_PROMPTS * 13, np.float64))
     t_fused_pageable = _med(lambda: idx.score_tokens_flat(BS, tokens, off, parents, out=pg_out), iters=9, warm=3)
     # device time of the two kernels inside the fused call (CUDA events recorded by the library on its own stream)
-    hus, sus = [], []
+    hus, sus, fus = [], [], []
+    L = kvb._lib
     for _ in range(15):
-        _score_timed(kvb, idx, tok_pin, off, parents, out_pinned)
+        _score_timed(kvb, idx, tok_pin, off, parents, out_pinned, L.SCORE_TWO_KERNELS | L.SCORE_COPY_TOKENS)
         s2 = idx.stats()
         hus.append(s2["last_hash_us"])
         sus.append(s2["last_score_us"])
-    hash_stage_us, score_us = float(np.median(hus)), float(np.median(sus))
+        _score_timed(kvb, idx, tok_pin, off, parents, out_pinned, 0)
+        fus.append(idx.stats()["last_hash_us"])
+    hash_stage_us, score_us, fused_kernel_us = float(np.median(hus)), float(np.median(sus)), float(np.median(fus))
     # hash kernel alone: everything resident in HBM, CUDA events on the launching stream, back-to-back launches
     d_tok, d_off, d_par = (torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a.view(np.int64)).cuda()
                            for a in (tokens, off, parents))
@@ -611,7 +614,8 @@ def run_index_configs(kvb):
         "api": "kvb_index_score_tokens_batch (C ABI, arguments bound once): pinned host tokens read in place by ONE fused launch, "
                "(pod, score) pairs written to pinned host memory, recency refreshed (default), completion word instead of a stream sync",
         "h2d_bytes_per_call": int(tokens.nbytes + off.nbytes + parents.nbytes), "d2h_bytes_per_call": N_PROMPTS * (4 + 13 * 10),
-        "hash_stage_us_in_call": hash_stage_us, "score_us_in_call": score_us,
+        "fused_kernel_us_in_call": fused_kernel_us,
+        "two_kernel_mode": {"token_copy_plus_hash_us": hash_stage_us, "score_kernel_us": score_us},
         "hash_kernel": {"device_resident_us": t_hash_kernel * 1e6, "keys_per_s": total_keys / t_hash_kernel,
                         "bound": "latency of dependent warp instructions (vote rounds), not HBM",
                         "floor_us": vote_floor * 1e6, "frac_of_floor": vote_floor / t_hash_kernel,
@@ -697,11 +701,11 @@ def _raw_call(kvb, idx, tokens, off, parents, out, flags):
     return call
 
 
-def _score_timed(kvb, idx, tokens, off, parents, out):
+def _score_timed(kvb, idx, tokens, off, parents, out, flags=0):
     n = len(off) - 1
     idx._check(idx._lib.kvb_index_score_tokens_batch(
         idx._h, tokens.ctypes.data, off.ctypes.data, parents.ctypes.data, n, BS, None, None, None, 0,
-        kvb._lib.SCORE_TIME_KERNELS, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
+        kvb._lib.SCORE_TIME_KERNELS | int(flags), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data))
 
 
 def run_ingest(kvb):

@@ -239,7 +239,9 @@ typedef struct kvb_index_stats {
   int64_t rehashes;           /* device-side table growth / tombstone purge */
   int64_t lru_evictions;      /* keys dropped because the index held `max_keys` (in_memory.go:197) */
   int64_t order_builds, order_stale_skipped, order_scans; /* LRU order array: sorts, stale records skipped, fallbacks */
-  float last_hash_us, last_score_us; /* device time of the last scoring call made with KVB_SCORE_TIME_KERNELS */
+  float last_hash_us, last_score_us; /* device time of the last scoring call made with KVB_SCORE_TIME_KERNELS: copies +
+                                        hash kernel and score kernel (two-kernel mode), or the whole fused launch in
+                                        last_hash_us and 0 in last_score_us */
 } kvb_index_stats_t;
 int kvb_index_get_stats(kvb_index_t* idx, kvb_index_stats_t* out);
 

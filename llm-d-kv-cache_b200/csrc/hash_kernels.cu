@@ -857,16 +857,23 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
   if (SCORE && warp == 1 + NST) {
     // ------------------------------------------------------------------------------------------------ scorer
     ScoreWalker wk;
-    for (int base = 0; base < nblk; base += 32) {
-      const int in_tile = min(32, nblk - base);
-      while (ld_acquire_cta(&folded) < base + in_tile) {
-      }
+    // keys are taken as they appear: at least `score_min_batch` at a time (a probe costs a DRAM round trip whatever the
+    // batch, so a lone prompt is followed a few keys behind and only those are left when its chain ends; a large batch
+    // waits for full tiles, fewer instructions), never more than 32
+    for (int base = 0; base < nblk;) {
+      const int want = min(A.score_min_batch, nblk - base);
+      int avail;
+      do {
+        avail = ld_acquire_cta(&folded) - base;
+      } while (avail < want);
+      const int in_tile = min(avail, 32);
       const uint64_t key = lane < in_tile ? skeys[(base + lane) & (kKeyRing - 1)] : 0ull;
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile int*>(&scored) = base + in_tile;  // the ring slots may be reused
-      if (!wk.chain_alive && A.ts == nullptr) continue;  // nothing left to add and nothing to stamp
-      wk.tile(A.table, A.mask, tile, key, lane < in_tile, base, in_tile, A.filter_bits, A.tier_w, A.ts,
-              A.stamp_base + (unsigned long long)(k0 + base + lane));
+      if (wk.chain_alive || A.ts != nullptr)  // else: nothing left to add and nothing to stamp
+        wk.tile(A.table, A.mask, tile, key, lane < in_tile, base, in_tile, A.filter_bits, A.tier_w, A.ts,
+                A.stamp_base + (unsigned long long)(k0 + base + lane));
+      base += in_tile;
     }
     wk.finish(p, A.out_n, A.out_pods, A.out_scores);
     __syncwarp();

@@ -1368,6 +1368,7 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     a.out_scores = k_sc;
     a.ts = touch ? idx->ts : nullptr;
     a.stamp_base = stamp_base;
+    a.score_min_batch = n_prompts <= 256 ? 4 : 32;
     const bool fuse = n_prompts <= 1536 && (flags & KVB_SCORE_TWO_KERNELS) == 0;
     if (fuse && !timing) {  // completion word: the last prompt to finish writes this call's number to pinned memory
       a.done_counter = idx->d_done;

@@ -180,6 +180,7 @@ struct ChainArgs {
   int32_t* out_n;
   uint16_t* out_pods;
   double* out_scores;
+  int32_t score_min_batch;    // keys the scorer waits for before it probes (1..32)
   unsigned long long* ts;     // nullable: stamp found keys
   unsigned long long stamp_base;
 };
