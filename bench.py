@@ -344,7 +344,7 @@ def run_reference(args):
     return 0
 
 
-def pcie_probe(kvb, dist, world, local):
+def pcie_probe(kvb, dist, world, local, huge_pages=False):
     """What a plain cudaMemcpyAsync of one contiguous 2 GiB buffer achieves when the host side is pinned memory placed on
     the GPU's NUMA node (kvb_host_alloc — the same placement the engine's arena uses), all ranks at once: the ceiling
     the e2e number is a fraction of.  Per-rank figures are kept so that a lagging root complex is visible."""
@@ -354,7 +354,7 @@ def pcie_probe(kvb, dist, world, local):
     except Exception:  # older cuda-python
         from cuda import cudart
     probe_n = 2 << 30
-    pin = kvb.pool.PinnedBuffer(probe_n)
+    pin = kvb.pool.PinnedBuffer(probe_n, huge_pages=huge_pages)
     dbuf = torch.empty(probe_n, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     out = {}
@@ -374,8 +374,9 @@ def pcie_probe(kvb, dist, world, local):
         out[name.replace("_gbs", "_gbs_per_gpu")] = [round(x, 2) for x in bx.gather_objects(dist, mine)]
     del dbuf
     pin.free()
-    out["what"] = ("contiguous 2 GiB cudaMemcpyAsync, host side pinned on the GPU's NUMA node (kvb_host_alloc), all ranks at once "
-                   "(aggregate GB/s = bytes / max-over-ranks time)")
+    out["what"] = ("contiguous 2 GiB cudaMemcpyAsync, host side pinned on the GPU's NUMA node ("
+                   + ("transparent huge pages + cudaHostRegister" if huge_pages else "kvb_host_alloc / cudaHostAlloc")
+                   + "), all ranks at once (aggregate GB/s = bytes / max-over-ranks time)")
     return out
 
 
@@ -582,6 +583,43 @@ def run_ours(args):
     eng_d.shutdown()
 
     probe = pcie_probe(kvb, dist, world, local)
+    probe_thp = pcie_probe(kvb, dist, world, local, huge_pages=True)
+    # the same e2e arm with the arena on transparent huge pages (A/B of the host side; where several GPUs share a socket
+    # the D2H leg is what falls behind): one warm-up step + two timed steps
+    thp_arm = None
+    if world > 1 or os.environ.get("KVB_BENCH_THP_ARM"):
+        eng_t = kvb.engine.StorageOffloadEngine(env_int("KVB_BENCH_IO_THREADS", 4), bpf, tensors, 3, "disabled", 0.0,
+                                                tier="host_arena", host_arena_bytes=payload + (64 << 20),
+                                                chunk_bytes=env_int("KVB_BENCH_CHUNK_MB", 64) << 20, arena_huge_pages=True)
+        jt = [0]
+
+        def thp_step(tag):
+            files = [f"{tag}/{i:06d}" for i in range(n_files)]
+            jt[0] += 1
+            assert eng_t.async_store_gpu_blocks(jt[0], files, groups)
+            _drain(eng_t, jt[0])
+            t_mid = time.perf_counter()
+            jt[0] += 1
+            assert eng_t.async_load_gpu_blocks(jt[0], files, groups)
+            _drain(eng_t, jt[0])
+            eng_t.arena_clear()
+            return t_mid
+        thp_step("tw")
+        barrier_sync(dist)
+        tt0 = time.perf_counter()
+        st_t = 0.0
+        for k in range(2):
+            ts = time.perf_counter()
+            st_t += thp_step(f"tt{k}") - ts
+        mine_t = time.perf_counter() - tt0
+        barrier_sync(dist)
+        tot_t = max_over_ranks(dist, time.perf_counter() - tt0)
+        pg = bx.gather_objects(dist, {"store": payload * 2 / st_t / 1e9, "load": payload * 2 / max(mine_t - st_t, 1e-9) / 1e9})
+        eng_t.shutdown()
+        assert pool_checksum(big) == sum0, "huge-page arena save+load did not restore the pool bit-exact"
+        thp_arm = {"value": world * 2 * payload * 2 / tot_t / 1e9, "unit": "GB/s", "steps": 2,
+                   "store_gbs_per_gpu": [round(x["store"], 2) for x in pg], "load_gbs_per_gpu": [round(x["load"], 2) for x in pg],
+                   "arena": "transparent huge pages + cudaHostRegister, first-touched on the GPU's NUMA node"}
 
     # ---- like-for-like storage tier: reference-format files on /dev/shm, every N
     file_tier = run_file_tier(kvb, dist, rank, world, tensors, n_ref, with_latency=(rank == 0 and world == 1))
@@ -645,7 +683,7 @@ def run_ours(args):
                     "load_gbs": world * payload * args.steps / max(e2e_s - store_s_max, 1e-9) / 1e9,
                     "store_gbs_per_gpu": [round(x["store"], 2) for x in per_gpu],
                     "load_gbs_per_gpu": [round(x["load"], 2) for x in per_gpu],
-                    "pcie_probe": probe,
+                    "pcie_probe": probe, "pcie_probe_huge_pages": probe_thp, "arena_huge_pages_arm": thp_arm,
                     "frac_of_pcie_probe": e2e_gbs / (2 * probe["d2h_gbs"] * probe["h2d_gbs"] / (probe["d2h_gbs"] + probe["h2d_gbs"])),
                     "pipelined_jobs_gbs": world * 2 * payload / t_pipe / 1e9,
                     "single_file_job_latency": job_latency,

@@ -123,7 +123,7 @@ typedef struct kvb_engine_opts {
                                       are then the reference's GDS format (head-aligned, n x block_bytes long) moved by
                                       cuFile between the file and the packed HBM chunk, ONE call per file.  Falls back to
                                       the CPU-staged path when libcufile cannot be loaded (storage_offload.cpp:129-134) */
-  int32_t reserved;                /* keeps the struct a multiple of 8 bytes; must be 0 */
+  int32_t arena_alloc_mode;        /* KVB_HOST_ALLOC_* backing of the host arena (0 = cudaHostAlloc, the default) */
 } kvb_engine_opts_t;
 
 #define KVB_GDS_DISABLED 0

@@ -29,7 +29,7 @@ class EngineOpts(C.Structure):
         ("io_threads", C.c_int32), ("gpu_blocks_per_file", C.c_int32), ("read_preferring_workers", C.c_int32),
         ("max_write_queued_seconds", C.c_float), ("tier", C.c_int32), ("copy_flags", C.c_int32),
         ("host_arena_bytes", C.c_int64), ("chunk_bytes", C.c_int64), ("direct_host_io", C.c_int32),
-        ("strict_load_errors", C.c_int32), ("gds_mode", C.c_int32), ("reserved", C.c_int32),
+        ("strict_load_errors", C.c_int32), ("gds_mode", C.c_int32), ("arena_alloc_mode", C.c_int32),
     ]
 
 

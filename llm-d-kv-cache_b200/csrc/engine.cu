@@ -88,19 +88,21 @@ class Arena {
   std::unordered_map<std::string, Entry> entries;
   std::list<std::string> lru;  // front = oldest
 
-  int init(int device, int64_t bytes) {
+  int init(int device, int64_t bytes, int alloc_mode) {
     cap = bytes;
-    cudaError_t e = host_alloc_near(device, reinterpret_cast<void**>(&base), (size_t)bytes, cudaHostAllocPortable);
-    if (e != cudaSuccess) {
-      set_error("host arena: cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    void* p = nullptr;
+    if (host_alloc_mode(device, (size_t)bytes, alloc_mode, &p) != KVB_OK) {
+      const std::string why = get_error();
+      set_error("host arena of %lld bytes: %s", (long long)bytes, why.c_str());
       base = nullptr;
       return KVB_ERR_NOMEM;
     }
+    base = static_cast<uint8_t*>(p);
     free_[0] = bytes;
     return KVB_OK;
   }
   void destroy() {
-    if (base) cudaFreeHost(base);
+    if (base) host_free_any(base);
     base = nullptr;
   }
   bool exists(const std::string& k) {
@@ -973,7 +975,7 @@ void kvb_engine_default_opts(kvb_engine_opts_t* o) {
   o->direct_host_io = 0;
   o->strict_load_errors = 0;
   o->gds_mode = KVB_GDS_DISABLED;
-  o->reserved = 0;
+  o->arena_alloc_mode = KVB_HOST_ALLOC_DEFAULT;
 }
 
 int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engine_t** out) {
@@ -1014,7 +1016,9 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
     }
     if (opts->tier == KVB_TIER_HOST_ARENA) {
       KVB_REQUIRE(opts->host_arena_bytes >= e->block_bytes, "host_arena_bytes too small");
-      int rc = e->arena.init(e->device, opts->host_arena_bytes);  // pinned and first-touched on the GPU-local node
+      KVB_REQUIRE(opts->arena_alloc_mode == KVB_HOST_ALLOC_DEFAULT || opts->arena_alloc_mode == KVB_HOST_ALLOC_THP,
+                  "unknown arena_alloc_mode %d", opts->arena_alloc_mode);
+      int rc = e->arena.init(e->device, opts->host_arena_bytes, opts->arena_alloc_mode);  // pinned, on the GPU-local node
       if (rc) return rc;
     }
     const int n_high = std::min(std::max(opts->read_preferring_workers, 0), opts->io_threads);

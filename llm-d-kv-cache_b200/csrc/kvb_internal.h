@@ -58,6 +58,8 @@ static inline int guarded(F&& f) noexcept {
 std::vector<int> gpu_local_cpus(int device);
 void bind_this_thread(const std::vector<int>& cpus);
 cudaError_t host_alloc_near(int device, void** out, size_t bytes, unsigned flags);
+int host_alloc_mode(int device, size_t bytes, int mode, void** out);  // KVB_HOST_ALLOC_*; release with host_free_any
+int host_free_any(void* p);
 
 // Set the device for the duration of a scope and restore the caller's on exit
 // (the caller is typically a torch process that owns "current device").

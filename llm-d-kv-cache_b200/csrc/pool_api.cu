@@ -309,64 +309,90 @@ int kvb_scatter_blocks_dev(kvb_pool_t* pool, const int64_t* ids_dev, int64_t n, 
 static std::mutex g_thp_mu;
 static std::map<void*, size_t> g_thp_regions;
 
+}  // extern "C"
+
+namespace kvb {
+// pinned host memory for `device`, placed on its NUMA node; mode = KVB_HOST_ALLOC_*.  Released with host_free_any.
+int host_alloc_mode(int device, size_t bytes, int mode, void** out) {
+  if (mode == KVB_HOST_ALLOC_DEFAULT) {
+    KVB_CUDA_TRY(host_alloc_near(device, out, bytes, cudaHostAllocPortable));
+    return KVB_OK;
+  }
+  const size_t len = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+  void* p = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) {
+    set_error("mmap of %zu bytes failed", len);
+    return KVB_ERR_NOMEM;
+  }
+  ::madvise(p, len, MADV_HUGEPAGE);  // best effort: without THP these are ordinary pages
+  const std::vector<int> cpus = gpu_local_cpus(device);
+  {  // first touch from the GPU's node (a few threads: page faults of a multi-GB region on one thread take seconds)
+    const int nt = 8;
+    std::vector<std::thread> th;
+    const size_t part = ((len / nt) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    for (int k = 0; k < nt; ++k) {
+      const size_t lo = (size_t)k * part;
+      if (lo >= len) break;
+      const size_t n = std::min(part, len - lo);
+      th.emplace_back([=, &cpus] {
+        bind_this_thread(cpus);
+        std::memset(static_cast<uint8_t*>(p) + lo, 0, n);
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  cudaError_t e = cudaSuccess;
+  {
+    DeviceGuard g(device);
+    e = cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  }
+  if (e != cudaSuccess) {
+    ::munmap(p, len);
+    set_error("cudaHostRegister of %zu bytes failed: %s", len, cudaGetErrorString(e));
+    return KVB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_thp_mu);
+    g_thp_regions[p] = len;
+  }
+  *out = p;
+  return KVB_OK;
+}
+int host_free_any(void* p) {
+  if (!p) return KVB_OK;
+  size_t len = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_thp_mu);
+    auto it = g_thp_regions.find(p);
+    if (it != g_thp_regions.end()) {
+      len = it->second;
+      g_thp_regions.erase(it);
+    }
+  }
+  if (len) {
+    KVB_CUDA_TRY(cudaHostUnregister(p));
+    ::munmap(p, len);
+    return KVB_OK;
+  }
+  KVB_CUDA_TRY(cudaFreeHost(p));
+  return KVB_OK;
+}
+}  // namespace kvb
+
+extern "C" {
+
 int kvb_host_alloc_mode(size_t bytes, int mode, void** out) {
   return kvb::guarded([&]() -> int {
     KVB_REQUIRE(out != nullptr && bytes > 0, "bad argument");
     KVB_REQUIRE(mode == KVB_HOST_ALLOC_DEFAULT || mode == KVB_HOST_ALLOC_THP, "unknown host allocation mode %d", mode);
     int dev = 0;
     KVB_CUDA_TRY(cudaGetDevice(&dev));  // placed on the NUMA node of the caller's current device
-    if (mode == KVB_HOST_ALLOC_DEFAULT) {
-      KVB_CUDA_TRY(host_alloc_near(dev, out, bytes, cudaHostAllocPortable));
-      return KVB_OK;
-    }
-    const size_t len = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
-    void* p = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (p == MAP_FAILED) {
-      set_error("mmap of %zu bytes failed", len);
-      return KVB_ERR_NOMEM;
-    }
-    ::madvise(p, len, MADV_HUGEPAGE);  // best effort: without THP these are ordinary pages
-    const std::vector<int> cpus = gpu_local_cpus(dev);
-    std::thread toucher([&] {  // first touch from the GPU's node, several threads' worth of page faults in one place
-      bind_this_thread(cpus);
-      std::memset(p, 0, len);
-    });
-    toucher.join();
-    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped);
-    if (e != cudaSuccess) {
-      ::munmap(p, len);
-      set_error("cudaHostRegister of %zu bytes failed: %s", len, cudaGetErrorString(e));
-      return KVB_ERR_CUDA;
-    }
-    {
-      std::lock_guard<std::mutex> lk(g_thp_mu);
-      g_thp_regions[p] = len;
-    }
-    *out = p;
-    return KVB_OK;
+    return kvb::host_alloc_mode(dev, bytes, mode, out);
   });
 }
 int kvb_host_alloc(size_t bytes, void** out) { return kvb_host_alloc_mode(bytes, KVB_HOST_ALLOC_DEFAULT, out); }
 int kvb_host_free(void* p) {
-  return kvb::guarded([&]() -> int {
-    if (!p) return KVB_OK;
-    size_t len = 0;
-    {
-      std::lock_guard<std::mutex> lk(g_thp_mu);
-      auto it = g_thp_regions.find(p);
-      if (it != g_thp_regions.end()) {
-        len = it->second;
-        g_thp_regions.erase(it);
-      }
-    }
-    if (len) {
-      KVB_CUDA_TRY(cudaHostUnregister(p));
-      ::munmap(p, len);
-      return KVB_OK;
-    }
-    KVB_CUDA_TRY(cudaFreeHost(p));
-    return KVB_OK;
-  });
+  return kvb::guarded([&]() -> int { return kvb::host_free_any(p); });
 }
 
 // ------------------------------------------------------------------------------- migration / IPC

@@ -28,7 +28,7 @@ class StorageOffloadEngine:
     def __init__(self, io_threads: int, gpu_blocks_per_file: int, tensors: Sequence, read_preferring_workers: int,
                  gds_mode: str = "disabled", max_write_queued_seconds: float = 10.0, *, tier: str = "file",
                  host_arena_bytes: int = 0, chunk_bytes: int = 0, copy_variant: int = 0,
-                 strict_load_errors: bool = False, direct_host_io: bool = False):
+                 strict_load_errors: bool = False, direct_host_io: bool = False, arena_huge_pages: bool = False):
         # reference parse_gds_mode (gds_file_io.cpp:425-446): unknown strings mean "disabled"
         gds_bits = {"read_only": 1, "write_only": 2, "read_write": 3, "bb_read_only": 5, "bb_write_only": 6,
                     "bb_read_write": 7}.get(gds_mode, 0)
@@ -47,6 +47,7 @@ class StorageOffloadEngine:
             opts.chunk_bytes = int(chunk_bytes)
         opts.strict_load_errors = 1 if strict_load_errors else 0
         opts.direct_host_io = 1 if direct_host_io else 0
+        opts.arena_alloc_mode = 1 if arena_huge_pages else 0  # KVB_HOST_ALLOC_THP: arena on transparent huge pages
         opts.gds_mode = gds_bits if tier == "file" else 0
         h = C.c_void_p()
         check(lib.kvb_engine_create(self.pool.handle, C.byref(opts), C.byref(h)))
