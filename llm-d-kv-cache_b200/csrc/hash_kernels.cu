@@ -779,8 +779,9 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
       while (committed <= c_need + kLookahead) fetch_chunk(committed++);
       asm volatile("cp.async.wait_group %0;" ::"n"(kLookahead) : "memory");  // all but the newest chunks: block i landed
       if (i >= S)
-        while (ld_acquire_cta(&folded) < i - S + 1) {
-        }  // the slot's previous block has been consumed
+        while (ld_acquire_cta(&folded) < i - S + 1) __nanosleep(64);  // until the slot's previous block is consumed
+      // (waiting warps sleep instead of spinning: at 1024 prompts five warps share a scheduler and a spinning one takes
+      //  issue slots from a folding one — profiles/r02_ncu_index_raw.csv: 45.7 M instructions, most of them polls)
       __syncwarp();  // a chunk is written by all lanes and read by others
       const uint32_t t = lane < BS ? tring[(mis + i * BS + lane) & (kRingTok - 1)] : 0u;
       const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
@@ -863,9 +864,7 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
     for (int base = 0; base < nblk;) {
       const int want = min(A.score_min_batch, nblk - base);
       int avail;
-      do {
-        avail = ld_acquire_cta(&folded) - base;
-      } while (avail < want);
+      while ((avail = ld_acquire_cta(&folded) - base) < want) __nanosleep(A.score_min_batch >= 32 ? 400 : 40);
       const int in_tile = min(avail, 32);
       const uint64_t key = lane < in_tile ? skeys[(base + lane) & (kKeyRing - 1)] : 0ull;
       __syncwarp();
@@ -924,8 +923,7 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
 #endif
   uint64_t parent = A.single ? A.single_parent : A.parents[p];
   int seen = 0;  // last value read from `staged`: the stagers run ahead, so the check below rarely has to look again
-  while ((seen = ld_acquire_cta(&staged)) < 1) {
-  }
+  while ((seen = ld_acquire_cta(&staged)) < 1) __nanosleep(20);
   uint4 ra = rec[0][0][lane], rb = rec[0][1][lane];
   int cbuf = 0, nbuf = 1, scored_seen = 0;
 #ifdef KVB_HASH_PROFILE
@@ -937,7 +935,10 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
     if (i + 1 < nblk) {
       // block i + 1 was normally published long ago and `seen` (read an iteration ago) already says so: the compare is
       // on a register, the loads are issued at once and consumed only when the next block starts
-      while (seen < i + 2) seen = ld_acquire_cta(&staged);
+      while (seen < i + 2) {
+        seen = ld_acquire_cta(&staged);
+        if (seen < i + 2) __nanosleep(40);  // the stager is waiting for tokens (host memory read in place): do not spin
+      }
       ra_n = rec[nbuf][0][lane];
       rb_n = rec[nbuf][1][lane];
       seen_nxt = *reinterpret_cast<volatile int*>(&staged);  // for the next iteration's check; not waited for here
@@ -1014,7 +1015,10 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
     }
     VPROF(3, tb, (uint32_t)key ^ (uint32_t)(key >> 32));
     if (SCORE) {  // the key ring is 64 deep and the scorer consumes 32 at a time: it is normally far ahead of this check
-      while (i - scored_seen >= kKeyRing) scored_seen = ld_acquire_cta(&scored);
+      while (i - scored_seen >= kKeyRing) {
+        scored_seen = ld_acquire_cta(&scored);
+        if (i - scored_seen >= kKeyRing) __nanosleep(64);
+      }
     }
     if (lane == 0) {
       if (SCORE) skeys[i & (kKeyRing - 1)] = key;
