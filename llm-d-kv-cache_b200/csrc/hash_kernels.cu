@@ -693,13 +693,17 @@ __device__ __forceinline__ void chain_signal_done(const ChainArgs& A) {
   }
 }
 
-template <int BS, bool MERGED, bool SCORE>
+template <int BS, bool MERGED, bool SCORE, int CHUNK_TOK = 128, int LOOKAHEAD = 2>
 __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const ChainArgs A) {
   static_assert(BS > 0 && BS < 24 && kWpcPrefix + 5 * BS + 1 <= kWpcPositions, "stream must fit 96 positions");
   constexpr uint32_t kFull = 0xffffffffu;
   constexpr int NST = 1;  // one stager warp keeps up (two were measured: no gain, profiles/r02_hash_time_c.json)
   constexpr int S = kV2Slots, NT = 32 * (1 + NST + (SCORE ? 1 : 0));
-  constexpr int kChunkTok = 128, kChunks = 4, kRingTok = kChunkTok * kChunks, kLookahead = 2;
+  // token chunks: CHUNK_TOK tokens each (CHUNK_TOK / 128 16-byte granules per lane), LOOKAHEAD chunks in flight beyond
+  // the one being consumed, ring of the next power of two >= LOOKAHEAD + 2 chunks
+  constexpr int kChunkTok = CHUNK_TOK, kLookahead = LOOKAHEAD, kGran = CHUNK_TOK / 128;
+  constexpr int kChunks = (LOOKAHEAD + 2) <= 4 ? 4 : 8, kRingTok = kChunkTok * kChunks;
+  static_assert(CHUNK_TOK % 128 == 0 && LOOKAHEAD + 2 <= kChunks, "chunk geometry");
   constexpr int kKeyRing = 64;
   // per staged block and lane: {w, c0.lo, c0.hi', c1.lo} {c1.hi', c2.lo, c2.hi', n_tot | text << 31}; w = the lane's 3
   // stream bytes (parent bytes zero) [+ static z bits 0/1 in bits 24..29 when MERGED]; c_j = P^(m - position), split for
@@ -757,17 +761,20 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
     const uint32_t* tka = tk - mis;
     const int need_hi = mis + nblk * BS;                                  // aligned token indices [mis, need_hi) are needed
     auto fetch_chunk = [&](int c) {  // one commit group per chunk, empty past the end so the group count stays uniform
-      const int a0 = (c * 32 + lane) * 4;
-      if (a0 + 3 >= mis && a0 < need_hi) {
-        const uint32_t* src = tka + a0;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[a0 & (kRingTok - 1)]);
-        if (src >= A.tokens_lo && src + 4 <= A.tokens_hi) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-        } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (src + q >= A.tokens_lo && src + q < A.tokens_hi)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * q), "l"(src + q));
+      for (int g = 0; g < kGran; ++g) {
+        const int a0 = c * kChunkTok + (g * 32 + lane) * 4;
+        if (a0 + 3 >= mis && a0 < need_hi) {
+          const uint32_t* src = tka + a0;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tring[a0 & (kRingTok - 1)]);
+          if (src >= A.tokens_lo && src + 4 <= A.tokens_hi) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (src + q >= A.tokens_lo && src + q < A.tokens_hi)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * q), "l"(src + q));
+          }
         }
       }
       asm volatile("cp.async.commit_group;");
@@ -849,8 +856,14 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
       }
       rec[buf][0][lane] = make_uint4(word, clo[0], chi[0], clo[1]);
       rec[buf][1][lane] = make_uint4(chi[1], clo[2], chi[2], (uint32_t)n_tot | (text ? 0x80000000u : 0u));
+      // Publish with a plain store after the warp barrier — NOT st.release: a release compiles to MEMBAR.ALL.CTA, and the
+      // membar waits for every memory operation this warp has in flight, i.e. for the token chunks being prefetched from
+      // host memory.  That serialised each block behind a PCIe round trip (ncu: 685 membar-stall samples, 37 GB/s over
+      // PCIe instead of the link's 51).  Ordering still holds: the record stores of all lanes precede the barrier, the
+      // counter store follows it, and one SM's shared-memory pipeline performs them in that order; readers poll the
+      // counter before they load the record.
       __syncwarp();
-      if (lane == 0) st_release_cta(&staged, i + 1);
+      if (lane == 0) *reinterpret_cast<volatile int*>(&staged) = i + 1;
     }
     return;
   }
@@ -1024,8 +1037,7 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
       if (SCORE) skeys[i & (kKeyRing - 1)] = key;
       // slot i may be restaged: its record is in registers and raw[] has been read — every value the key depends on has
       // arrived, so a relaxed store is enough (a release here would put a MEMBAR, and the wait for the global store
-      // below, on the chain).  The scorer reads `folded` with acquire after the key store above (same thread, in order).
-      if (SCORE) __threadfence_block();
+      // below, on the chain).  The key store above and this counter store come from the same thread, in order.
       *reinterpret_cast<volatile int*>(&folded) = i + 1;
       if (A.out_keys != nullptr) A.out_keys[k0 + i] = key;
     }
@@ -1056,9 +1068,20 @@ static void launch_chain_bs(const ChainArgs& a, int n_prompts, cudaStream_t s) {
   // every folder has a scheduler to itself and loses when they share one (profiles/r02_hash_time_c.json).  A/B: KVB_HASH_MERGED
   const char* e2 = std::getenv("KVB_HASH_MERGED");
   const bool merged = e2 ? std::atoi(e2) != 0 : n_prompts <= 512;
+  // token fetch geometry (A/B: KVB_CHAIN_FETCH = 128x2 | 256x2 | 256x4 | 128x6): chunk size in tokens x chunks ahead
+  const char* e3 = std::getenv("KVB_CHAIN_FETCH");
+  const int geo = !e3 ? 0 : (!std::strcmp(e3, "256x2") ? 1 : (!std::strcmp(e3, "256x4") ? 2 : (!std::strcmp(e3, "128x6") ? 3 : 0)));
   const int threads = 32 * (2 + (SCORE ? 1 : 0));
-  if (merged) chain_kernel<BS, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
-  else chain_kernel<BS, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  if (merged) {
+    chain_kernel<BS, true, SCORE><<<n_prompts, threads, 0, s>>>(a);
+    return;
+  }
+  switch (geo) {
+    case 1: chain_kernel<BS, false, SCORE, 256, 2><<<n_prompts, threads, 0, s>>>(a); break;
+    case 2: chain_kernel<BS, false, SCORE, 256, 4><<<n_prompts, threads, 0, s>>>(a); break;
+    case 3: chain_kernel<BS, false, SCORE, 128, 6><<<n_prompts, threads, 0, s>>>(a); break;
+    default: chain_kernel<BS, false, SCORE><<<n_prompts, threads, 0, s>>>(a);
+  }
 }
 
 static bool chain_kernel_supports(int32_t block_size) { return block_size == 16 || block_size == 8 || block_size == 4; }

@@ -105,6 +105,32 @@ def main():
                 row[f"{name}_merged_{merged}"] = round(med(lambda: idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl),
                                                            iters=300 if n == 1 else 60, warm=30 if n == 1 else 10), 2)
         os.environ.pop("KVB_HASH_MERGED", None)
+        if n > 1:  # the token buffer on transparent huge pages (fewer IOMMU / ATS translations for 1024 scattered streams?)
+            pin_h = kvb.pool.PinnedBuffer(tokens.nbytes, huge_pages=True)
+            tok_h = pin_h.numpy(np.uint32)[:tokens.size]
+            tok_h[:] = tokens
+            o = o_pin
+            for a in o:
+                a[:] = 0
+            idx.score_tokens_flat(BS, tok_h, off, parents, out=o, flags=L.SCORE_PINNED_IO)
+            got = [{int(o[1][p * 13 + j]): float(o[2][p * 13 + j]) for j in range(int(o[0][p]))} for p in range(n)]
+            assert got == want, (n, "thp")
+            row["fused_in_place_tokens_on_huge_pages"] = round(med(lambda: idx.score_tokens_flat(BS, tok_h, off, parents, out=o, flags=L.SCORE_PINNED_IO),
+                                                                   iters=60, warm=10), 2)
+            del tok_h
+            pin_h.free()
+        if n > 1:  # token-fetch geometry of the in-place form (chunk tokens x chunks ahead)
+            for geo in ("128x2", "256x2", "256x4", "128x6"):
+                os.environ["KVB_CHAIN_FETCH"] = geo
+                tk, o, fl = variants["fused_in_place_pinned_io"]
+                for a in o:
+                    a[:] = 0
+                idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl)
+                got = [{int(o[1][p * 13 + j]): float(o[2][p * 13 + j]) for j in range(int(o[0][p]))} for p in range(n)]
+                assert got == want, (n, geo)
+                row[f"fused_in_place_fetch_{geo}"] = round(med(lambda: idx.score_tokens_flat(BS, tk, off, parents, out=o, flags=fl),
+                                                               iters=60, warm=10), 2)
+            os.environ.pop("KVB_CHAIN_FETCH", None)
         # the same call as a host-language shim makes it: arguments bound once, no Python wrapper around the C entry point
         fn = kvb.lib.kvb_index_score_tokens_batch
         args = (idx._h, tok_pin.ctypes.data, off.ctypes.data, parents.ctypes.data, n, BS, None, None, None, 0, L.SCORE_PINNED_IO,
