@@ -48,7 +48,7 @@ while not eng.get_finished():
     pass
 eng.shutdown()
 rng = np.random.default_rng(0)
-for family, bs in [(f, b) for f in ("", "lanes", "wpc") for b in (4, 16, 17, 64)]:  # warp-per-prompt and lane-per-prompt kernels
+for family, bs in [(f, b) for f in ("", "lanes", "wpc", "chain") for b in (4, 16, 17, 64)]:  # warp-per-prompt and lane-per-prompt kernels
     if family:
         os.environ["KVB_HASH_KERNEL"] = family
     else:
@@ -68,7 +68,34 @@ for p in prompts:
     if ks:
         d = int(rng.integers(1, len(ks) + 1))
         idx.add(None, ks[:d], [K.PodEntry("p%d" % int(rng.integers(0, 5)), "gpu")])
-got = kvb.indexer.Indexer(tp, idx).score_tokens_batch(prompts, "m")
+oidx = ko.InMemoryIndex()
+idx2 = K.Index(size=40, pod_cache_size=3, expected_keys=16)          # at capacity: the sequential apply path + order array
+o2 = ko.InMemoryIndex(size=40, pod_cache_size=3)
+keyspace = [int(x) for x in rng.integers(1, 1 << 62, 120)]
+for step in range(60):
+    ks = [keyspace[int(i)] for i in rng.integers(0, 120, int(rng.integers(1, 30)))]
+    e = ("p%d" % int(rng.integers(0, 6)), "gpu")
+    idx2.add(None, ks, [K.PodEntry(*e)])
+    o2.add(None, ks, [ko.PodEntry(*e)])
+    if step % 7 == 0:
+        idx2.evict(ks[0], K.REQUEST_KEY, [K.PodEntry(*e)])
+        o2.evict(ks[0], ko.REQUEST_KEY, [ko.PodEntry(*e)])
+    probe = keyspace[::5]
+    assert set(idx2.lookup(probe)) == set(o2.lookup(probe)), step
+big = [int(x) for x in rng.integers(1, 1 << 62, 5000)]               # parallel apply path + rehash
+idx3 = K.Index(expected_keys=16)
+idx3.add(None, big, [K.PodEntry("p", "gpu"), K.PodEntry("q", "cpu")])
+idx3.add(None, big[:2500], [K.PodEntry("r", "gpu")])
+assert len(idx3.lookup(big)) == 5000 and len(idx3) == 5000
+oix = ko.Indexer(otp, oidx)
+for p in prompts:
+    ks = otp.tokens_to_kv_block_keys(0, [int(x) for x in p], "m") or []
+ix = kvb.indexer.Indexer(tp, idx)
+got = ix.score_tokens_batch(prompts, "m")                             # fused tokens -> scores launch (chain kernel + scorer warp)
 assert len(got) == 40
+one = ix.score_tokens(prompts[3], "m")                                # single-prompt form (arguments in the launch)
+assert one == got[3] or (one is None and got[3] is None)
+two = idx.score_tokens_flat(16, *tp.prepare_batch(prompts, "m")[:3], flags=kvb._lib.SCORE_TWO_KERNELS)
+assert int(two[0].sum()) == sum(len(g or {}) for g in got)
 assert idx.lookup([1, 2, 3]) == {}
 print("sanitize smoke ok; kernels launched:", kvb.lib.kvb_launch_count())
