@@ -412,6 +412,7 @@ struct kvb_engine {
   struct Worker {
     std::thread th;
     bool high_first = false;
+    bool remote_cpu = false;  // file tier: this worker's page-cache copies run on another NUMA node's CPUs
     cudaStream_t stream = nullptr;
     uint8_t* d_packed = nullptr;
     uint8_t* h_stage = nullptr;  // file tier only
@@ -440,7 +441,8 @@ struct kvb_engine {
   std::map<int64_t, std::shared_ptr<JobState>> jobs;
 
   Arena arena;
-  std::vector<int> local_cpus;  // CPUs of the GPU's NUMA node (empty: unknown, no binding)
+  std::vector<int> local_cpus;   // CPUs of the GPU's NUMA node (empty: unknown, no binding)
+  std::vector<int> remote_cpus;  // CPUs of the other nodes (file tier: every second worker runs there)
   std::atomic<uint64_t> avg_write_us{0};
   std::string tmp_suffix;
 
@@ -499,8 +501,9 @@ bool kvb_engine::worker_init(Worker& w) {
   if (cudaMalloc(&w.d_packed, chunk) != cudaSuccess) return false;
   if (cudaMalloc(&w.d_ids, blocks_per_chunk * sizeof(int64_t)) != cudaSuccess) return false;
   if (cudaHostAlloc(&w.h_ids, blocks_per_chunk * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) return false;
+  // the pinned staging buffer stays on the GPU's node (the DMA side) whichever node this worker's CPU is on
   if (opts.tier == KVB_TIER_FILE &&
-      cudaHostAlloc(&w.h_stage, chunk, cudaHostAllocDefault) != cudaSuccess)
+      host_alloc_near(device, reinterpret_cast<void**>(&w.h_stage), chunk, cudaHostAllocDefault) != cudaSuccess)
     return false;
   if ((gds_read || gds_write) && CuFile::get().BufRegister)  // optional: unregistered buffers go through cuFile's own
     w.packed_registered = CuFile::get().BufRegister(w.d_packed, chunk, 0).err == CU_FILE_SUCCESS;
@@ -821,7 +824,7 @@ kvb_engine::LoadResult kvb_engine::run_load(Worker& w, ChunkTask& t) {
 }
 
 void kvb_engine::worker_loop(Worker* w) {
-  bind_this_thread(local_cpus);
+  bind_this_thread(w->remote_cpu && !remote_cpus.empty() ? remote_cpus : local_cpus);
   const bool inited = worker_init(*w);
   {
     std::lock_guard<std::mutex> lk(init_mu);
@@ -1004,6 +1007,13 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
       return KVB_ERR_CUDA;
     }
     e->local_cpus = gpu_local_cpus(e->device);
+    // File tier on tmpfs: a store is a copy into freshly allocated page-cache pages, and that insertion tops out per NUMA
+    // node (~35 GB/s here, whatever the thread count: profiles/r02_file_tier_probe.json; both nodes together reach ~70 at
+    // N=8).  Every second worker therefore runs on the OTHER node's CPUs: its pages land there (first touch), its pinned
+    // staging buffer stays next to the GPU.  KVB_FILE_SPREAD=0 keeps every worker on the GPU's node like the reference
+    // (thread_pool.cpp:73-131).
+    const char* spread = std::getenv("KVB_FILE_SPREAD");
+    if (opts->tier == KVB_TIER_FILE && !(spread && spread[0] == '0')) e->remote_cpus = gpu_remote_cpus(e->device);
     if (opts->tier == KVB_TIER_FILE && (opts->gds_mode & (KVB_GDS_READ | KVB_GDS_WRITE))) {
       cudaFree(nullptr);  // cuFileDriverOpen wants a CUDA context
       if (CuFile::get().ok) {
@@ -1025,6 +1035,7 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
     for (int i = 0; i < opts->io_threads; ++i) {
       auto w = std::make_unique<kvb_engine::Worker>();
       w->high_first = i < n_high;  // thread_pool.cpp:52-57
+      w->remote_cpu = (i & 1) != 0;
       e->workers.push_back(std::move(w));
     }
     for (auto& w : e->workers) w->th = std::thread([eng = e.get(), wp = w.get()] { eng->worker_loop(wp); });

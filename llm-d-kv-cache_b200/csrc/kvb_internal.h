@@ -56,6 +56,7 @@ static inline int guarded(F&& f) noexcept {
 // NUMA placement (pool_api.cu): CPUs of the GPU's node (empty: unknown or KVB_NO_NUMA_BIND), thread binding, and
 // pinned host memory first-touched on that node.
 std::vector<int> gpu_local_cpus(int device);
+std::vector<int> gpu_remote_cpus(int device);  // CPUs of the other NUMA nodes
 void bind_this_thread(const std::vector<int>& cpus);
 cudaError_t host_alloc_near(int device, void** out, size_t bytes, unsigned flags);
 int host_alloc_mode(int device, size_t bytes, int mode, void** out);  // KVB_HOST_ALLOC_*; release with host_free_any

@@ -138,6 +138,21 @@ std::vector<int> gpu_local_cpus(int device) {
   return it->second;
 }
 
+// CPUs of every OTHER NUMA node (empty on a single-node box or with KVB_NO_NUMA_BIND): the file tier spreads its writer
+// threads over all nodes, because what bounds it on tmpfs is page-cache insertion per node, not the copy
+std::vector<int> gpu_remote_cpus(int device) {
+  if (std::getenv("KVB_NO_NUMA_BIND")) return {};
+  const int mine = gpu_numa_node(device);
+  if (mine < 0) return {};
+  std::vector<int> cpus;
+  for (int node = 0; node < 64; ++node) {
+    if (node == mine) continue;
+    const std::vector<int> c = cpus_of_node(node);
+    cpus.insert(cpus.end(), c.begin(), c.end());
+  }
+  return cpus;
+}
+
 // Pinned host memory placed on the GPU's NUMA node: allocated (pinning touches every page) from a short-lived thread
 // bound to that node, so the caller's own affinity is left alone.
 cudaError_t host_alloc_near(int device, void** out, size_t bytes, unsigned flags) {

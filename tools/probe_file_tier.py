@@ -81,8 +81,13 @@ def child():
 
 def main():
     out = {}
-    for mode in ("auto", "pwrite", "mmap"):
-        env = dict(os.environ, KVB_FILE_WRITE=mode, PROBE_CHILD="1")
+    modes = {"spread_nodes": {"KVB_FILE_SPREAD": "1"}, "gpu_node_only": {"KVB_FILE_SPREAD": "0"},
+             "gpu_node_only_pwrite": {"KVB_FILE_SPREAD": "0", "KVB_FILE_WRITE": "pwrite"},
+             "gpu_node_only_mmap": {"KVB_FILE_SPREAD": "0", "KVB_FILE_WRITE": "mmap"}}
+    if os.environ.get("PROBE_MODES"):
+        modes = {k: v for k, v in modes.items() if k in os.environ["PROBE_MODES"].split(",")}
+    for mode, extra in modes.items():
+        env = dict(os.environ, PROBE_CHILD="1", **extra)
         r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=900)
         try:
             out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
