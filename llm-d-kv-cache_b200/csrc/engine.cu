@@ -1007,13 +1007,12 @@ int kvb_engine_create(kvb_pool_t* pool, const kvb_engine_opts_t* opts, kvb_engin
       return KVB_ERR_CUDA;
     }
     e->local_cpus = gpu_local_cpus(e->device);
-    // File tier on tmpfs: a store is a copy into freshly allocated page-cache pages, and that insertion tops out per NUMA
-    // node (~35 GB/s here, whatever the thread count: profiles/r02_file_tier_probe.json; both nodes together reach ~70 at
-    // N=8).  Every second worker therefore runs on the OTHER node's CPUs: its pages land there (first touch), its pinned
-    // staging buffer stays next to the GPU.  KVB_FILE_SPREAD=0 keeps every worker on the GPU's node like the reference
-    // (thread_pool.cpp:73-131).
+    // KVB_FILE_SPREAD=1 (A/B, off by default): every second file-tier worker runs on the OTHER NUMA node's CPUs, so that its
+    // page-cache pages land there while its pinned staging buffer stays next to the GPU.  Measured on tmpfs
+    // (profiles/r02_file_tier_probe_b.json, 16 workers): stores 38.8 vs 36.5 GB/s, loads 29.3 vs 34.8 — the limit is the
+    // kernel's page-cache insertion path, which more threads or more nodes do not widen (24 / 32 / 48 workers are slower).
     const char* spread = std::getenv("KVB_FILE_SPREAD");
-    if (opts->tier == KVB_TIER_FILE && !(spread && spread[0] == '0')) e->remote_cpus = gpu_remote_cpus(e->device);
+    if (opts->tier == KVB_TIER_FILE && spread && spread[0] == '1') e->remote_cpus = gpu_remote_cpus(e->device);
     if (opts->tier == KVB_TIER_FILE && (opts->gds_mode & (KVB_GDS_READ | KVB_GDS_WRITE))) {
       cudaFree(nullptr);  // cuFileDriverOpen wants a CUDA context
       if (CuFile::get().ok) {
