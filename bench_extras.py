@@ -745,6 +745,17 @@ def run_ingest(kvb):
     proc.process_many(work)
     idx.flush()
     dt = time.perf_counter() - t0
+    # the same batch through the native entry point (kvb_index_ingest_events): Python only flattens the batch
+    idx_n = K.Index()
+    proc_n = E.EventProcessor(idx_n, tp)
+    proc_n.process_many_native(work[:2])          # warm: interners, scratch
+    idx_n.close()
+    idx_n = K.Index()
+    proc_n = E.EventProcessor(idx_n, tp)
+    t0 = time.perf_counter()
+    proc_n.process_many_native(work)
+    idx_n.flush()
+    dt_n = time.perf_counter() - t0
     oidx, otp = ko.InMemoryIndex(), ko.TokenProcessor(BS, "")
     t0 = time.perf_counter()
     for pod, model, evs in owork:
@@ -755,9 +766,34 @@ def run_ingest(kvb):
     got = {k: sorted((e.pod_identifier, e.device_tier) for e in v) for k, v in idx.lookup(sample).items()}
     want = {k: sorted((e.pod_identifier, e.device_tier) for e in v) for k, v in oidx.lookup(sample).items()}
     assert got == want, "ingest: index contents differ from the oracle"
+    assert len(idx_n) == len(oidx.data), "native ingest: index sizes differ from the oracle"
+    got_n = {k: sorted((e.pod_identifier, e.device_tier) for e in v) for k, v in idx_n.lookup(sample).items()}
+    assert got_n == want, "native ingest: index contents differ from the oracle"
+    # CPU baseline closer to the reference's cost: hashing by the oracle's C restatement (one thread, event by event, chained
+    # parents) — its index is not part of this figure, so it flatters the CPU
+    from oracle import kvblock_oracle_c as oc
+    root = tp.get_init_hash(MODEL)
+    t0 = time.perf_counter()
+    for pod, model, evs in owork:
+        last = {}
+        for ev in evs:
+            if isinstance(ev, keo.BlockStored):
+                toks = np.asarray(ev.tokens, dtype=np.uint32)
+                par = np.asarray([last.get(ev.parent_hash, root)], dtype=np.uint64)
+                ks, _ = oc.hash_batch(toks, np.asarray([0, toks.size], dtype=np.int64), par, BS, threads=1)
+                if ks.size:
+                    last[ev.block_hashes[-1]] = int(ks[-1])
+    dt_c = time.perf_counter() - t0
     idx.close()
+    idx_n.close()
     return {"events": n_events, "block_keys": n_keys, "pods": n_pods, "events_per_s": n_events / dt, "keys_per_s": n_keys / dt,
             "seconds": dt, "api": "EventProcessor.process_many (Python host logic; device hashing, device index updates)",
+            "native": {"events_per_s": n_events / dt_n, "keys_per_s": n_keys / dt_n, "seconds": dt_n,
+                       "api": "kvb_index_ingest_events: one library call for the decoded batch (parents, hashing per round, engine map, "
+                              "device index ops); Python only flattens the events", "bit_exact_vs_oracle": True},
+            "cpu_c_hash_only_1_thread": {"events_per_s": n_events / dt_c, "seconds": dt_c,
+                                          "what": "the hashing of the same stream by the oracle's C restatement, event by event on one "
+                                                  "core (no index work): a floor for a single reference worker shard"},
             "bit_exact_vs_oracle": True,
             "cpu_baseline": {"kind": "port", "cores": 1, "unit": "events/s", "value": n_events / dt_o,
                              "sample": "the same stream through the oracle's pure-Python restatement of pool.go:253-398"}}

@@ -226,6 +226,28 @@ int kvb_index_add(kvb_index_t* idx, const uint64_t* engine_keys, int64_t n_engin
 int kvb_index_evict(kvb_index_t* idx, uint64_t key, int key_type, const kvb_pod_entry_t* entries, int32_t n_entries);
 int kvb_index_get_request_key(kvb_index_t* idx, uint64_t engine_key, uint64_t* out);
 int64_t kvb_index_num_keys(kvb_index_t* idx);
+/* KV-event ingest, the writer side of the index: Pool.processEventBatch (pkg/kvevents/pool.go:253-398) for a DECODED batch
+ * in one call.  Events of one `stream` (the pod) are applied in order, streams are independent (the reference shards pods
+ * over parallel workers, pool.go:154-166).  Per round the library resolves the parents of the BlockStored events through the
+ * engine-key map (GetRequestKey; an unknown parent drops the event, pool.go:284-294), hashes them in ONE device launch and adds
+ * them; BlockRemoved events evict by engine key (pool.go:379-386).  Text-only events: multimodal extras go through
+ * kvb_hash_token_blocks + kvb_index_add.  *out_skipped = events the reference would log and skip. */
+#define KVB_EVENT_BLOCK_STORED 0
+#define KVB_EVENT_BLOCK_REMOVED 1
+#define KVB_EVENT_OTHER 2 /* AllBlocksCleared / unknown: ignored, as in the reference (pool.go:388-395) */
+typedef struct kvb_kv_event {
+  int32_t type;               /* KVB_EVENT_* */
+  int32_t stream;             /* ordering domain: the pod */
+  int64_t token_off, n_tokens;            /* into tokens[] (BlockStored) */
+  int64_t engine_key_off, n_engine_keys;  /* into engine_keys[]: BlockStored.BlockHashes / BlockRemoved.BlockHashes */
+  uint64_t parent_engine_key; /* BlockStored.ParentHash, 0 = none */
+  uint64_t root_hash;         /* getInitHash of the event's model or LoRA name (pool.go:271-274): parent of a parentless event */
+  kvb_pod_entry_t entry;      /* the pod and the event's device tier */
+  int32_t pad;
+} kvb_kv_event_t;
+int kvb_index_ingest_events(kvb_index_t* idx, const kvb_kv_event_t* events, int32_t n_events, const uint32_t* tokens,
+                            const uint64_t* engine_keys, int32_t block_size, int32_t* out_skipped);
+
 /* apply the queued Add / Evict operations to the device table and wait for it (reads do this implicitly) */
 int kvb_index_flush(kvb_index_t* idx, void* stream);
 

@@ -50,6 +50,15 @@ class PodEntryC(C.Structure):
     _fields_ = [("pod", C.c_uint16), ("tier", C.c_uint8), ("speculative", C.c_uint8)]
 
 
+class KvEvent(C.Structure):  # kvb_kv_event_t
+    _fields_ = [("type", C.c_int32), ("stream", C.c_int32), ("token_off", C.c_int64), ("n_tokens", C.c_int64),
+                ("engine_key_off", C.c_int64), ("n_engine_keys", C.c_int64), ("parent_engine_key", C.c_uint64),
+                ("root_hash", C.c_uint64), ("entry", PodEntryC), ("pad", C.c_int32)]
+
+
+EVENT_BLOCK_STORED, EVENT_BLOCK_REMOVED, EVENT_OTHER = 0, 1, 2
+
+
 class IpcMem(C.Structure):
     _fields_ = [("handle", C.c_uint8 * 64), ("offset", C.c_int64)]
 
@@ -97,6 +106,7 @@ SIGNATURES = {
     "kvb_index_evict": (C.c_int, [_vp, _u64, C.c_int, _P(PodEntryC), _i32]),
     "kvb_index_get_request_key": (C.c_int, [_vp, _u64, _P(_u64)]),
     "kvb_index_num_keys": (_i64, [_vp]),
+    "kvb_index_ingest_events": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _P(_i32)]),
     "kvb_index_flush": (C.c_int, [_vp, _vp]),
     "kvb_index_get_stats": (C.c_int, [_vp, _P(IndexStats)]),
     "kvb_index_lookup": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _P(_i64)]),

@@ -890,6 +890,41 @@ int kvb_index::set_filter(const uint16_t* pods, int32_t n, uint8_t* h_stage, boo
   return KVB_OK;
 }
 
+// engineKey -> requestKeys mapping of one Add (in_memory.go:166-177): ek = engine[i*|E|/n], rk = request[i*|R|/n], n = max
+static void map_engine_keys(EngMap& em, const uint64_t* engine_keys, int64_t n_engine, const uint64_t* request_keys,
+                            int64_t n_request) {
+  bool one_to_one = n_engine == n_request;  // the common shape: one request key per engine key, no repeats
+  if (one_to_one && n_engine > 1) {
+    std::vector<uint64_t> sorted(engine_keys, engine_keys + n_engine);
+    std::sort(sorted.begin(), sorted.end());
+    one_to_one = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
+  }
+  if (one_to_one) {
+    for (int64_t i = 0; i < n_engine; ++i) em.put(engine_keys[i], &request_keys[i], 1);
+    return;
+  }
+  const int64_t n = std::max(n_engine, n_request);
+  std::vector<uint64_t> order;
+  std::unordered_map<uint64_t, std::vector<uint64_t>> m;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t ek = engine_keys[i * n_engine / n];
+    const uint64_t rk = request_keys[i * n_request / n];
+    auto it = m.find(ek);
+    if (it == m.end()) {
+      order.push_back(ek);
+      m[ek].push_back(rk);
+    } else {
+      it->second.push_back(rk);
+    }
+  }
+  // Go iterates newMappings in random order (in_memory.go:174-176); first-seen order here (only observable when the
+  // engine-key LRU is at capacity)
+  for (uint64_t ek : order) {
+    const auto& v = m[ek];
+    em.put(ek, v.data(), v.size());
+  }
+}
+
 extern "C" {
 
 int kvb_index_create(int device, int64_t max_keys, int32_t pods_per_key, int64_t expected_keys, kvb_index_t** out) {
@@ -999,39 +1034,7 @@ int kvb_index_add(kvb_index_t* idx, const uint64_t* engine_keys, int64_t n_engin
     KVB_REQUIRE(n_entries <= 65535, "too many entries in one Add");
     std::lock_guard<std::mutex> lk(idx->mu);
     DeviceGuard g(idx->device);
-    if (has_engine_keys) {  // in_memory.go:166-177
-      EngMap& em = *idx->eng;
-      bool one_to_one = n_engine == n_request;  // the common shape: one request key per engine key, no repeats
-      if (one_to_one && n_engine > 1) {
-        std::vector<uint64_t> sorted(engine_keys, engine_keys + n_engine);
-        std::sort(sorted.begin(), sorted.end());
-        one_to_one = std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end();
-      }
-      if (one_to_one) {
-        for (int64_t i = 0; i < n_engine; ++i) em.put(engine_keys[i], &request_keys[i], 1);
-      } else {
-        const int64_t n = std::max(n_engine, n_request);
-        std::vector<uint64_t> order;
-        std::unordered_map<uint64_t, std::vector<uint64_t>> m;
-        for (int64_t i = 0; i < n; ++i) {
-          const uint64_t ek = engine_keys[i * n_engine / n];
-          const uint64_t rk = request_keys[i * n_request / n];
-          auto it = m.find(ek);
-          if (it == m.end()) {
-            order.push_back(ek);
-            m[ek].push_back(rk);
-          } else {
-            it->second.push_back(rk);
-          }
-        }
-        // Go iterates newMappings in random order (in_memory.go:174-176); first-seen order here (only observable when
-        // the engine-key LRU is at capacity)
-        for (uint64_t ek : order) {
-          const auto& v = m[ek];
-          em.put(ek, v.data(), v.size());
-        }
-      }
-    }
+    if (has_engine_keys) map_engine_keys(*idx->eng, engine_keys, n_engine, request_keys, n_request);  // in_memory.go:166-177
     return idx->queue_ops(kOpAdd, request_keys, n_request, entries, n_entries);  // in_memory.go:180-221
   });
 }
@@ -1074,6 +1077,129 @@ int kvb_index_get_request_key(kvb_index_t* idx, uint64_t engine_key, uint64_t* o
     return KVB_OK;
   });
 }
+
+#ifndef KVB_HOST_SIM
+// Pool.processEventBatch (pkg/kvevents/pool.go:253-398) for a decoded batch, inside the library: per round, the next event of
+// every stream (= pod; a pod's events stay in order, pods are independent — the reference runs them on parallel worker shards,
+// pool.go:154-166).  BlockRemoved events evict through the engine-key map; the round's BlockStored events resolve their parents
+// (GetRequestKey, pool.go:284-294), are hashed in ONE device launch, and are added (engine map on the host, bucket ops queued
+// for the device).  Nothing returns to the host language per event.
+int kvb_index_ingest_events(kvb_index_t* idx, const kvb_kv_event_t* ev, int32_t n_events, const uint32_t* tokens,
+                            const uint64_t* engine_keys, int32_t block_size, int32_t* out_skipped) {
+  return kvb::guarded([&]() -> int {
+    KVB_REQUIRE(idx != nullptr, "index is NULL");
+    KVB_REQUIRE(n_events >= 0 && (n_events == 0 || ev), "bad event list");
+    KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);
+    if (out_skipped) *out_skipped = 0;
+    if (n_events == 0) return KVB_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard g(idx->device);
+    int32_t skipped = 0;
+    // rounds: position of each event inside its stream
+    std::unordered_map<int32_t, int32_t> seen;
+    std::vector<std::vector<int32_t>> rounds;
+    for (int32_t e = 0; e < n_events; ++e) {
+      KVB_REQUIRE(ev[e].n_tokens >= 0 && ev[e].n_engine_keys >= 0, "event %d has negative sizes", e);
+      const int32_t r = seen[ev[e].stream]++;
+      if ((size_t)r >= rounds.size()) rounds.resize((size_t)r + 1);
+      rounds[(size_t)r].push_back(e);
+    }
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    std::vector<int32_t> stored;
+    std::vector<uint64_t> keys_tmp;
+    for (const auto& round : rounds) {
+      stored.clear();
+      int64_t tot_tok = 0, tot_keys = 0;
+      for (int32_t e : round) {
+        const kvb_kv_event_t& x = ev[e];
+        if (x.type == KVB_EVENT_BLOCK_REMOVED) {  // pool.go:379-386: every engine key, ENGINE key type
+          for (int64_t k = 0; k < x.n_engine_keys; ++k) {
+            const int64_t id = idx->eng->find(engine_keys[x.engine_key_off + k]);
+            if (id < 0) continue;
+            keys_tmp.clear();
+            idx->eng->for_each_rk(id, [&](uint64_t rk) { keys_tmp.push_back(rk); });
+            idx->eng->erase(id);
+            if (!keys_tmp.empty()) {
+              int rc = idx->queue_ops(kOpEvict, keys_tmp.data(), (int64_t)keys_tmp.size(), &x.entry, 1);
+              if (rc) return rc;
+            }
+          }
+          continue;
+        }
+        if (x.type != KVB_EVENT_BLOCK_STORED) continue;  // AllBlocksCleared and unknown events: log only (pool.go:388-395)
+        if (x.n_tokens / block_size == 0 || x.n_engine_keys == 0) {
+          ++skipped;  // "no request keys produced, skipping" (pool.go:350-355)
+          continue;
+        }
+        stored.push_back(e);
+        tot_tok += x.n_tokens;
+        tot_keys += x.n_tokens / block_size;
+      }
+      if (stored.empty()) continue;
+      const int32_t n = (int32_t)stored.size();
+      // staging: [poff | koff | parents | tokens]  ->  device;  keys  <-  device
+      size_t o = 0;
+      const size_t o_poff = o;  o += al(((size_t)n + 1) * 8);
+      const size_t o_koff = o;  o += al(((size_t)n + 1) * 8);
+      const size_t o_par = o;   o += al((size_t)n * 8);
+      const size_t o_tok = o;   o += al((size_t)tot_tok * 4);
+      const size_t in_end = o;
+      const size_t o_keys = o;  o += al((size_t)tot_keys * 8);
+      int rc = idx->ensure_scratch(o, o);
+      if (rc) return rc;
+      uint8_t *H = idx->h_scratch, *D = idx->d_scratch;
+      int64_t* h_poff = reinterpret_cast<int64_t*>(H + o_poff);
+      int64_t* h_koff = reinterpret_cast<int64_t*>(H + o_koff);
+      uint64_t* h_par = reinterpret_cast<uint64_t*>(H + o_par);
+      uint32_t* h_tok = reinterpret_cast<uint32_t*>(H + o_tok);
+      h_poff[0] = h_koff[0] = 0;
+      int32_t m = 0;  // events that survive the parent lookup
+      for (int32_t e : stored) {
+        const kvb_kv_event_t& x = ev[e];
+        uint64_t parent = x.root_hash;
+        if (x.parent_engine_key != 0) {  // pool.go:284-294: unknown parent -> the event is dropped
+          const int64_t id = idx->eng->find(x.parent_engine_key);
+          if (id < 0 || idx->eng->node(id).n == 0) {
+            ++skipped;
+            continue;
+          }
+          idx->eng->touch(id);
+          parent = idx->eng->node(id).rk_last;
+        }
+        h_par[m] = parent;
+        std::memcpy(h_tok + h_poff[m], tokens + x.token_off, (size_t)x.n_tokens * 4);
+        h_poff[m + 1] = h_poff[m] + x.n_tokens;
+        h_koff[m + 1] = h_koff[m] + x.n_tokens / block_size;
+        stored[(size_t)m] = e;
+        ++m;
+      }
+      if (m == 0) continue;
+      cudaStream_t s = idx->stream;
+      KVB_CUDA_TRY(cudaMemcpyAsync(D, H, in_end, cudaMemcpyHostToDevice, s));
+      rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
+                              reinterpret_cast<uint64_t*>(D + o_par), m, block_size, nullptr, nullptr,
+                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
+      if (rc) return rc;
+      KVB_CUDA_TRY(cudaMemcpyAsync(H + o_keys, D + o_keys, (size_t)h_koff[m] * 8, cudaMemcpyDeviceToHost, s));
+      KVB_CUDA_TRY(cudaStreamSynchronize(s));
+      const uint64_t* h_keys = reinterpret_cast<const uint64_t*>(H + o_keys);
+      // the staging block is reused by the next round and by queue_ops' flushes: take the keys out first
+      keys_tmp.assign(h_keys, h_keys + h_koff[m]);
+      std::vector<int64_t> koff(h_koff, h_koff + m + 1);
+      for (int32_t i = 0; i < m; ++i) {
+        const kvb_kv_event_t& x = ev[stored[(size_t)i]];
+        const uint64_t* rks = keys_tmp.data() + koff[(size_t)i];
+        const int64_t n_rk = koff[(size_t)i + 1] - koff[(size_t)i];
+        map_engine_keys(*idx->eng, engine_keys + x.engine_key_off, x.n_engine_keys, rks, n_rk);  // pool.go:360 Index.Add
+        rc = idx->queue_ops(kOpAdd, rks, n_rk, &x.entry, 1);
+        if (rc) return rc;
+      }
+    }
+    if (out_skipped) *out_skipped = skipped;
+    return KVB_OK;
+  });
+}
+#endif  // !KVB_HOST_SIM
 
 int64_t kvb_index_num_keys(kvb_index_t* idx) {
   if (!idx) return 0;

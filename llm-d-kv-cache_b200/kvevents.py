@@ -229,6 +229,58 @@ class EventProcessor:
             return
         self.process_event_batch(batch, pod, model)
 
+    # -- native form: one library call per batch ----------------------------------------------------------------
+    def process_many_native(self, work: Sequence) -> int:
+        """work: [(pod_identifier, model_name, events)] like ``process_many``, applied by ``kvb_index_ingest_events``:
+        parent lookups, hashing (one device launch per round of events), engine-key mapping and the index updates all
+        happen inside the library; Python only flattens the batch.  Text-only events (an event with extra_keys makes the
+        whole batch fall back to ``process_many``).  Returns the number of events the reference would log and skip."""
+        import ctypes as C
+        from . import _lib
+        if any(isinstance(ev, BlockStoredEvent) and ev.extra_keys is not None for _, _, evs in work for ev in evs):
+            before = self.skipped
+            self.process_many(work)
+            return self.skipped - before
+        n = sum(len(evs) for _, _, evs in work)
+        if n == 0:
+            return 0
+        arr = (_lib.KvEvent * n)()
+        tok_parts, ek_parts = [], []
+        tok_off = ek_off = i = 0
+        idx, tp = self.index, self.token_processor
+        for stream, (pod, model, evs) in enumerate(work):
+            for ev in evs:
+                r = arr[i]
+                i += 1
+                r.stream = stream
+                if isinstance(ev, BlockStoredEvent):
+                    r.type = _lib.EVENT_BLOCK_STORED
+                    toks = np.asarray(ev.tokens, dtype=np.uint32)
+                    r.token_off, r.n_tokens = tok_off, toks.size
+                    tok_parts.append(toks)
+                    tok_off += toks.size
+                    r.parent_engine_key = int(ev.parent_hash)
+                    r.root_hash = tp.get_init_hash(ev.lora_name if ev.lora_name else model)  # pool.go:271-274
+                elif isinstance(ev, BlockRemovedEvent):
+                    r.type = _lib.EVENT_BLOCK_REMOVED
+                else:
+                    r.type = _lib.EVENT_OTHER
+                    continue
+                eks = np.asarray(ev.block_hashes, dtype=np.uint64)
+                r.engine_key_off, r.n_engine_keys = ek_off, eks.size
+                ek_parts.append(eks)
+                ek_off += eks.size
+                r.entry.pod = idx.pods.get(pod)
+                r.entry.tier = idx._tier_id(self._tier(ev))
+                r.entry.speculative = 0
+        tokens = np.concatenate(tok_parts) if tok_parts else np.zeros(1, np.uint32)
+        eks = np.concatenate(ek_parts) if ek_parts else np.zeros(1, np.uint64)
+        skipped = C.c_int32()
+        idx._check(idx._lib.kvb_index_ingest_events(idx._h, C.addressof(arr), n, tokens.ctypes.data, eks.ctypes.data,
+                                                     tp.block_size(), C.byref(skipped)))
+        self.skipped += int(skipped.value)
+        return int(skipped.value)
+
     # -- data-parallel form ------------------------------------------------------------------------------------
     def process_many(self, work: Sequence) -> None:
         """work: [(pod_identifier, model_name, events)], one entry per pod.  Per-pod order is kept; in every round

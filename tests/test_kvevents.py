@@ -128,7 +128,7 @@ def test_adapter_matches_oracle(kvb):
 
 
 # ------------------------------------------------------------------------------------------ GPU parity
-def _stream(rnd, n_events, key_base, with_parent=True):
+def _stream(rnd, n_events, key_base, with_parent=True, with_extra=True):
     """A plausible per-pod stream: stores (sometimes chained to an earlier engine key), removals of earlier keys."""
     events, oevents, known = [], [], []
     next_key = key_base
@@ -146,7 +146,7 @@ def _stream(rnd, n_events, key_base, with_parent=True):
             tier = rnd.choice(["", "GPU", "CPU", "disk"])
             lora = rnd.choice([None, None, "lora-1"])
             extra = None
-            if rnd.random() < 0.3:
+            if with_extra and rnd.random() < 0.3:
                 extra = [rnd.choice([None, ["img-%d" % rnd.randrange(4)], [["aud-%d" % rnd.randrange(3), 7]], []])
                          for _ in range(nb)]
             kw = dict(block_hashes=hashes, tokens=toks, parent_hash=parent, device_tier=tier, lora_name=lora, extra_keys=extra)
@@ -223,6 +223,41 @@ def test_process_many_equals_per_pod_processing(kvb, torch_cuda):
     _assert_same_index(kvb, idx_a, oidx)
     _assert_same_index(kvb, idx_b, oidx)
     assert launches_many * 4 < launches_seq          # ~12x fewer hash launches: one per round instead of one per event
+
+
+@pytest.mark.gpu
+def test_native_ingest_equals_the_oracle(kvb, torch_cuda):
+    """kvb_index_ingest_events: a decoded batch of many pods applied inside the library (parents through the engine-key map,
+    one hash launch per round, BlockRemoved by engine key, unknown parents and short events skipped) gives the same index
+    as the oracle's processEventBatch pod by pod — text-only streams; a batch with multimodal extras falls back."""
+    E, K = kvb.kvevents, kvb.kvblock
+    rnd = random.Random(31)
+    specs = [("pod-%d" % p, "m", _stream(rnd, 40, 100000 * (p + 1), with_extra=False)) for p in range(16)]
+    idx, tp = K.Index(), K.ChunkedTokenDatabase(16, "")
+    oidx, otp = ko.InMemoryIndex(), ko.TokenProcessor(16, "")
+    proc = E.EventProcessor(idx, tp)
+    launches0 = kvb.lib.kvb_launch_count()
+    skipped = proc.process_many_native([(pod, m, [_mk(k, kw, E, False) for k, kw in spec]) for pod, m, spec in specs])
+    launches = kvb.lib.kvb_launch_count() - launches0
+    for pod, m, spec in specs:
+        eo.process_event_batch(oidx, otp, [_mk(k, kw, E, True) for k, kw in spec], pod, m)
+    _assert_same_index(kvb, idx, oidx)
+    assert skipped > 0                                   # the streams contain unknown parents
+    assert launches < 40 * 8                             # hash launches: one per ROUND (40), plus the index's own kernels
+    for ek in range(100000, 100400, 7):
+        try:
+            want = oidx.get_request_key(ek)
+        except KeyError:
+            with pytest.raises(KeyError):
+                idx.get_request_key(ek)
+        else:
+            assert idx.get_request_key(ek) == want
+    # a batch with extras takes the Python path and still matches
+    specs2 = [("pod-x%d" % p, "m", _stream(rnd, 20, 900000 + 10000 * p)) for p in range(3)]
+    proc.process_many_native([(pod, m, [_mk(k, kw, E, False) for k, kw in spec]) for pod, m, spec in specs2])
+    for pod, m, spec in specs2:
+        eo.process_event_batch(oidx, otp, [_mk(k, kw, E, True) for k, kw in spec], pod, m)
+    _assert_same_index(kvb, idx, oidx)
 
 
 @pytest.mark.gpu
