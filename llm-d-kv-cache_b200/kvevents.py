@@ -235,15 +235,19 @@ class EventProcessor:
         parent lookups, hashing (one device launch per round of events), engine-key mapping and the index updates all
         happen inside the library; Python only flattens the batch.  Text-only events (an event with extra_keys makes the
         whole batch fall back to ``process_many``).  Returns the number of events the reference would log and skip."""
-        import ctypes as C
-        from . import _lib
         if any(isinstance(ev, BlockStoredEvent) and ev.extra_keys is not None for _, _, evs in work for ev in evs):
             before = self.skipped
             self.process_many(work)
             return self.skipped - before
+        batch = self.flatten_events(work)
+        return self.ingest_flat(batch) if batch is not None else 0
+
+    def flatten_events(self, work: Sequence):
+        """The C-ABI form of a decoded batch: (kvb_kv_event_t[n], uint32 tokens, uint64 engine keys), or None if empty."""
+        from . import _lib
         n = sum(len(evs) for _, _, evs in work)
         if n == 0:
-            return 0
+            return None
         arr = (_lib.KvEvent * n)()
         tok_parts, ek_parts = [], []
         tok_off = ek_off = i = 0
@@ -275,9 +279,16 @@ class EventProcessor:
                 r.entry.speculative = 0
         tokens = np.concatenate(tok_parts) if tok_parts else np.zeros(1, np.uint32)
         eks = np.concatenate(ek_parts) if ek_parts else np.zeros(1, np.uint64)
+        return arr, n, tokens, eks
+
+    def ingest_flat(self, batch) -> int:
+        """One kvb_index_ingest_events call on a flattened batch; returns the events the reference would skip."""
+        import ctypes as C
+        arr, n, tokens, eks = batch
+        idx = self.index
         skipped = C.c_int32()
         idx._check(idx._lib.kvb_index_ingest_events(idx._h, C.addressof(arr), n, tokens.ctypes.data, eks.ctypes.data,
-                                                     tp.block_size(), C.byref(skipped)))
+                                                     self.token_processor.block_size(), C.byref(skipped)))
         self.skipped += int(skipped.value)
         return int(skipped.value)
 
