@@ -3,7 +3,7 @@
 A restatement, on the CPU, of the reference algorithms on the hot path
 (llm-d/llm-d-kv-cache @ 82d31d1).  Nothing under ``oracle/`` is part of the
 product: only ``tests/`` (the pytest suite and the two measurement / sanitizer
-drivers kept there: ``tests/bench_index.py``, ``tests/sanitize_smoke.py``, ``tests/soak_engine.py``, ``tests/soak_hash.py``),
+drivers kept there: ``bench_extras.py`` (part of bench.py), ``tests/bench_fused.py``, ``tests/bench_hash.py``, ``tests/sanitize_smoke.py``, ``tests/soak_engine.py``, ``tests/soak_hash.py``),
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it, and only as the checker / the reported
 baseline.  ``tools/`` never does.  The product (``llm-d-kv-cache_b200``) never
