@@ -90,6 +90,13 @@ class StorageOffloadEngine {
   }
   // Wait for all tasks of the job; cancels the ones still queued (storage_offload.cpp:214)
   void wait_job(int job_id) { kvb_engine_wait(eng_, job_id); }
+  // SharedStorageOffloadingManager.lookup (llmd_fs_backend/manager.py:43-53) in one call: consecutive hits from the start.
+  // `hashes` = the low 64 bits of the block hashes; the names <base>/<hhh>/<hh>/<016x>.bin are built inside the library.
+  int lookup(const std::string& base_path, const std::vector<uint64_t>& hashes) {
+    int32_t hits = 0;
+    if (kvb_engine_lookup_prefix_hashes(eng_, base_path.c_str(), hashes.data(), (int32_t)hashes.size(), &hits) != KVB_OK) return 0;
+    return hits;
+  }
 
  private:
   template <typename Fn>

@@ -53,6 +53,20 @@ int main(int argc, char** argv) {
     for (int t = 0; t < T; ++t) CHECK(cudaMemset(dev[t], 0, N * page) == cudaSuccess);
     CHECK(eng.async_load_gpu_blocks(2, files, groups));
     CHECK(drain(eng, 2, &ok) && ok);
+    {  // manager lookup in one call: files named as FileMapper names them, <base>/<hhh>/<hh>/<016x>.bin
+      const std::string base = dir + "/lk" + std::to_string(tier);
+      auto name = [&](uint64_t h) {
+        char hex[17];
+        std::snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)h);
+        const std::string x(hex);
+        return base + "/" + x.substr(0, 3) + "/" + x.substr(3, 2) + "/" + x + ".bin";
+      };
+      const std::vector<uint64_t> hs{0x1111222233334444ull, 0xaaaabbbbccccddddull, 0x0123456789abcdefull, 0xfeedfacecafebeefull};
+      CHECK(eng.async_store_gpu_blocks(7, {name(hs[0]), name(hs[1]), name(hs[3])}, {{1}, {2}, {4}}));
+      CHECK(drain(eng, 7, &ok) && ok);
+      CHECK(eng.lookup(base, hs) == 2);                      // the hole at hs[2] ends the prefix
+      CHECK(eng.lookup(base, {hs[3], hs[0]}) == 2 && eng.lookup(base, {hs[2]}) == 0 && eng.lookup(base, {}) == 0);
+    }
     eng.wait_job(12345);  // unknown job: returns
     CHECK(!eng.async_store_gpu_blocks(3, files, {{0}}));          // files / id lists differ in length -> false
     CHECK(!eng.async_store_gpu_blocks(4, {"x"}, {{99}}));        // block id out of range -> false, nothing thrown

@@ -325,3 +325,63 @@ def test_device_side_build_uses_the_parallel_path(kvb, torch_cuda):
     assert st["live_keys"] == len(oidx.data) == 50000 and st["flushes_parallel"] >= 1 and st["rehashes"] >= 1
     sample = [keys[int(i)] for i in rng.integers(0, 50000, 3000)]
     assert _as_tuples(idx.lookup(sample)) == _as_tuples(oidx.lookup(sample))
+
+
+@pytest.mark.parametrize("bs", [4, 8, 16, 5, 32])
+def test_fused_scoring_every_block_size_and_shape(kvb, torch_cuda, bs):
+    """The fused tokens -> scores launch (block sizes 4 / 8 / 16) and the two-kernel form (any other size) against the oracle:
+    ragged prompts incl. empty and shorter-than-a-block ones, unaligned prompt starts (odd token offsets, so the 16 B token
+    granules begin before the prompt), a pod filter, multimodal extras on some prompts, one prompt alone, and pinned buffers."""
+    K, L = kvb.kvblock, kvb._lib
+    rng = np.random.default_rng(100 + bs)
+    tp, otp = K.ChunkedTokenDatabase(bs, "seed"), o.TokenProcessor(bs, "seed")
+    idx, oidx = K.Index(expected_keys=1 << 12), o.InMemoryIndex()
+    pods = ["pod-%d" % i for i in range(9)]
+    lens = [0, 1, bs - 1, bs, bs + 1, 3 * bs + 2] + [int(x) for x in rng.integers(0, 40 * bs, 40)]
+    prompts = [rng.integers(0, 1 << int(rng.choice([7, 16, 17, 20])), n).astype(np.uint32) for n in lens]
+    feats = []
+    for i, p in enumerate(prompts):                      # every 5th prompt carries an image over its first blocks
+        nb = len(p) // bs
+        feats.append([K.BlockExtraFeatures([K.MMHash("img-%d" % i)]) if b < 2 else None for b in range(nb)] if (i % 5 == 0 and nb) else None)
+    ofeats = [None if f is None else [None if x is None else o.BlockExtraFeatures([o.MMHash(m.hash) for m in x.mm_hashes]) for x in f]
+              for f in feats]
+    for i, p in enumerate(prompts):
+        keys = otp.tokens_to_kv_block_keys(0, [int(t) for t in p], "m", ofeats[i]) or []
+        for _ in range(int(rng.integers(0, 4))):
+            d = int(rng.integers(0, len(keys) + 1))
+            if d:
+                ent = (pods[int(rng.integers(0, 9))], "gpu" if rng.random() < 0.7 else "cpu")
+                idx.add(None, keys[:d], [K.PodEntry(*ent)])
+                oidx.add(None, keys[:d], [o.PodEntry(*ent)])
+    ix, oix = kvb.indexer.Indexer(tp, idx), o.Indexer(otp, oidx)
+    for flt in (None, pods[:4], ["nobody"]):
+        got = ix.score_tokens_batch(prompts, "m", flt, feats)
+        for i, p in enumerate(prompts):
+            assert got[i] == oix.score_tokens([int(t) for t in p], "m", flt or (), ofeats[i]), (bs, i, flt)
+    for i in (3, 5, 17):                                  # one prompt per call: its offsets travel in the kernel arguments
+        assert ix.score_tokens(prompts[i], "m", None, feats[i]) == oix.score_tokens([int(t) for t in prompts[i]], "m", (), ofeats[i])
+    # pinned buffers read / written in place, text-only prompts packed back to back (odd starts)
+    text = [p for p, f in zip(prompts, feats) if f is None]
+    off = np.zeros(len(text) + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in text], out=off[1:])
+    pin = kvb.pool.PinnedBuffer(int(off[-1]) * 4 + 64)
+    tok = pin.numpy(np.uint32)[1:1 + int(off[-1])]       # start 4 bytes into the buffer: never 16 B aligned
+    tok[:] = np.concatenate(text) if off[-1] else 0
+    parents = np.full(len(text), tp.get_init_hash("m"), dtype=np.uint64)
+    n = len(text)
+    pout = kvb.pool.PinnedBuffer(n * 136 + 1024)
+    raw = pout.numpy(np.uint8)
+    b1 = (n * 4 + 255) // 256 * 256
+    b2 = b1 + (n * 26 + 255) // 256 * 256
+    out = (raw[:n * 4].view(np.int32), raw[b1:b1 + n * 26].view(np.uint16), raw[b2:b2 + n * 104].view(np.float64))
+    for flags in (L.SCORE_PINNED_IO, L.SCORE_PINNED_IO | L.SCORE_TWO_KERNELS, L.SCORE_COPY_TOKENS, L.SCORE_NO_TOUCH):
+        for a in out:
+            a[:] = 0
+        idx.score_tokens_flat(bs, tok, off, parents, out=out, flags=flags)
+        for i, p in enumerate(text):
+            g = {idx.pods.names[int(out[1][i * 13 + j])]: float(out[2][i * 13 + j]) for j in range(int(out[0][i]))}
+            want = oix.score_tokens([int(t) for t in p], "m") or {}
+            assert g == want, (bs, i, flags)
+    del tok
+    pin.free()
+    pout.free()
