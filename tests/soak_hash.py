@@ -54,7 +54,7 @@ def main():
             extra = rng.integers(0, 256, max(int(extra_off[-1]), 1), dtype=np.uint8)
             with_extra += 1
         want, woff = oc.hash_batch(tokens, off, parents, bs, extra, extra_off)
-        for family in ("", "lanes", "wpc"):
+        for family in ("", "lanes", "wpc", "chain"):
             if family:
                 os.environ["KVB_HASH_KERNEL"] = family
             else:
