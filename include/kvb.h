@@ -16,9 +16,15 @@
  *     when no sm_100 device is usable.
  *   - environment switches (diagnostics and A/B runs, never needed for correctness):
  *       KVB_HASH_KERNEL=lanes   hash with the lane-per-prompt kernels at every batch size (read per call)
- *       KVB_HASH_KERNEL=wpc     hash with round 1's warp-per-prompt kernel instead of the current chain kernel
+ *       KVB_HASH_KERNEL=wpc     hash with the warp-per-prompt kernel at every batch size it supports (the default up to 1536 prompts)
+ *       KVB_HASH_KERNEL=chain   hash with round 2's chain kernel in its hash-only form (it is the fused scoring launch's kernel)
+ *       KVB_HASH_MERGED=0|1     chain kernel: vote-free first two bits off / on (default: on up to 512 prompts)
+ *       KVB_CHAIN_FETCH=128x2|256x2|256x4|128x6   chain kernel: token chunk size x chunks in flight
  *       KVB_HASH_ONE_WARP=1     hash with the one-warp lane kernel (read once)
  *       KVB_NO_NUMA_BIND=1      do not bind engine threads / arena to the GPU's NUMA node
+ *       KVB_FILE_WRITE=pwrite|mmap   file tier: force one write path (default: pwrite per worker, a shared mapping written by
+ *                                    KVB_FILE_LONE_PARTS helper threads (8) when a store is alone in the queue)
+ *       KVB_FILE_SPREAD=1       file tier: every second worker runs on the other NUMA node's CPUs
  */
 #ifndef KVB_H_
 #define KVB_H_

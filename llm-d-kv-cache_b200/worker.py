@@ -48,10 +48,13 @@ class BaseStorageOffloadingHandler:
         self.engine = engine
         self.transfer_type = transfer_type
         self.per_block_bytes = per_block_bytes
-        self._pending_jobs: dict = {}  # job_id -> (submit_time, bytes); shared by the two handlers
+        # job_id -> (submit_time, bytes, transfer_type); shared by the two handlers.  The type travels with the job: both
+        # handlers drain the SAME engine, so whichever vLLM polls first reports the other's jobs too — the reference
+        # labels those with the polling handler's type (worker.py:107-122), a metrics quirk not reproduced here
+        self._pending_jobs: dict = {}
 
     def _record_job(self, job_id: int, num_blocks: int) -> None:
-        self._pending_jobs[job_id] = (time.monotonic(), num_blocks * self.per_block_bytes)
+        self._pending_jobs[job_id] = (time.monotonic(), num_blocks * self.per_block_bytes, self.transfer_type)
 
     def get_finished(self) -> list:
         now = time.monotonic()
@@ -61,9 +64,9 @@ class BaseStorageOffloadingHandler:
             if info is None:  # unknown job: still reported, without metrics (worker.py:139-145)
                 results.append(TransferResult(job_id=job_id, success=success))
                 continue
-            t_submit, size = info
+            t_submit, size, ttype = info
             results.append(TransferResult(job_id=job_id, success=success, transfer_size=size,
-                                          transfer_time=now - t_submit, transfer_type=self.transfer_type))
+                                          transfer_time=now - t_submit, transfer_type=ttype))
         return results
 
     def wait(self, job_ids) -> None:
