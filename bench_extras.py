@@ -638,6 +638,26 @@ def run_index_configs(kvb):
                         "cpu_c_restatement_1_thread_s": t_build_cpu, "where": "Add/Evict applied by kernels, no host copy"},
     }
 
+    # ---- the index AT CAPACITY: exact-LRU eviction, ops replayed in the reference's order by one thread
+    cap = 1 << 20
+    idx_c = K.Index(size=cap, expected_keys=cap)
+    fill = rng.integers(1, 1 << 62, cap + 200_000, dtype=np.int64).astype(np.uint64)
+    ent_c = [K.PodEntry(pods[0], "gpu")]
+    idx_c.add(None, fill[:cap], ent_c)
+    idx_c.flush()
+    t0 = time.perf_counter()
+    idx_c.add(None, fill[cap:], ent_c)
+    idx_c.flush()
+    t_cap = time.perf_counter() - t0
+    st_c = idx_c.stats()
+    assert st_c["live_keys"] == cap and st_c["lru_evictions"] == 200_000, st_c
+    survivors = idx_c.lookup(fill[[0, 199_999, 200_000, cap - 1, cap, cap + 199_999]])
+    assert set(int(k) for k in survivors) == {int(fill[200_000]), int(fill[cap - 1]), int(fill[cap]), int(fill[cap + 199_999])}
+    cfg5["index_at_capacity"] = {"size": cap, "new_keys": 200_000, "seconds": t_cap, "keys_per_s": 200_000 / t_cap,
+                                 "lru_evictions": st_c["lru_evictions"], "order_builds": st_c["order_builds"],
+                                 "exact": "the 200 000 oldest keys were evicted, in insertion order (checked on the boundaries)"}
+    idx_c.close()
+
     # ---- config #1: one prompt, 4 pods
     idx1 = K.Index()
     tok1 = np.random.default_rng(0).integers(0, 128256, 1000).astype(np.uint32)

@@ -258,6 +258,14 @@ KVB_DEV inline void apply_seq(const TableRef& t, const OpRec* ops, const uint32_
                                           unsigned long long order_n) {
   Counters& c = *t.ctr;
   for (int64_t j = 0; j < n; ++j) {
+#ifndef KVB_HOST_SIM
+    constexpr int64_t kAhead = 12;  // the one thread walks dependent DRAM probes: pull the home buckets of the next ops into L2
+    if (j + kAhead < n) {
+      const Bucket* nb = &t.table[mix64(ops[j + kAhead].key) & t.mask];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&t.ts[mix64(ops[j + kAhead].key) & t.mask]));
+    }
+#endif
     const OpRec op = ops[j];
     int64_t reuse = -1;
     int64_t slot = find_slot(t, op.key, &reuse);
