@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define KVB_ABI_VERSION 3
+#define KVB_ABI_VERSION 4
 
 #define KVB_OK 0
 #define KVB_ERR_INVALID (-1)   /* bad argument */
@@ -263,7 +263,10 @@ typedef struct kvb_index_stats {
   int64_t live_keys, tombstones, table_slots, engine_keys;
   int64_t ops_applied;        /* Add / Evict records applied on the device */
   int64_t flushes_parallel;   /* sorted, one thread per distinct key */
-  int64_t flushes_sequential; /* one thread in the reference's order (tiny batches, or the index is at capacity) */
+  int64_t flushes_sequential; /* one thread in the reference's order (tiny batches; at capacity, batches that also
+                                 remove pods or whose eviction plan hit a conflict) */
+  int64_t flushes_planned;    /* parallel flushes at capacity: LRU victims planned up front, same result as in order */
+  int64_t plan_fallbacks;     /* planned flushes that had to be replayed sequentially */
   int64_t rehashes;           /* device-side table growth / tombstone purge */
   int64_t lru_evictions;      /* keys dropped because the index held `max_keys` (in_memory.go:197) */
   int64_t order_builds, order_stale_skipped, order_scans; /* LRU order array: sorts, stale records skipped, fallbacks */

@@ -363,6 +363,110 @@ __global__ void index_collect_order_kernel(TableRef t, unsigned long long* __res
   }
 }
 
+// ---- parallel apply AT CAPACITY (add-only batches).  The reference evicts the outer LRU's oldest key at every
+// insertion past Size (lru.Add, in_memory.go:197), one op at a time.  For a batch of adds the same victims can be
+// planned up front: live grows by one per NEW key, so eviction number e happens at the op of insertion number
+// slack + e (slack = Size - live before the batch), and its victim is the e-th record of the recency order that the
+// batch has not touched by then.  A record the batch touches BEFORE the eviction that would reach it has moved to the
+// newest end and survives; one it touches only AFTER is evicted and re-created from nothing by that later op — a
+// "conflict" key: it is a victim AND one more insertion, which shifts the plan, so the plan is iterated to a fixed
+// point (conflict keys only ever get added) and every member is re-verified in the final pass.  Victims are removed
+// before the apply kernel runs, so a conflict key is simply absent when its ops are replayed.
+//
+// classify: run heads whose key is absent append their first op index (= the op that inserts the key)
+__global__ void index_classify_kernel(TableRef t, const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
+                                      int64_t n, uint32_t* __restrict__ ins_ops, unsigned long long* __restrict__ cursor) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = skey[i];
+  if (i > 0 && skey[i - 1] == key) return;
+  if (find_slot(t, key, nullptr) >= 0) return;
+  ins_ops[atomicAdd(cursor, 1ull)] = sidx[i];
+}
+
+constexpr uint32_t kUntouched = 0xffffffffu;
+
+// one window of the order array.  touch[p] = position of the record's key among the sorted batch keys (its run head:
+// the stable sort puts the key's first op there) or kUntouched; is_victim[p] = valid record that is untouched or a
+// known conflict key.  Stale records (re-stamped or removed since the order was built) are neither.
+__global__ void index_evict_flag_kernel(TableRef t, const unsigned long long* __restrict__ order_ts,
+                                        const uint32_t* __restrict__ order_slot, int64_t pos, int64_t w,
+                                        const uint64_t* __restrict__ skey, int64_t n, const uint8_t* __restrict__ conflict,
+                                        uint32_t* __restrict__ is_victim, uint32_t* __restrict__ touch) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= w) return;
+  const uint32_t s = order_slot[pos + p];
+  uint32_t vic = 0, tch = kUntouched;
+  if ((ld_meta(&t.table[s]) & 3u) == kFull && t.ts[s] == order_ts[pos + p]) {
+    const uint64_t key = ld_key(&t.table[s]);
+    int64_t lo = 0, hi = n;  // first position with skey >= key
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (skey[mid] < key) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < n && skey[lo] == key) {
+      tch = (uint32_t)lo;
+      vic = conflict[lo];
+    } else {
+      vic = 1;
+    }
+  }
+  is_victim[p] = vic;
+  touch[p] = tch;
+}
+
+// rank[p] = victims (under the current conflict set) before p in this window; `found` were taken from earlier
+// windows, `need` more are wanted.  Every touched record is decided afresh into conflict_next.
+// out[0] = records whose decision differs from the current set, out[1] = window position just past the last victim
+// taken, out[2] = victims taken here, out[3] = insertion cursor (conflict keys append their re-creating op)
+__global__ void index_evict_decide_kernel(const uint32_t* __restrict__ is_victim, const uint32_t* __restrict__ touch,
+                                          const uint32_t* __restrict__ rank, int64_t w, int64_t pos,
+                                          const uint32_t* __restrict__ order_slot, const uint32_t* __restrict__ sidx,
+                                          int64_t found, int64_t need, int64_t slack,
+                                          const uint32_t* __restrict__ ins_sorted, uint32_t* __restrict__ ins_ops,
+                                          uint8_t* __restrict__ conflict_next, uint32_t* __restrict__ victims,
+                                          unsigned long long* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= w) return;
+  const int64_t r = (int64_t)rank[p];
+  const uint32_t tch = touch[p];
+  const bool vic = is_victim[p] != 0;
+  if (r >= need) {  // past the last eviction of this batch: not looked at, so a conflict key out here stops being one
+    if (vic && tch != kUntouched) atomicAdd(&out[0], 1ull);
+    return;
+  }
+  const uint32_t evict_op = ins_sorted[slack + found + r];  // the op whose insertion evicts victim number found + r
+  if (tch != kUntouched) {
+    const bool c = sidx[tch] > evict_op;  // first touched only after the eviction reaches it
+    if (c) {
+      conflict_next[tch] = 1;
+      ins_ops[atomicAdd(&out[3], 1ull)] = sidx[tch];
+    }
+    if (c != vic) atomicAdd(&out[0], 1ull);
+  }
+  if (vic) {
+    victims[found + r] = order_slot[pos + p];
+    if (r == need - 1) out[1] = (unsigned long long)(p + 1);
+    atomicAdd(&out[2], 1ull);
+  }
+}
+
+__global__ void index_evict_apply_kernel(TableRef t, const uint32_t* __restrict__ victims, int64_t n_victims,
+                                         unsigned long long new_head, unsigned long long skipped) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_victims) return;
+  kill_slot(t, victims[i]);
+  if (i == 0) {
+    Counters& c = *t.ctr;
+    atomicAdd(&c.live, (unsigned long long)(-(long long)n_victims));
+    atomicAdd(&c.tombs, (unsigned long long)n_victims);
+    atomicAdd(&c.evicted, (unsigned long long)n_victims);
+    atomicAdd(&c.stale_skipped, skipped);
+    c.order_head = new_head;
+  }
+}
+
 // Lookup: one thread per key.  counts: -1 absent, -2 present but empty, else #entries after the pod filter.
 // stamp_base != 0: found keys are re-stamped (data.Get, in_memory.go:120) with stamp_base + position.
 __global__ void index_lookup_kernel(const Bucket* __restrict__ table, uint64_t mask, const uint64_t* __restrict__ keys,
@@ -600,6 +704,11 @@ struct kvb_index {
   uint32_t* order_slot_in = nullptr;
   int64_t order_cap = 0, order_n = 0;
   bool order_valid = false;
+  // eviction planner (parallel apply at capacity): one window of the order array at a time
+  static constexpr int64_t kWinCap = 1 << 20;
+  uint32_t *d_ins_ops = nullptr, *d_victims = nullptr, *d_win = nullptr;  // d_win: is_victim | touch | rank
+  unsigned long long* d_plan = nullptr;                                     // see index_evict_decide_kernel
+  uint8_t* d_conflict = nullptr;                                            // per sorted batch position
 
   // read scratch
   uint8_t* d_scratch = nullptr;
@@ -618,6 +727,7 @@ struct kvb_index {
 
   // statistics
   int64_t n_flush_par = 0, n_flush_seq = 0, n_rehash = 0, n_order_builds = 0, n_ops_total = 0;
+  int64_t n_flush_planned = 0, n_plan_fallbacks = 0;
 
   TableRef ref() const { return TableRef{table, ts, slots - 1, d_ctr, pods_per_key}; }
 
@@ -681,7 +791,9 @@ struct kvb_index {
   }
 
   int rehash(uint64_t new_slots);
-  int ensure_order();
+  int ensure_order(int64_t min_records = 1);
+  int ensure_sort_tmp(size_t need);
+  int plan_evictions(int64_t n, int64_t* n_victims, unsigned long long* new_head, unsigned long long* skipped, bool* ok);
   int flush_locked();
   int queue_ops(uint8_t type, const uint64_t* keys, int64_t n_keys, const kvb_pod_entry_t* entries, int32_t n_entries);
   int set_filter(const uint16_t* pods, int32_t n, uint8_t* h_stage, bool* staged, const uint32_t** out);
@@ -717,8 +829,23 @@ int kvb_index::rehash(uint64_t new_slots) {
 
 // (stamp, slot) of every live key sorted by stamp: the outer LRU order at this moment.  Later stamps only make
 // records stale, and keys inserted later are newer than every valid record, so the array serves until it runs out.
-int kvb_index::ensure_order() {
-  if (order_valid && h_ctr.order_head < (unsigned long long)order_n) return KVB_OK;
+int kvb_index::ensure_sort_tmp(size_t need) {
+  if (need <= sort_tmp_bytes) return KVB_OK;
+  if (d_sort_tmp) cudaFree(d_sort_tmp);
+  d_sort_tmp = nullptr;
+  sort_tmp_bytes = 0;
+  KVB_CUDA_TRY(cudaMalloc(&d_sort_tmp, need));
+  sort_tmp_bytes = need;
+  return KVB_OK;
+}
+
+// `min_records`: how many evictions the coming batch can ask for — an array with fewer records left is rebuilt now
+// (running out inside a batch costs a whole-table scan per eviction on the sequential path).
+int kvb_index::ensure_order(int64_t min_records) {
+  if (order_valid) {
+    const int64_t left = order_n - (int64_t)h_ctr.order_head;
+    if (left >= std::min<int64_t>(std::max<int64_t>(min_records, 1), (int64_t)h_ctr.live)) return KVB_OK;
+  }
   int rc = sync_counters();
   if (rc) return rc;
   const int64_t live = (int64_t)h_ctr.live;
@@ -750,13 +877,9 @@ int kvb_index::ensure_order() {
     size_t need = 0;
     KVB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, order_ts_in, order_ts, order_slot_in, order_slot,
                                                  (int)live, 0, 64, stream));
-    if (need > sort_tmp_bytes) {
-      if (d_sort_tmp) cudaFree(d_sort_tmp);
-      d_sort_tmp = nullptr;
-      sort_tmp_bytes = 0;
-      KVB_CUDA_TRY(cudaMalloc(&d_sort_tmp, need));
-      sort_tmp_bytes = need;
-    }
+    rc = ensure_sort_tmp(need);
+    if (rc) return rc;
+    need = sort_tmp_bytes;
     KVB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_sort_tmp, need, order_ts_in, order_ts, order_slot_in, order_slot,
                                                  (int)live, 0, 64, stream));
     count_launch();
@@ -769,6 +892,127 @@ int kvb_index::ensure_order() {
   h_ctr = c;
   order_valid = true;
   ++n_order_builds;
+  return KVB_OK;
+}
+
+// Victims of an add-only batch at capacity, planned before anything is applied (see index_classify_kernel).
+// *ok = false: the batch needs the one-thread replay (the order array cannot supply enough records even after a
+// rebuild — an index smaller than the batch — or the plan did not settle).
+int kvb_index::plan_evictions(int64_t n, int64_t* n_victims, unsigned long long* new_head, unsigned long long* skipped,
+                              bool* ok) {
+  *ok = false;
+  *n_victims = 0;
+  if (!d_ins_ops) KVB_CUDA_TRY(cudaMalloc(&d_ins_ops, 2 * kOpsCap * sizeof(uint32_t)));
+  if (!d_victims) KVB_CUDA_TRY(cudaMalloc(&d_victims, 2 * kOpsCap * sizeof(uint32_t)));
+  if (!d_win) KVB_CUDA_TRY(cudaMalloc(&d_win, 3 * kWinCap * sizeof(uint32_t)));
+  if (!d_plan) KVB_CUDA_TRY(cudaMalloc(&d_plan, 8 * sizeof(unsigned long long)));
+  if (!d_conflict) KVB_CUDA_TRY(cudaMalloc(&d_conflict, 2 * kOpsCap));
+  const unsigned threads = 128;
+  KVB_CUDA_TRY(cudaMemsetAsync(d_plan, 0, 8 * sizeof(unsigned long long), stream));
+  KVB_CUDA_TRY(cudaMemsetAsync(d_conflict, 0, (size_t)n, stream));
+  KVB_LAUNCH(index_classify_kernel, (unsigned)((n + threads - 1) / threads), threads, stream, ref(), d_skey_out,
+             d_sidx_out, n, d_ins_ops, d_plan + 3);
+  KVB_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  unsigned long long h_plan[5] = {};
+  KVB_CUDA_TRY(cudaMemcpyAsync(h_plan, d_plan, sizeof(h_plan), cudaMemcpyDeviceToHost, stream));
+  KVB_CUDA_TRY(cudaStreamSynchronize(stream));
+  const int64_t new_keys = (int64_t)h_plan[3];
+  const int64_t live0 = (int64_t)h_ctr.live;  // exact: read after the last launch that changes it
+  const int64_t slack = max_keys - live0;
+  if (new_keys - slack <= 0) {  // the batch fits: no eviction at all
+    *ok = true;
+    *new_head = h_ctr.order_head;
+    *skipped = 0;
+    return KVB_OK;
+  }
+  if (slack < 0) return KVB_OK;
+  uint32_t* ins_sorted = d_ins_ops + kOpsCap;
+  uint32_t *is_victim = d_win, *touch = d_win + kWinCap, *rank = d_win + 2 * kWinCap;
+  uint8_t *conf_cur = d_conflict, *conf_next = d_conflict + kOpsCap;
+  int64_t n_conflicts = 0;  // size of the current conflict set; its ops sit behind the new keys' in d_ins_ops
+  bool rebuilt = false;
+  for (int iter = 0; iter < 24; ++iter) {
+    const int64_t insertions = new_keys + n_conflicts;  // <= distinct keys of the batch <= kOpsCap
+    const int64_t want = insertions - slack;
+#ifdef KVB_HOST_SIM
+    std::copy(d_ins_ops, d_ins_ops + insertions, ins_sorted);
+    std::sort(ins_sorted, ins_sorted + insertions);
+#else
+    {
+      size_t need = 0;
+      KVB_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, d_ins_ops, ins_sorted, (int)insertions, 0, 32, stream));
+      int rc = ensure_sort_tmp(need);
+      if (rc) return rc;
+      need = sort_tmp_bytes;
+      KVB_CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_sort_tmp, need, d_ins_ops, ins_sorted, (int)insertions, 0, 32, stream));
+      count_launch();
+    }
+#endif
+    KVB_CUDA_TRY(cudaMemsetAsync(conf_next, 0, (size_t)n, stream));
+    h_plan[3] = (unsigned long long)new_keys;  // the next set's ops are appended from here
+    KVB_CUDA_TRY(cudaMemcpyAsync(d_plan + 3, &h_plan[3], sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    const int64_t head0 = (int64_t)h_ctr.order_head;
+    int64_t pos = head0, found = 0, end = -1, changed = 0;
+    while (found < want && pos < order_n) {
+      const int64_t w = std::min<int64_t>(order_n - pos, std::min<int64_t>(kWinCap, std::max<int64_t>(2 * (want - found), 65536)));
+      const unsigned grid = (unsigned)((w + threads - 1) / threads);
+      KVB_CUDA_TRY(cudaMemsetAsync(d_plan, 0, 3 * sizeof(unsigned long long), stream));
+      KVB_LAUNCH(index_evict_flag_kernel, grid, threads, stream, ref(), order_ts, order_slot, pos, w, d_skey_out, n,
+                 conf_cur, is_victim, touch);
+      KVB_CUDA_TRY(cudaGetLastError());
+#ifdef KVB_HOST_SIM
+      for (int64_t p = 0, acc = 0; p < w; ++p) {
+        rank[p] = (uint32_t)acc;
+        acc += is_victim[p];
+      }
+#else
+      size_t need = 0;
+      KVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, is_victim, rank, (int)w, stream));
+      int rc = ensure_sort_tmp(need);
+      if (rc) return rc;
+      need = sort_tmp_bytes;
+      KVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_sort_tmp, need, is_victim, rank, (int)w, stream));
+#endif
+      KVB_LAUNCH(index_evict_decide_kernel, grid, threads, stream, is_victim, touch, rank, w, pos, order_slot,
+                 d_sidx_out, found, want - found, slack, ins_sorted, d_ins_ops, conf_next, d_victims, d_plan);
+      KVB_CUDA_TRY(cudaGetLastError());
+      count_launch(3);
+      KVB_CUDA_TRY(cudaMemcpyAsync(h_plan, d_plan, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      KVB_CUDA_TRY(cudaStreamSynchronize(stream));
+      changed += (int64_t)h_plan[0];
+      found += (int64_t)h_plan[2];
+      if (found >= want) {
+        end = pos + (int64_t)h_plan[1];
+        break;
+      }
+      pos += w;
+    }
+    const int64_t next_conflicts = (int64_t)h_plan[3] - new_keys;
+    static const bool plan_debug = getenv("KVB_PLAN_DEBUG") != nullptr;
+    if (plan_debug)
+      fprintf(stderr, "plan n %lld new %lld slack %lld iter %d: want %lld found %lld end %lld changed %lld conflicts %lld -> %lld head %lld order_n %lld\n", (long long)n, (long long)new_keys, (long long)slack, iter,
+              (long long)want, (long long)found, (long long)end, (long long)changed, (long long)n_conflicts,
+              (long long)next_conflicts, (long long)head0, (long long)order_n);
+    if (end >= 0 && changed == 0 && next_conflicts == n_conflicts) {  // the plan reproduces itself: these are the victims
+      *ok = true;
+      *n_victims = want;
+      *new_head = (unsigned long long)end;
+      *skipped = (unsigned long long)(end - head0 - want);
+      return KVB_OK;
+    }
+    if (end < 0 && changed == 0 && next_conflicts == n_conflicts) {
+      // a settled plan that ran out of records: stale ones (lookups re-stamp keys) may have used the array up
+      if (rebuilt) return KVB_OK;
+      rebuilt = true;
+      order_valid = false;
+      int rc = ensure_order();
+      if (rc) return rc;
+      continue;
+    }
+    std::swap(conf_cur, conf_next);
+    n_conflicts = next_conflicts;
+  }
   return KVB_OK;
 }
 
@@ -791,9 +1035,14 @@ int kvb_index::flush_locked() {
     if (rc) return rc;
     may_evict = live_ub > max_keys;
   }
-  const bool sequential = may_evict || (int64_t)n_ops <= kSeqThreshold;
+  const bool small = (int64_t)n_ops <= kSeqThreshold;
+  // at capacity an add-only batch still runs in parallel, with its evictions planned up front; batches that also
+  // remove pods (live moves both ways inside the batch) replay on one thread in the reference's order
+  static const bool plan_off = getenv("KVB_INDEX_PLAN") != nullptr && getenv("KVB_INDEX_PLAN")[0] == '0';
+  bool planned = may_evict && !small && q_evicts == 0 && !plan_off;
+  bool sequential = small || (may_evict && !planned);
   if (may_evict) {
-    int rc = ensure_order();
+    int rc = ensure_order((int64_t)n_ops);
     if (rc) return rc;
   }
   KVB_CUDA_TRY(cudaMemcpyAsync(d_ops, h_ops, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, stream));
@@ -803,15 +1052,11 @@ int kvb_index::flush_locked() {
   const unsigned long long seq_base = seq;
   seq += n_ops;
   const int64_t n = (int64_t)n_ops;
-  if (sequential) {
-    KVB_LAUNCH(index_apply_seq_kernel, 1, 1, stream, ref(), d_ops, d_ents, n, seq_base, (unsigned long long)max_keys,
-               order_ts, order_slot, (unsigned long long)(may_evict ? order_n : 0));
-    KVB_CUDA_TRY(cudaGetLastError());
-    count_launch();
-    ++n_flush_seq;
-  } else {
-    const unsigned threads = 128;
-    const unsigned grid = (unsigned)((n + threads - 1) / threads);
+  const unsigned threads = 128;
+  const unsigned grid = (unsigned)((n + threads - 1) / threads);
+  int64_t n_victims = 0;
+  unsigned long long new_head = 0, skipped = 0;
+  if (!sequential) {
     KVB_LAUNCH(index_sort_keys_kernel, grid, threads, stream, d_ops, n, d_skey_in, d_sidx_in);
     KVB_CUDA_TRY(cudaGetLastError());
 #ifdef KVB_HOST_SIM
@@ -825,10 +1070,38 @@ int kvb_index::flush_locked() {
       return KVB_ERR_CUDA;
     }
 #endif
+    count_launch(2);
+    if (planned) {
+      bool ok = false;
+      int rc = plan_evictions(n, &n_victims, &new_head, &skipped, &ok);
+      if (rc) return rc;
+      if (!ok) {
+        sequential = true;
+        planned = false;
+        ++n_plan_fallbacks;
+      }
+    }
+  }
+  if (sequential) {
+    KVB_LAUNCH(index_apply_seq_kernel, 1, 1, stream, ref(), d_ops, d_ents, n, seq_base, (unsigned long long)max_keys,
+               order_ts, order_slot, (unsigned long long)(may_evict ? order_n : 0));
+    KVB_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    ++n_flush_seq;
+  } else {
+    if (planned) {  // victims go first: a conflict key must be absent when its ops are replayed
+      ++n_flush_planned;
+      if (n_victims > 0) {
+        KVB_LAUNCH(index_evict_apply_kernel, (unsigned)((n_victims + threads - 1) / threads), threads, stream, ref(),
+                   d_victims, n_victims, new_head, skipped);
+        KVB_CUDA_TRY(cudaGetLastError());
+        count_launch();
+      }
+    }
     KVB_LAUNCH(index_apply_par_kernel, grid, threads, stream, ref(), d_ops, d_ents, d_skey_out, d_sidx_out, n,
                seq_base);
     KVB_CUDA_TRY(cudaGetLastError());
-    count_launch(3);
+    count_launch();
     ++n_flush_par;
   }
   n_ops_total += n;
@@ -1009,7 +1282,8 @@ void kvb_index_destroy(kvb_index_t* idx) {
                   (void*)idx->d_ents, (void*)idx->d_skey_in, (void*)idx->d_skey_out, (void*)idx->d_sidx_in,
                   (void*)idx->d_sidx_out, idx->d_sort_tmp, (void*)idx->order_ts, (void*)idx->order_slot,
                   (void*)idx->order_ts_in, (void*)idx->order_slot_in, (void*)idx->d_cursor, (void*)idx->d_scratch,
-                  (void*)idx->d_filter, (void*)idx->d_done})
+                  (void*)idx->d_filter, (void*)idx->d_done, (void*)idx->d_ins_ops, (void*)idx->d_victims,
+                  (void*)idx->d_win, (void*)idx->d_plan, (void*)idx->d_conflict})
     if (p) cudaFree(p);
   for (void* p : {(void*)idx->h_ops, (void*)idx->h_ents, (void*)idx->h_scratch, (void*)idx->h_done})
     if (p) cudaFreeHost(p);
@@ -1252,6 +1526,8 @@ int kvb_index_get_stats(kvb_index_t* idx, kvb_index_stats_t* out) {
     out->ops_applied = idx->n_ops_total;
     out->flushes_parallel = idx->n_flush_par;
     out->flushes_sequential = idx->n_flush_seq;
+    out->flushes_planned = idx->n_flush_planned;
+    out->plan_fallbacks = idx->n_plan_fallbacks;
     out->rehashes = idx->n_rehash;
     out->lru_evictions = (int64_t)idx->h_ctr.evicted;
     out->order_builds = idx->n_order_builds;

@@ -327,6 +327,46 @@ def test_device_side_build_uses_the_parallel_path(kvb, torch_cuda):
     assert _as_tuples(idx.lookup(sample)) == _as_tuples(oidx.lookup(sample))
 
 
+def test_at_capacity_add_only_batches_are_planned_on_the_device(kvb, torch_cuda):
+    """The scenarios of tests/test_index_sim.py on the real kernels (cub sort / scan, atomics): add-only batches into a
+    full index are applied in parallel with the LRU victims planned up front, reads equal the oracle's at every step."""
+    from tests.test_index_sim import _random_traffic
+    st = _random_traffic(kvb, kvb.lib, seed=21, size=1500, ppk=3, n_keys=5000, steps=400, max_batch=400, lookup_frac=0.4,
+                         evict_frac=0.0)
+    assert st["flushes_planned"] > 50 and st["plan_fallbacks"] == 0 and st["lru_evictions"] > 10000, st
+    st = _random_traffic(kvb, kvb.lib, seed=22, size=700, ppk=2, n_keys=900, steps=500, max_batch=120, lookup_frac=0.5,
+                         evict_frac=0.02)
+    assert st["flushes_planned"] > 50, st
+    st = _random_traffic(kvb, kvb.lib, seed=5, size=3, ppk=2, n_keys=60, steps=300, max_batch=40)   # index smaller than a batch
+    assert st["live_keys"] <= 3
+
+
+def test_planned_eviction_walks_several_windows_of_stale_records(kvb, torch_cuda):
+    """200 000 keys at capacity; a lookup re-stamps the 150 000 oldest, so the order array starts with 150 000 stale
+    records (more than two planning windows) before the first real victim."""
+    K = kvb.kvblock
+    n = 200_000
+    keys = np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    idx, oidx = K.Index(size=n, pod_cache_size=2, expected_keys=n), o.InMemoryIndex(size=n, pod_cache_size=2)
+    ent, oent = [K.PodEntry("a", "gpu")], [o.PodEntry("a", "gpu")]
+    idx.add(None, keys, ent)
+    oidx.add(None, [int(k) for k in keys], oent)
+    idx.flush()
+    idx.add(None, keys[:1] + np.uint64(1), ent)              # at capacity from here: builds the order array
+    oidx.add(None, [int(keys[0] + np.uint64(1))], oent)
+    assert len(idx.lookup(keys[1:150_001])) == 150_000       # refresh: their order records are stale now
+    oidx.lookup([int(k) for k in keys[1:150_001]])
+    new = keys[:20_000] + np.uint64(7)
+    idx.add(None, new, ent)
+    oidx.add(None, [int(k) for k in new], oent)
+    st = idx.stats()
+    assert st["flushes_planned"] >= 1 and st["plan_fallbacks"] == 0 and st["lru_evictions"] == 20_001, st
+    assert st["order_stale_skipped"] >= 150_000
+    probe = np.concatenate([keys[:2], keys[149_990:150_010], keys[169_990:170_020], keys[-5:], new[:5]])
+    assert _as_tuples(idx.lookup(probe)) == _as_tuples(oidx.lookup([int(k) for k in probe]))
+    assert len(idx) == len(oidx.data) == n
+
+
 @pytest.mark.parametrize("bs", [4, 8, 16, 5, 32])
 def test_fused_scoring_every_block_size_and_shape(kvb, torch_cuda, bs):
     """The fused tokens -> scores launch (block sizes 4 / 8 / 16) and the two-kernel form (any other size) against the oracle:

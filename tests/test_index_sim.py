@@ -36,7 +36,7 @@ def _as_tuples(d):
     return {int(k): [(e.pod_identifier, e.device_tier, bool(e.speculative)) for e in v] for k, v in d.items()}
 
 
-def _random_traffic(kvb, lib, seed, size, ppk, n_keys, steps, max_batch, lookup_frac=0.35):
+def _random_traffic(kvb, lib, seed, size, ppk, n_keys, steps, max_batch, lookup_frac=0.35, evict_frac=0.2):
     K = kvb.kvblock
     rng = np.random.default_rng(seed)
     idx = K.Index(size=size, pod_cache_size=ppk, expected_keys=16, lib=lib)
@@ -46,7 +46,7 @@ def _random_traffic(kvb, lib, seed, size, ppk, n_keys, steps, max_batch, lookup_
     keyspace = [int(x) for x in rng.integers(1, 1 << 63, n_keys)]
     for step in range(steps):
         op = rng.random()
-        if op < 1.0 - lookup_frac - 0.2:
+        if op < 1.0 - lookup_frac - evict_frac:
             n = int(rng.integers(1, max_batch + 1))
             rks = [keyspace[int(i)] for i in rng.integers(0, len(keyspace), n)]
             mode = rng.integers(0, 3)
@@ -114,6 +114,68 @@ def test_capacity_crossing_mixed_paths(sim):
     kvb, lib = sim
     st = _random_traffic(kvb, lib, seed=11, size=2000, ppk=3, n_keys=6000, steps=300, max_batch=300, lookup_frac=0.3)
     assert st["flushes_parallel"] > 0 and st["flushes_sequential"] > 0 and st["lru_evictions"] > 0
+
+
+def test_at_capacity_add_only_batches_are_planned_in_parallel(sim):
+    """Add-only batches of up to 400 keys into a full index: the victims are planned before the parallel apply and the
+    result is the reference's one-at-a-time LRU, lookups (which re-stamp keys and leave stale order records) included."""
+    kvb, lib = sim
+    st = _random_traffic(kvb, lib, seed=21, size=1500, ppk=3, n_keys=5000, steps=400, max_batch=400, lookup_frac=0.4,
+                         evict_frac=0.0)
+    assert st["flushes_planned"] > 20 and st["lru_evictions"] > 1000
+    st = _random_traffic(kvb, lib, seed=22, size=700, ppk=2, n_keys=900, steps=500, max_batch=120, lookup_frac=0.5,
+                         evict_frac=0.02)   # small key space: old keys are re-announced all the time
+    assert st["flushes_planned"] > 20
+
+
+def test_planned_eviction_conflicts_and_survivors(sim):
+    """The two cases the plan must tell apart (in_memory.go:186-199): an old key announced BEFORE the insertion that
+    would have evicted it moves to the newest end and survives; announced AFTER, the reference evicts it and then
+    re-creates it with only the new entry (one more insertion, so one more eviction) — the plan absorbs it."""
+    kvb, lib = sim
+    K = kvb.kvblock
+    for late in (False, True):
+        idx, oidx = K.Index(size=100, pod_cache_size=4, expected_keys=16, lib=lib), o.InMemoryIndex(size=100, pod_cache_size=4)
+        for i in range(100):
+            idx.add(None, [1000 + i], [K.PodEntry("old", "gpu")])
+            oidx.add(None, [1000 + i], [o.PodEntry("old", "gpu")])
+        idx.flush()
+        new = list(range(5000, 5050))
+        batch = new + [1010] if late else [1040] + new
+        idx.add(None, batch, [K.PodEntry("new", "cpu")])
+        oidx.add(None, batch, [o.PodEntry("new", "cpu")])
+        probe = list(range(1000, 1100)) + new
+        assert _as_tuples(idx.lookup(probe)) == _as_tuples(oidx.lookup(probe))
+        st = idx.stats()
+        assert st["plan_fallbacks"] == 0 and st["flushes_planned"] == 1 and st["lru_evictions"] == (51 if late else 50)
+        if late:
+            assert _as_tuples(idx.lookup([1010])) == {1010: [("new", "cpu", False)]}
+        else:
+            assert len(idx.lookup([1040])[1040]) == 2 and idx.lookup([1050]) == {}
+        idx.close()
+
+
+def test_planned_eviction_rebuilds_a_used_up_order(sim):
+    """Lookups re-stamp most keys after the order array was built: its records go stale, the plan runs out of
+    untouched records, rebuilds the order once and finishes in parallel."""
+    kvb, lib = sim
+    K = kvb.kvblock
+    idx, oidx = K.Index(size=400, pod_cache_size=2, expected_keys=16, lib=lib), o.InMemoryIndex(size=400, pod_cache_size=2)
+    keys = list(range(1, 401))
+    for blk in (keys[:200], keys[200:]):
+        idx.add(None, blk, [K.PodEntry("a", "gpu")])
+        oidx.add(None, blk, [o.PodEntry("a", "gpu")])
+    idx.flush()
+    idx.add(None, list(range(1000, 1020)), [K.PodEntry("b", "gpu")])       # first eviction: builds the order array
+    oidx.add(None, list(range(1000, 1020)), [o.PodEntry("b", "gpu")])
+    assert _as_tuples(idx.lookup(keys[20:390])) == _as_tuples(oidx.lookup(keys[20:390]))   # ... and makes it stale
+    idx.add(None, list(range(2000, 2100)), [K.PodEntry("c", "gpu")])
+    oidx.add(None, list(range(2000, 2100)), [o.PodEntry("c", "gpu")])
+    probe = keys + list(range(1000, 1020)) + list(range(2000, 2100))
+    assert _as_tuples(idx.lookup(probe)) == _as_tuples(oidx.lookup(probe))
+    st = idx.stats()
+    assert (st["flushes_planned"], st["plan_fallbacks"]) == (2, 0) and st["order_builds"] >= 2, st
+    idx.close()
 
 
 def test_contract_scenarios_on_the_sim(sim):
