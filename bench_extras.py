@@ -638,7 +638,8 @@ def run_index_configs(kvb):
                         "cpu_c_restatement_1_thread_s": t_build_cpu, "where": "Add/Evict applied by kernels, no host copy"},
     }
 
-    # ---- the index AT CAPACITY: exact-LRU eviction, ops replayed in the reference's order by one thread
+    # ---- the index AT CAPACITY: exact-LRU eviction; an add-only batch is applied in parallel with its victims planned up
+    # front ("Planned")
     cap = 1 << 20
     idx_c = K.Index(size=cap, expected_keys=cap)
     fill = rng.integers(1, 1 << 62, cap + 200_000, dtype=np.int64).astype(np.uint64)
@@ -655,6 +656,7 @@ def run_index_configs(kvb):
     assert set(int(k) for k in survivors) == {int(fill[200_000]), int(fill[cap - 1]), int(fill[cap]), int(fill[cap + 199_999])}
     cfg5["index_at_capacity"] = {"size": cap, "new_keys": 200_000, "seconds": t_cap, "keys_per_s": 200_000 / t_cap,
                                  "lru_evictions": st_c["lru_evictions"], "order_builds": st_c["order_builds"],
+                                 "flushes_planned": st_c["flushes_planned"], "plan_fallbacks": st_c["plan_fallbacks"],
                                  "exact": "the 200 000 oldest keys were evicted, in insertion order (checked on the boundaries)"}
     idx_c.close()
 
