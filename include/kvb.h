@@ -198,10 +198,11 @@ int kvb_init_hash(int device, uint64_t seed_hash, const char* model_name, size_t
 int kvb_hash_token_blocks(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
                           int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
                           uint64_t* out_keys, int64_t* out_key_off, void* stream);
-/* device-resident variant: every pointer is a DEVICE pointer, key_off precomputed; no host sync */
+/* device-resident variant: every pointer is a DEVICE pointer, key_off precomputed; no host sync.
+ * total_keys = key_off[n_prompts] if the caller knows it (small batches then use the table kernel), else -1 */
 int kvb_hash_token_blocks_dev(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
                               int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
-                              uint64_t* out_keys, const int64_t* key_off, void* stream);
+                              uint64_t* out_keys, const int64_t* key_off, int64_t total_keys, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Block index + longest-prefix scorer

@@ -98,7 +98,7 @@ SIGNATURES = {
     "kvb_fnv64a": (_u64, [_vp, C.c_size_t]),
     "kvb_init_hash": (C.c_int, [C.c_int, _u64, C.c_char_p, C.c_size_t, _P(_u64)]),
     "kvb_hash_token_blocks": (C.c_int, [C.c_int, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "kvb_hash_token_blocks_dev": (C.c_int, [C.c_int, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "kvb_hash_token_blocks_dev": (C.c_int, [C.c_int, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, C.c_int64, _vp]),
     "kvb_index_create": (C.c_int, [C.c_int, _i64, _i32, _i64, _P(_vp)]),
     "kvb_index_destroy": (None, [_vp]),
     "kvb_index_set_tier_weight": (C.c_int, [_vp, C.c_uint8, C.c_double, C.c_int]),

@@ -685,6 +685,10 @@ __device__ __forceinline__ void st_release_cta(int* p, int v) {
 __device__ __forceinline__ void chain_signal_done(const ChainArgs& A) {
   if (A.done_counter == nullptr) return;
   __threadfence_system();  // this prompt's results (possibly written to pinned host memory) before the count
+  if (A.done_target == 1u) {  // one prompt: nobody to count
+    *reinterpret_cast<volatile unsigned long long*>(A.done_flag_host) = A.done_value;
+    return;
+  }
   const unsigned prev = atomicAdd(A.done_counter, 1u);
   if (prev + 1u == A.done_target) {
     *A.done_counter = 0u;  // ready for the next call (stream order: no other launch touches it before this one ends)
@@ -1097,6 +1101,448 @@ bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_siz
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// "Spec" kernel for small batches: take the token bytes OFF the chain.
+//
+// FNV-1a is  h <- (h ^ b) * P.  The xor touches only the low byte, and the low byte of a product depends only on the
+// low bytes of its factors, so with h = u + l (l = low byte, u = the rest):
+//     fold(h, bytes[0..m)) = u * P^m + fold(l, bytes[0..m))                                    (mod 2^64, exactly)
+// A block's byte stream is  83 | U(parent) | tail  where  tail = array-head(bs) | tokens | extra  does not depend on
+// the chain.  So fold(v, tail) is tabulated for all 256 values of v — 256 independent plain FNV runs per block, in
+// parallel over every block of every prompt (phase A: one 256-thread CTA per block) — and the serial chain per block
+// shrinks to the 10 prefix bytes plus one table look-up and one multiply by P^m (phase B: one thread per prompt):
+// ~170 cycles per block instead of ~1000 for the vote rounds.  The price is 256x the byte work, which idle SMs absorb
+// for small batches only (the vote kernels stay the choice from a few dozen prompts up).
+constexpr int kSpecThreads = 256;
+constexpr int kSpecPassRows = 20;   // table rows (blocks) per staging buffer; two buffers: 2 x 20 x 2 KiB
+constexpr int kSpecChunk = 640;     // tail bytes staged per round (128 tokens x 5 B)
+constexpr int kSpecMaxPrompts = 64;
+constexpr int kSpecAutoPrompts = 16;  // chosen without being asked for up to this many prompts
+constexpr int kSpecKeyRing = 64;
+
+struct SpecArgs {
+  int32_t n_prompts, block_size;
+  int64_t total_keys;
+  uint64_t* table;  // [total_keys][256]  fold(v, tail_k)
+  uint64_t* pm;     // [total_keys]       P^len(tail_k)
+  unsigned* done;   // [n_prompts] tables finished per prompt; zero at launch, reset by the prompt's CTA
+  // up to kSpecAutoPrompts prompts travel in the launch arguments (no array to fetch before the first table can start —
+  // the fused call keeps these arrays in pinned HOST memory, a PCIe round trip per dependent read)
+  int32_t inl;
+  int64_t koff[kSpecAutoPrompts + 1], poff[kSpecAutoPrompts + 1];
+  uint64_t par[kSpecAutoPrompts];
+};
+
+__device__ __forceinline__ uint64_t pow_prime(uint32_t e) {
+  uint64_t r = 1, b = kFnvPrime;
+  while (e) {
+    if (e & 1u) r *= b;
+    b *= b;
+    e >>= 1;
+  }
+  return r;
+}
+
+// all threads fold the n staged bytes (same bytes for every thread: shared-memory broadcasts)
+__device__ __forceinline__ void spec_fold_chunk(Fnv& h, const uint32_t* words, int n) {
+  const int nw = n >> 2;
+  int i = 0;
+  for (; i + 4 <= nw; i += 4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(words + i);
+    fold4(h, q.x);
+    fold4(h, q.y);
+    fold4(h, q.z);
+    fold4(h, q.w);
+  }
+  for (; i < nw; ++i) fold4(h, words[i]);
+  const int tail = n & 3;
+  if (tail) {
+    const uint32_t tw = words[nw];
+    fold(h, tw & 0xffu);
+    if (tail > 1) fold(h, (tw >> 8) & 0xffu);
+    if (tail > 2) fold(h, (tw >> 16) & 0xffu);
+  }
+}
+
+constexpr uint64_t kSpecAfter831b = (((kFnvOffset ^ 0x83ull) * kFnvPrime) ^ 0x1bull) * kFnvPrime;  // state after 83 1b
+
+__device__ __forceinline__ void spec_wait_ge(const int* p, int v) {
+  while (ld_acquire_cta(p) < v) __nanosleep(20);
+}
+
+// A: the chain kernel's arguments (tokens may be pinned host memory read in place; `single` = one prompt whose offsets
+// travel in the arguments; SCORE adds lookup + longest-prefix scores by a scorer warp that follows the chain)
+template <bool SCORE>
+__global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs A, const SpecArgs X) {
+  extern __shared__ __align__(16) uint8_t spec_smem[];
+  __shared__ int s_scan[kSpecThreads / 32];
+  __shared__ int s_n;
+  __shared__ int loaded, chained, folded, scored;  // passes staged / passes consumed / keys produced / keys consumed
+  __shared__ uint64_t skeys[SCORE ? kSpecKeyRing : 1];
+  __shared__ Bucket tile[SCORE ? 32 : 1];
+  __shared__ int64_t s_koff[kSpecMaxPrompts + 1], s_poff[kSpecMaxPrompts + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bs = X.block_size;
+  if (!A.single) {  // prompt and key offsets: one parallel fetch (launch arguments, or one read of the arrays)
+    for (int i = tid; i <= X.n_prompts; i += kSpecThreads) {
+      s_koff[i] = X.inl ? X.koff[i] : A.key_off[i];
+      s_poff[i] = X.inl ? X.poff[i] : A.prompt_off[i];
+    }
+    __syncthreads();
+  }
+#ifdef KVB_HASH_PROFILE
+#define SPROF(slot) do { if (blockIdx.x == 0) g_hash_prof[slot] = clock64(); } while (0)
+  if (tid == 0) SPROF(0);
+#else
+#define SPROF(slot) do { } while (0)
+#endif
+
+  // ---- phase A: tables.  Task k = key k of the batch (prompt p, block i), strided over the grid.
+  uint8_t* stage = spec_smem;  // <= 5 + kSpecChunk bytes
+  for (int64_t k = blockIdx.x; k < X.total_keys; k += gridDim.x) {
+    int p = 0;
+    int64_t i = k, tok0 = 0;
+    if (!A.single) {
+      int lo = 0, hi = X.n_prompts;  // p = last prompt with key_off[p] <= k
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_koff[mid] <= k) lo = mid;
+        else hi = mid;
+      }
+      p = lo;
+      i = k - s_koff[p];
+      tok0 = s_poff[p];
+    }
+    const uint32_t* tk = A.tokens + tok0 + i * bs;
+    Fnv h{(uint32_t)tid, 0u};
+    uint32_t m = 0;
+    for (int t0 = 0; t0 < bs; t0 += 128) {
+      // stage: [array head, first round only] + up to 128 tokens, compacted by a CTA-wide prefix sum of the lengths
+      const int nt = min(128, bs - t0);
+      int len = 0;
+      uint32_t head = 0, pay = 0;
+      if (tid < nt) {
+        const uint32_t t = __ldg(tk + t0 + tid);
+        const bool ge24 = t >= 24u, ge256 = t >= 0x100u, ge64k = t >= 0x10000u;
+        head = ge64k ? 0x1au : (ge256 ? 0x19u : (ge24 ? 0x18u : t));
+        pay = ge64k ? t : (ge256 ? (t << 16) : (t << 24));
+        len = ge64k ? 5 : (ge256 ? 3 : (ge24 ? 2 : 1));
+      }
+      int incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; ++w) base += s_scan[w];
+      int hl = 0;  // array head in front of the first round's tokens
+      if (t0 == 0) hl = bs < 24 ? 1 : (bs < 256 ? 2 : (bs < 65536 ? 3 : 5));
+      const int at = hl + base + incl - len;
+      if (tid < nt) {
+        stage[at] = (uint8_t)head;
+        if (len > 1) stage[at + 1] = (uint8_t)(pay >> 24);
+        if (len > 2) stage[at + 2] = (uint8_t)(pay >> 16);
+        if (len > 3) {
+          stage[at + 3] = (uint8_t)(pay >> 8);
+          stage[at + 4] = (uint8_t)pay;
+        }
+      }
+      if (tid == 0) {
+        if (t0 == 0) {
+          if (bs < 24) {
+            stage[0] = (uint8_t)(0x80u | bs);
+          } else if (bs < 256) {
+            stage[0] = 0x98u;
+            stage[1] = (uint8_t)bs;
+          } else if (bs < 65536) {
+            stage[0] = 0x99u;
+            stage[1] = (uint8_t)(bs >> 8);
+            stage[2] = (uint8_t)bs;
+          } else {
+            stage[0] = 0x9au;
+            stage[1] = (uint8_t)(bs >> 24);
+            stage[2] = (uint8_t)(bs >> 16);
+            stage[3] = (uint8_t)(bs >> 8);
+            stage[4] = (uint8_t)bs;
+          }
+        }
+        int total = hl;
+        for (int w = 0; w < kSpecThreads / 32; ++w) total += s_scan[w];
+        s_n = total;
+      }
+      __syncthreads();
+      const int n = s_n;
+      spec_fold_chunk(h, reinterpret_cast<const uint32_t*>(stage), n);
+      m += (uint32_t)n;
+      __syncthreads();
+    }
+    // extra: pre-encoded X(extra_k) (extra_keys.go) or CBOR null
+    int64_t e0 = 0, e1 = 0;
+    if (A.extra_off != nullptr) {
+      e0 = A.extra_off[k];
+      e1 = A.extra_off[k + 1];
+    }
+    if (e1 > e0) {
+      for (int64_t e = e0; e < e1; e += kSpecChunk) {
+        const int n = (int)min((int64_t)kSpecChunk, e1 - e);
+        for (int j = tid; j < n; j += kSpecThreads) stage[j] = A.extra[e + j];
+        __syncthreads();
+        spec_fold_chunk(h, reinterpret_cast<const uint32_t*>(stage), n);
+        m += (uint32_t)n;
+        __syncthreads();
+      }
+    } else {
+      fold(h, 0xf6u);
+      m += 1;
+    }
+    X.table[k * 256 + tid] = fnv_value(h);
+    if (tid == 0) X.pm[k] = pow_prime(m);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(&X.done[p], 1u);
+  }
+
+  if (tid == 0) SPROF(1);
+  // ---- phase B: CTA p follows prompt p.  Every CTA of the grid is resident (the host sizes the grid for that), so the
+  // tables this CTA waits for are being produced.  Lane 0 of warp 0 walks the chain, warp 1 scores behind it, warps 2..7
+  // stage the table rows (two buffers of kSpecPassRows rows, cp.async) ahead of it.
+  const int p = blockIdx.x;
+  if (p >= X.n_prompts) return;
+  const int64_t k0 = A.single ? 0 : s_koff[p];
+  const int nblk = A.single ? (int)(A.single_tokens / bs) : (int)(s_koff[p + 1] - k0);
+  if (nblk == 0) {
+    if (SCORE && tid == 0) {
+      A.out_n[p] = 0;
+      chain_signal_done(A);
+    }
+    return;
+  }
+  if (tid == 0) {
+    loaded = 0;
+    chained = 0;
+    folded = 0;
+    scored = 0;
+  }
+  __syncthreads();
+  uint64_t* rows = reinterpret_cast<uint64_t*>(spec_smem);                    // [2][kSpecPassRows][256]
+  uint64_t* pms = rows + (size_t)2 * kSpecPassRows * 256;                      // [2][kSpecPassRows]
+  const int npass = (nblk + kSpecPassRows - 1) / kSpecPassRows;
+
+  if (warp >= 2) {
+    // ------------------------------------------------------------------------------------------------ loaders
+    const int lt = tid - 64;
+    constexpr int kLoaders = kSpecThreads - 64;
+    if (lt == 0) {
+      const volatile unsigned* d = X.done + p;
+      while (*d < (unsigned)nblk) __nanosleep(50);
+      __threadfence();
+      SPROF(2);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kLoaders));
+    for (int q = 0; q < npass; ++q) {
+      if (q >= 2) {
+        if (lt == 0) spec_wait_ge(&chained, q - 1);  // buffer q & 1 was last used by pass q - 2
+        asm volatile("bar.sync 1, %0;" ::"n"(kLoaders));
+      }
+      const int b0 = q * kSpecPassRows, cnt = min(kSpecPassRows, nblk - b0);
+      const uint4* src = reinterpret_cast<const uint4*>(X.table + (k0 + b0) * 256);
+      uint64_t* buf = rows + (size_t)(q & 1) * kSpecPassRows * 256;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf);
+      for (int j = lt; j < cnt * 128; j += kLoaders)  // .cg: the rows were written by other SMs (L2, never this SM's L1)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * j), "l"(src + j) : "memory");
+      if (lt < cnt) pms[(q & 1) * kSpecPassRows + lt] = __ldcg(X.pm + k0 + b0 + lt);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __threadfence_block();
+      asm volatile("bar.sync 1, %0;" ::"n"(kLoaders));
+      if (lt == 0) st_release_cta(&loaded, q + 1);
+      if (lt == 0 && q == 0) SPROF(3);
+    }
+    if (lt == 0) X.done[p] = 0u;  // ready for the next launch
+    return;
+  }
+
+  if (warp == 1) {
+    if (!SCORE) return;
+    // ------------------------------------------------------------------------------------------------ scorer
+    ScoreWalker wk;
+    for (int base = 0; base < nblk;) {
+      const int want = min(A.score_min_batch, nblk - base);
+      int avail;
+      while ((avail = ld_acquire_cta(&folded) - base) < want) __nanosleep(40);
+      const int in_tile = min(avail, 32);
+      const uint64_t key = lane < in_tile ? skeys[(base + lane) & (kSpecKeyRing - 1)] : 0ull;
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(&scored) = base + in_tile;  // the ring slots may be reused
+      if (lane == 0 && base == 0) SPROF(7);
+      if (wk.chain_alive || A.ts != nullptr)
+        wk.tile(A.table, A.mask, tile, key, lane < in_tile, base, in_tile, A.filter_bits, A.tier_w, A.ts,
+                A.stamp_base + (unsigned long long)(k0 + base + lane));
+      if (lane == 0 && base == 0) SPROF(8);
+      base += in_tile;
+    }
+    if (lane == 0) SPROF(9);
+    wk.finish(p, A.out_n, A.out_pods, A.out_scores);
+    __syncwarp();
+    if (lane == 0) SPROF(10);
+    if (lane == 0) chain_signal_done(A);
+    if (lane == 0) SPROF(6);
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------------------------- chain
+  if (lane != 0) return;
+  uint64_t parent = A.single ? A.single_parent : (X.inl ? X.par[p] : A.parents[p]);
+  for (int q = 0; q < npass; ++q) {
+    spec_wait_ge(&loaded, q + 1);
+    if (q == 0) SPROF(4);
+    const int b0 = q * kSpecPassRows, cnt = min(kSpecPassRows, nblk - b0);
+    const uint64_t* rowp = rows + (size_t)(q & 1) * kSpecPassRows * 256;
+    const uint64_t* pq = pms + (q & 1) * kSpecPassRows;
+    uint64_t pm_next = pq[0];
+    for (int b = 0; b < cnt; ++b, rowp += 256) {
+      const uint64_t pm = pm_next;
+      if (b + 1 < cnt) pm_next = pq[b + 1];  // off the chain: fetched a block early
+      Fnv h;
+      if (parent >= 0x100000000ull) {  // U(parent) is the 9-byte form: 83 1b are constants, 8 bytes to fold
+        h = Fnv{(uint32_t)kSpecAfter831b, (uint32_t)(kSpecAfter831b >> 32)};
+        fold4(h, __byte_perm((uint32_t)(parent >> 32), 0u, 0x0123));  // most significant byte first
+        fold4(h, __byte_perm((uint32_t)parent, 0u, 0x0123));
+      } else {
+        h = fnv_init();
+        fold(h, 0x83u);
+        fold_head64(h, 0x00u, parent);
+      }
+      const uint32_t l = h.lo & 0xffu;
+      const uint64_t u = ((uint64_t)h.hi << 32) | (h.lo ^ l);  // the state with its low byte cleared
+      parent = u * pm + rowp[l];
+      const int kb = b0 + b;
+      if (A.out_keys != nullptr) A.out_keys[k0 + kb] = parent;
+      if (SCORE) {
+        if (kb >= kSpecKeyRing) spec_wait_ge(&scored, kb - kSpecKeyRing + 1);
+        skeys[kb & (kSpecKeyRing - 1)] = parent;
+        // plain store behind the key's (one thread, shared memory: performed in order); a release would put a CTA-wide
+        // memory barrier on the chain for every block
+        *reinterpret_cast<volatile int*>(&folded) = kb + 1;
+      }
+    }
+    st_release_cta(&chained, q + 1);
+  }
+  SPROF(5);
+#undef SPROF
+}
+
+// per-device scratch of the spec kernel (tables are 2 KiB per key)
+struct SpecScratch {
+  std::mutex mu;
+  uint8_t* d = nullptr;
+  size_t cap = 0;
+  unsigned* done = nullptr;
+  int max_grid = 0;
+};
+// one scratch per (device, stream): launches on one stream run in order, so the next launch may reuse the tables;
+// launches on different streams (two indexes, the hash entry points) must not share them
+static SpecScratch& spec_scratch(int device, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, std::unique_ptr<SpecScratch>> all;
+  std::lock_guard<std::mutex> lk(mu);
+  auto& p = all[std::make_pair(device, s)];
+  if (!p) p.reset(new SpecScratch());
+  return *p;
+}
+constexpr size_t kSpecSmem = (size_t)2 * kSpecPassRows * 256 * 8 + (size_t)2 * kSpecPassRows * 8;
+constexpr int64_t kSpecMaxKeys = 16384;  // 32 MiB of tables
+
+// true if the batch was handed to the spec kernel (*rc_out tells how that went); false = not applicable, the caller
+// picks another kernel.
+static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int32_t block_size, int64_t total_keys,
+                        cudaStream_t s, int* rc_out, const int64_t* h_prompt_off = nullptr,
+                        const int64_t* h_key_off = nullptr, const uint64_t* h_parents = nullptr) {
+  *rc_out = KVB_OK;
+  if (n_prompts > kSpecMaxPrompts || total_keys <= 0 || total_keys > kSpecMaxKeys) return false;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SpecScratch& sc = spec_scratch(dev, s);
+  std::lock_guard<std::mutex> lk(sc.mu);
+  auto fail = [&](const char* what, cudaError_t e) {
+    set_error("hash (spec kernel): %s: %s", what, cudaGetErrorString(e));
+    *rc_out = KVB_ERR_CUDA;
+    return true;
+  };
+  if (sc.max_grid == 0) {
+    cudaError_t e = cudaFuncSetAttribute(hash_spec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(hash_spec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
+    if (e != cudaSuccess) return fail("shared memory opt-in", e);
+    int per_sm = 0, per_sm2 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_spec_kernel<false>, kSpecThreads, kSpecSmem);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hash_spec_kernel<true>, kSpecThreads, kSpecSmem);
+    if (e != cudaSuccess || per_sm < 1 || per_sm2 < 1) return fail("occupancy query", e);
+    e = cudaMalloc(&sc.done, kSpecMaxPrompts * sizeof(unsigned));
+    if (e != cudaSuccess) return fail("counters", e);
+    cudaMemset(sc.done, 0, kSpecMaxPrompts * sizeof(unsigned));
+    sc.max_grid = std::min(per_sm, per_sm2) * sm_count(dev);  // every CTA resident: the chains wait for the tables
+  }
+  const size_t need = (size_t)total_keys * (256 + 1) * 8;
+  if (need > sc.cap) {
+    cudaStreamSynchronize(s);  // an earlier launch may still read the old tables
+    if (sc.d) cudaFree(sc.d);
+    sc.d = nullptr;
+    sc.cap = 0;
+    const size_t cap = std::max<size_t>(need * 3 / 2, 4 << 20);
+    cudaError_t e = cudaMalloc(&sc.d, cap);
+    if (e != cudaSuccess) return fail("table scratch", e);
+    sc.cap = cap;
+  }
+  SpecArgs x{};
+  x.n_prompts = n_prompts;
+  x.block_size = block_size;
+  x.total_keys = total_keys;
+  x.table = reinterpret_cast<uint64_t*>(sc.d);
+  x.pm = x.table + (size_t)total_keys * 256;
+  x.done = sc.done;
+  if (h_prompt_off && h_key_off && h_parents && n_prompts <= kSpecAutoPrompts) {  // host copies at hand: in the arguments
+    x.inl = 1;
+    for (int i = 0; i <= n_prompts; ++i) {
+      x.koff[i] = h_key_off[i];
+      x.poff[i] = h_prompt_off[i];
+    }
+    for (int i = 0; i < n_prompts; ++i) x.par[i] = h_parents[i];
+  }
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(total_keys, n_prompts), sc.max_grid);
+  if (score) hash_spec_kernel<true><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x);
+  else hash_spec_kernel<false><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch", e);
+  count_launch();
+  return true;
+}
+
+static bool spec_wanted(int32_t n_prompts) {
+  // KVB_HASH_KERNEL=spec forces the table kernel for every batch it can take; any other forced family or KVB_HASH_SPEC=0
+  // keeps it out; by default it takes the batches it wins on
+  const char* f0 = std::getenv("KVB_HASH_KERNEL");
+  const char* s0 = std::getenv("KVB_HASH_SPEC");
+  if (f0 != nullptr) return std::strcmp(f0, "spec") == 0;
+  return !(s0 && s0[0] == '0') && n_prompts <= kSpecAutoPrompts;
+}
+
+// fused tokens -> scores for small batches (see launch_chain_score); false = not applicable
+bool launch_spec_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, int64_t total_keys, cudaStream_t s,
+                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents) {
+  *rc_out = KVB_OK;
+  if (!spec_wanted(n_prompts)) return false;
+  // this chain hands over a key every ~0.16 us, a probe round costs ~1.5 us whatever its size: the scorer takes full
+  // tiles (with the vote-round chain, four times slower, small tiles keep it closer behind)
+  ChainArgs b = a;
+  const char* e = std::getenv("KVB_SPEC_SCORE_BATCH");
+  b.score_min_batch = e ? std::max(1, std::min(32, std::atoi(e))) : 32;
+  return launch_spec(b, true, n_prompts, block_size, total_keys, s, rc_out, h_prompt_off, h_key_off, h_parents);
+}
+
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
 __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__ name, uint32_t len,
                                  uint64_t* __restrict__ out) {
@@ -1112,8 +1558,21 @@ __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__
 
 int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents, int32_t n_prompts,
                        int32_t block_size, const uint8_t* extra, const int64_t* extra_off, uint64_t* out_keys,
-                       const int64_t* key_off, cudaStream_t s) {
+                       const int64_t* key_off, cudaStream_t s, int64_t total_keys, const int64_t* h_prompt_off,
+                       const int64_t* h_key_off, const uint64_t* h_parents) {
   if (n_prompts <= 0) return KVB_OK;
+  if (total_keys > 0 && spec_wanted(n_prompts)) {  // small batches whose key count the caller knows: tables off the chain
+    ChainArgs a{};
+    a.tokens = tokens;
+    a.prompt_off = prompt_off;
+    a.parents = parents;
+    a.extra = extra;
+    a.extra_off = extra_off;
+    a.out_keys = out_keys;
+    a.key_off = key_off;
+    int rc = KVB_OK;
+    if (launch_spec(a, false, n_prompts, block_size, total_keys, s, &rc, h_prompt_off, h_key_off, h_parents)) return rc;
+  }
   // small batches: 32-thread CTAs so the chains spread over the SMs; large: 128
   const int threads = n_prompts >= 148 * 128 ? 128 : 32;
   const int grid = (n_prompts + threads - 1) / threads;
@@ -1287,7 +1746,7 @@ int kvb_init_hash(int device, uint64_t seed_hash, const char* model_name, size_t
 
 int kvb_hash_token_blocks_dev(int device, const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents,
                               int32_t n_prompts, int32_t block_size, const uint8_t* extra, const int64_t* extra_off,
-                              uint64_t* out_keys, const int64_t* key_off, void* stream) {
+                              uint64_t* out_keys, const int64_t* key_off, int64_t total_keys, void* stream) {
   return kvb::guarded([&]() -> int {
     KVB_REQUIRE(block_size > 0, "blockSize must be greater than 0, got %d", block_size);  // token_processor.go:86-88
     KVB_REQUIRE(n_prompts >= 0, "negative prompt count");
@@ -1295,7 +1754,7 @@ int kvb_hash_token_blocks_dev(int device, const uint32_t* tokens, const int64_t*
     KVB_REQUIRE(tokens && prompt_off && parents && out_keys && key_off, "NULL argument");
     DeviceGuard g(device);
     return launch_hash_blocks(tokens, prompt_off, parents, n_prompts, block_size, extra, extra_off, out_keys, key_off,
-                              static_cast<cudaStream_t>(stream));
+                              static_cast<cudaStream_t>(stream), total_keys);
   });
 }
 
@@ -1357,7 +1816,8 @@ int kvb_hash_token_blocks(int device, const uint32_t* tokens, const int64_t* pro
     rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
                             reinterpret_cast<uint64_t*>(D + o_par), n_prompts, block_size,
                             extra_off ? D + o_ext : nullptr, extra_off ? reinterpret_cast<int64_t*>(D + o_eoff) : nullptr,
-                            reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
+                            reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s, total_keys,
+                            h_poff, out_key_off, parents);
     cudaError_t e = cudaSuccess;
     if (rc == KVB_OK) e = cudaMemcpyAsync(out_keys, D + o_keys, (size_t)total_keys * 8, cudaMemcpyDeviceToHost, s);
     const cudaError_t e2 = cudaStreamSynchronize(s);  // the scratch and the caller's buffers must outlive the copies

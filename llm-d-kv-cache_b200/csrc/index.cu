@@ -1460,7 +1460,7 @@ int kvb_index_ingest_events(kvb_index_t* idx, const kvb_kv_event_t* ev, int32_t 
       KVB_CUDA_TRY(cudaMemcpyAsync(D, H, in_end, cudaMemcpyHostToDevice, s));
       rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
                               reinterpret_cast<uint64_t*>(D + o_par), m, block_size, nullptr, nullptr,
-                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s);
+                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s, h_koff[m]);
       if (rc) return rc;
       KVB_CUDA_TRY(cudaMemcpyAsync(H + o_keys, D + o_keys, (size_t)h_koff[m] * 8, cudaMemcpyDeviceToHost, s));
       KVB_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1786,13 +1786,23 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
       a.done_flag_host = idx->h_done;
       a.done_value = ++idx->done_seq;
     }
-    if (fuse && launch_chain_score(a, n_prompts, block_size, s)) {
+    // a handful of prompts: the table kernel (token bytes off the chain, any block size); else the chain kernel
+    int spec_rc = KVB_OK;
+    if (fuse && launch_spec_score(a, n_prompts, block_size, total_keys, s, &spec_rc,
+                                  reinterpret_cast<const int64_t*>(H + o_poff), h_koff,
+                                  reinterpret_cast<const uint64_t*>(H + o_par))) {
+      if (spec_rc) return spec_rc;
+      scored = true;
+      watch_flag = a.done_counter != nullptr;
+    } else if (fuse && launch_chain_score(a, n_prompts, block_size, s)) {
       KVB_CUDA_TRY(cudaGetLastError());
       scored = true;  // ONE launch did tokens -> keys -> lookup -> scores
       watch_flag = a.done_counter != nullptr;
     } else {
       rc = launch_hash_blocks(tok_dev, a.prompt_off, a.parents, n_prompts, block_size, a.extra, a.extra_off,
-                              reinterpret_cast<uint64_t*>(D + o_keys), a.key_off, s);
+                              reinterpret_cast<uint64_t*>(D + o_keys), a.key_off, s, total_keys,
+                              reinterpret_cast<const int64_t*>(H + o_poff), h_koff,
+                              reinterpret_cast<const uint64_t*>(H + o_par));
       if (rc) return rc;
     }
   }

@@ -44,100 +44,98 @@ __device__ __host__ __forceinline__ bool pod_allowed(const uint32_t* __restrict_
 
 #ifndef KVB_HOST_SIM
 // LongestPrefixScorer.Score (kvblock_scorer.go:106-154) for ONE prompt by ONE warp, fed 32 keys at a time.
-//   tile(): phase A — 32 independent probes (random 64 B reads), found buckets staged in shared memory and re-stamped
-//           (Lookup's data.Get refreshes every key it finds, in_memory.go:119-120);
-//           phase B — the serial walk over the tile's keys: bucket entries sit on lanes 16..28, the reported pods
-//           ("owners", in the order they appeared at key 0) on lanes 0..12, ONE match.any per key pairs every owner with
-//           the entries that carry its pod; scores are float64 sums in key order, bit-identical to the Go loop.
+//   tile(): one key per lane.  Each lane probes its key (a random 64 B read), re-stamps the bucket it finds (Lookup's
+//   data.Get refreshes every key it finds, in_memory.go:119-120) and keeps the bucket in registers.  Key 0 names the
+//   reported pods ("owners", distinct pods in the order their entries appear, lanes 0..n_own-1).  Then, per owner, every
+//   lane looks for that pod among ITS key's entries (max weight over the pod's tiers) and one ballot finds the first key
+//   of the tile without it; the owner's lane adds the weights of the keys before that one in key order — float64,
+//   the same sum as the Go loop — out of a [8 owners][32 keys] matrix in shared memory (the caller's 2 KiB tile buffer).
+//   The walk is parallel over keys; only the additions are serial (round 1/2's walk went key by key: ~1000 cycles per key).
 struct ScoreWalker {
   bool active = false;  // this lane owns a pod that is still on the consecutive prefix
   bool owner = false;   // this lane owns a pod that appeared at key 0 (it is reported)
   uint32_t my_pod = 0xffffffffu;
   double score = 0.0;
   bool chain_alive = true;
+  int n_own = 0;
 
   __device__ __forceinline__ void tile(const Bucket* __restrict__ table, uint64_t mask, Bucket* __restrict__ tile_smem,
                                        uint64_t key, bool have_key, int64_t base, int in_tile,
                                        const uint32_t* __restrict__ filter_bits, const double* __restrict__ tier_w,
                                        unsigned long long* __restrict__ ts, unsigned long long stamp) {
     constexpr unsigned FULL = 0xffffffffu;
+    static_assert(kMaxEnt == 13, "bucket words are unpacked by hand below");
     const int lane = threadIdx.x & 31;
     int64_t slot = -1;
     if (have_key) slot = probe(table, mask, key);
     if (ts != nullptr && slot >= 0) atomicMax(&ts[slot], stamp);
+    if (!chain_alive) return;
+    uint32_t ent[kMaxEnt];
+    int cnt = 0;
     if (slot >= 0) {
       const uint4* src = reinterpret_cast<const uint4*>(&table[slot]);
-      uint4* dst = reinterpret_cast<uint4*>(&tile_smem[lane]);
+      const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];  // key | meta ent0 | ent1-4 | ent5-8 | ent9-12
+      cnt = min((int)((q0.z >> 8) & 0xffu), kMaxEnt);
+      ent[0] = q0.w;
+      ent[1] = q1.x, ent[2] = q1.y, ent[3] = q1.z, ent[4] = q1.w;
+      ent[5] = q2.x, ent[6] = q2.y, ent[7] = q2.z, ent[8] = q2.w;
+      ent[9] = q3.x, ent[10] = q3.y, ent[11] = q3.z, ent[12] = q3.w;
+    } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = src[q];
+      for (int e = 0; e < kMaxEnt; ++e) ent[e] = 0u;
     }
-    __syncwarp();
-    if (!chain_alive) return;
-    for (int j = 0; j < in_tile; ++j) {
-      const int64_t sj = __shfl_sync(FULL, slot, j);
-      bool valid = false;
-      uint32_t pod = 0x10000u + lane;  // unique sentinel for lanes without a valid entry
-      double w = 0.0;
-      if (sj >= 0) {
-        const Bucket& b = tile_smem[j];
-        const int cnt = (int)((b.meta >> 8) & 0xff);
-        const int e = lane - 16;
-        if (e >= 0 && e < cnt && e < kMaxEnt) {
-          const uint32_t v = b.ent[e];
-          if (pod_allowed(filter_bits, v & 0xffffu)) {
-            valid = true;
-            pod = v & 0xffffu;
-            w = tier_w[(v >> 16) & 0xffu];
-          }
-        }
+    if (base == 0) {
+      // owners: distinct pods of key 0's entries that pass the pod filter, in entry order (fillMaxWeights' key set)
+      const int cnt0 = __shfl_sync(FULL, cnt, 0);
+      uint32_t v = 0u;
+#pragma unroll
+      for (int e = 0; e < kMaxEnt; ++e) {
+        const uint32_t x = __shfl_sync(FULL, ent[e], 0);
+        if (lane == e) v = x;
       }
-      if (base + j == 0) {
-        // key 0: active set = distinct pods, weight = max over that pod's tiers (fillMaxWeights)
-        const unsigned group = __match_any_sync(FULL, pod) & 0x1fff0000u;  // entry lanes with this lane's pod
-        const bool leader = valid && (group & ((1u << lane) - 1u)) == 0u;   // first entry of its pod
-        double wmax = w;
-        unsigned rest = valid ? (group & ~(1u << lane)) : 0u;
-        while (__any_sync(FULL, rest != 0u)) {  // usually zero or one round: a pod on two tiers
-          const int src = rest ? __ffs((int)rest) - 1 : lane;
-          const double we = __shfl_sync(FULL, w, src);
-          if (rest) {
-            if (we > wmax) wmax = we;
-            rest &= rest - 1u;
-          }
-        }
-        const bool l2 = __shfl_down_sync(FULL, leader ? 1 : 0, 16) != 0;
-        const uint32_t p2 = __shfl_down_sync(FULL, pod, 16);
-        const double w2 = __shfl_down_sync(FULL, wmax, 16);
-        owner = active = lane < kMaxEnt && l2;
-        my_pod = owner ? p2 : 0xffffffffu;
-        score = owner ? w2 : 0.0;
-      } else {
-        const uint32_t val = lane < 16 ? (active ? my_pod : 0x20000u + lane) : pod;
-        unsigned em = __match_any_sync(FULL, val) >> 16;  // entry lanes (as bits 0..12) that carry my_pod
-        if (!(lane < 16 && active)) em = 0u;
-        const bool hit = em != 0u;
-        double wm = 0.0;
-        bool first = true;
-        while (__any_sync(FULL, em != 0u)) {
-          const int src = em ? 16 + __ffs((int)em) - 1 : lane;
-          const double we = __shfl_sync(FULL, w, src);
-          if (em) {
-            if (first || we > wm) wm = we;
-            first = false;
-            em &= em - 1u;
-          }
-        }
-        if (active) {
-          if (hit) score += wm;  // float64, key order: same sum as the Go loop
-          else active = false;
-        }
-      }
-      if (!__any_sync(FULL, active)) {
-        chain_alive = false;
-        break;
-      }
+      const bool valid = lane < cnt0 && pod_allowed(filter_bits, v & 0xffffu);
+      const uint32_t pod = valid ? (v & 0xffffu) : (0x10000u + lane);  // unique sentinel for lanes without an entry
+      const unsigned group = __match_any_sync(FULL, pod);
+      const bool leader = valid && (group & ((1u << lane) - 1u)) == 0u;  // first entry of its pod
+      const unsigned lm = __ballot_sync(FULL, leader);
+      n_own = __popc(lm);
+      const unsigned src = __fns(lm, 0, lane + 1);  // lane of the (lane + 1)-th leader
+      const uint32_t p2 = __shfl_sync(FULL, pod, (int)(src & 31u));
+      owner = active = lane < n_own;
+      my_pod = owner ? p2 : 0xffffffffu;
+      score = 0.0;
     }
-    __syncwarp();
+    double* wmat = reinterpret_cast<double*>(tile_smem);  // [8][32], sizeof(Bucket[32]) == 2048
+    const unsigned in_mask = in_tile >= 32 ? FULL : ((1u << in_tile) - 1u);
+    for (int o0 = 0; o0 < n_own; o0 += 8) {
+      const int oc = min(8, n_own - o0);
+      int my_f = in_tile;
+      for (int oo = 0; oo < oc; ++oo) {
+        const uint32_t po = __shfl_sync(FULL, my_pod, o0 + oo);
+        if (__shfl_sync(FULL, active ? 1 : 0, o0 + oo) == 0) continue;  // this pod already left the prefix (uniform)
+        bool hit = false;
+        double best = 0.0;
+#pragma unroll
+        for (int e = 0; e < kMaxEnt; ++e) {
+          if (e < cnt && (ent[e] & 0xffffu) == po) {
+            const double w = tier_w[(ent[e] >> 16) & 0xffu];
+            if (!hit || w > best) best = w;  // a pod on two tiers counts with the larger weight
+            hit = true;
+          }
+        }
+        const unsigned absent = __ballot_sync(FULL, !hit) & in_mask;
+        wmat[oo * 32 + lane] = best;
+        if (lane == o0 + oo) my_f = absent ? __ffs((int)absent) - 1 : in_tile;
+      }
+      __syncwarp();
+      if (active && lane >= o0 && lane < o0 + oc) {
+        const double* row = wmat + (lane - o0) * 32;
+        for (int j = 0; j < my_f; ++j) score += row[j];  // float64, key order: same sum as the Go loop
+        if (my_f < in_tile) active = false;
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(FULL, active)) chain_alive = false;
   }
 
   // compact (pod, score) pairs of the owner lanes
@@ -187,6 +185,11 @@ struct ChainArgs {
 
 // one launch: tokens -> keys -> lookup -> scores.  false if the block size has no chain kernel (hash and score separately)
 bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, cudaStream_t s);
+// the same for small batches by the table ("spec") kernel: any block size, total_keys = key_off[n_prompts];
+// false = not applicable (batch too large or switched off), true = launched or failed (*rc_out)
+// h_*: host-readable copies of prompt_off / key_off / parents
+bool launch_spec_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, int64_t total_keys, cudaStream_t s,
+                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents);
 #endif  // !KVB_HOST_SIM
 
 }  // namespace kvb

@@ -19,7 +19,7 @@ def main():
     torch.cuda.set_device(0)
     kvb = importlib.import_module("llm-d-kv-cache_b200")
     lib = kvb.lib
-    sizes = [int(x) for x in sys.argv[1:]] or [1, 148, 592, 1024, 1536]
+    sizes = [int(x) for x in sys.argv[1:]] or [1, 4, 16, 64, 148, 1024]
     bs, ntok = 16, 1000
     rng = np.random.default_rng(2)
     out = {}
@@ -35,9 +35,11 @@ def main():
 
         def launch():
             kvb._lib.check(lib.kvb_hash_token_blocks_dev(0, d_tok.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), n, bs, None, None,
-                                                         d_keys.data_ptr(), d_koff.data_ptr(), st.cuda_stream))
+                                                         d_keys.data_ptr(), d_koff.data_ptr(), int(koff[-1]), st.cuda_stream))
         row = {}
-        for family in ("chain_s1", "chain_s2", "chain_s1_merged", "chain_s2_merged", "wpc", "lanes"):
+        for family in ("spec", "chain_s1", "chain_s1_merged", "wpc", "lanes"):
+            if family == "spec" and n > 64:
+                continue
             for k in ("KVB_HASH_STAGERS", "KVB_HASH_MERGED", "KVB_HASH_KERNEL"):
                 os.environ.pop(k, None)
             if family.startswith("chain"):

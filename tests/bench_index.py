@@ -130,7 +130,7 @@ def main():
 
     def hash_dev():
         kvb._lib.check(kvb.lib.kvb_hash_token_blocks_dev(0, d_tok.data_ptr(), d_off.data_ptr(), d_par.data_ptr(), N_PROMPTS, BS,
-                                                         None, None, d_keys.data_ptr(), d_koff.data_ptr(), st.cuda_stream))
+                                                         None, None, d_keys.data_ptr(), d_koff.data_ptr(), int(koff_g[-1]), st.cuda_stream))
     for _ in range(5):
         hash_dev()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]

@@ -7,11 +7,11 @@ from oracle import kvblock_oracle as o
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "lanes", "wpc", "chain"])
+@pytest.fixture(autouse=True, params=["auto", "lanes", "wpc", "chain", "spec"])
 def hash_kernel_family(request, monkeypatch):
     """Every test runs twice: default dispatch (warp-per-chain kernel for small batches of block size 4/8/16) and with
     the lane-per-prompt kernels forced (KVB_HASH_KERNEL is read on every launch)."""
-    if request.param in ("lanes", "wpc", "chain"):   # "wpc": round 1's warp kernel (the default); "chain": round 2's chain kernel, hash-only form
+    if request.param in ("lanes", "wpc", "chain", "spec"):   # "spec": the table kernel for batches of up to 64 prompts;   # "wpc": round 1's warp kernel (the default); "chain": round 2's chain kernel, hash-only form
         monkeypatch.setenv("KVB_HASH_KERNEL", request.param)
     else:
         monkeypatch.delenv("KVB_HASH_KERNEL", raising=False)
