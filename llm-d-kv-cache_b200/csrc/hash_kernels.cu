@@ -1126,6 +1126,8 @@ struct SpecArgs {
   uint64_t* table;  // [total_keys][256]  fold(v, tail_k)
   uint64_t* pm;     // [total_keys]       P^len(tail_k)
   unsigned* done;   // [n_prompts] tables finished per prompt; zero at launch, reset by the prompt's CTA
+  unsigned* next_task;  // task counter: a launch with T tasks advances it by exactly T (one fetch per executed task)
+  unsigned task_base;   // its value at launch
   // up to kSpecAutoPrompts prompts travel in the launch arguments (no array to fetch before the first table can start —
   // the fused call keeps these arrays in pinned HOST memory, a PCIe round trip per dependent read)
   int32_t inl;
@@ -1197,9 +1199,14 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
 #define SPROF(slot) do { } while (0)
 #endif
 
-  // ---- phase A: tables.  Task k = key k of the batch (prompt p, block i), strided over the grid.
+  // ---- phase A: tables.  Task k = key k of the batch (prompt p, block i).  A CTA's first task is its own index, the
+  // rest come from a counter (fetched while the current task runs).  Whoever is resident drains the queue, the prompts'
+  // own CTAs included, so the chains below never wait for a CTA that has not been scheduled — whatever else holds SMs.
+  __shared__ unsigned s_next;
   uint8_t* stage = spec_smem;  // <= 5 + kSpecChunk bytes
-  for (int64_t k = blockIdx.x; k < X.total_keys; k += gridDim.x) {
+  const int64_t first_round = min((int64_t)gridDim.x, X.total_keys);
+  for (int64_t k = blockIdx.x; k < X.total_keys;) {
+    if (tid == 0) s_next = atomicAdd(X.next_task, 1u) - X.task_base;  // read after the barriers inside the task
     int p = 0;
     int64_t i = k, tok0 = 0;
     if (!A.single) {
@@ -1303,11 +1310,13 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
     __threadfence();
     __syncthreads();
     if (tid == 0) atomicAdd(&X.done[p], 1u);
+    k = first_round + (int64_t)s_next;
+    __syncthreads();  // everybody has read s_next before thread 0 fetches again
   }
 
   if (tid == 0) SPROF(1);
-  // ---- phase B: CTA p follows prompt p.  Every CTA of the grid is resident (the host sizes the grid for that), so the
-  // tables this CTA waits for are being produced.  Lane 0 of warp 0 walks the chain, warp 1 scores behind it, warps 2..7
+  // ---- phase B: CTA p follows prompt p.  The queue is empty, so every table this CTA waits for is done or being computed
+  // by a running CTA.  Lane 0 of warp 0 walks the chain, warp 1 scores behind it, warps 2..7
   // stage the table rows (two buffers of kSpecPassRows rows, cp.async) ahead of it.
   const int p = blockIdx.x;
   if (p >= X.n_prompts) return;
@@ -1439,7 +1448,8 @@ struct SpecScratch {
   std::mutex mu;
   uint8_t* d = nullptr;
   size_t cap = 0;
-  unsigned* done = nullptr;
+  unsigned* done = nullptr;   // kSpecMaxPrompts counters + the task counter
+  unsigned task_base = 0;
   int max_grid = 0;
 };
 // one scratch per (device, stream): launches on one stream run in order, so the next launch may reuse the tables;
@@ -1481,10 +1491,10 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
     if (e == cudaSuccess)
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hash_spec_kernel<true>, kSpecThreads, kSpecSmem);
     if (e != cudaSuccess || per_sm < 1 || per_sm2 < 1) return fail("occupancy query", e);
-    e = cudaMalloc(&sc.done, kSpecMaxPrompts * sizeof(unsigned));
+    e = cudaMalloc(&sc.done, (kSpecMaxPrompts + 1) * sizeof(unsigned));
     if (e != cudaSuccess) return fail("counters", e);
-    cudaMemset(sc.done, 0, kSpecMaxPrompts * sizeof(unsigned));
-    sc.max_grid = std::min(per_sm, per_sm2) * sm_count(dev);  // every CTA resident: the chains wait for the tables
+    cudaMemset(sc.done, 0, (kSpecMaxPrompts + 1) * sizeof(unsigned));
+    sc.max_grid = std::min(per_sm, per_sm2) * sm_count(dev);  // one wave when the GPU is ours; not needed for progress
   }
   const size_t need = (size_t)total_keys * (256 + 1) * 8;
   if (need > sc.cap) {
@@ -1504,6 +1514,9 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
   x.table = reinterpret_cast<uint64_t*>(sc.d);
   x.pm = x.table + (size_t)total_keys * 256;
   x.done = sc.done;
+  x.next_task = sc.done + kSpecMaxPrompts;
+  x.task_base = sc.task_base;
+  sc.task_base += (unsigned)total_keys;  // wraps with the counter
   if (h_prompt_off && h_key_off && h_parents && n_prompts <= kSpecAutoPrompts) {  // host copies at hand: in the arguments
     x.inl = 1;
     for (int i = 0; i <= n_prompts; ++i) {
