@@ -685,6 +685,27 @@ def run_index_configs(kvb):
                                  "lru_evictions": st_c["lru_evictions"], "order_builds": st_c["order_builds"],
                                  "flushes_planned": st_c["flushes_planned"], "plan_fallbacks": st_c["plan_fallbacks"],
                                  "exact": "the 200 000 oldest keys were evicted, in insertion order (checked on the boundaries)"}
+    # a mixed batch at capacity: 150 000 new keys interleaved with 30 000 removals of resident keys' only pod (those keys
+    # disappear, so live moves both ways inside the batch); queued first, the flush is what is timed
+    fresh = rng.integers(1, 1 << 62, 150_000, dtype=np.int64).astype(np.uint64)
+    gone = fill[cap - 30_000:cap]                      # among the newest residents: not evicted by this batch
+    for c in range(30):
+        idx_c.add(None, fresh[c * 5000:(c + 1) * 5000], ent_c)
+        for k in gone[c * 1000:(c + 1) * 1000]:
+            idx_c.evict(int(k), K.REQUEST_KEY, ent_c)
+    t0 = time.perf_counter()
+    idx_c.flush()
+    t_mix = time.perf_counter() - t0
+    st_m = idx_c.stats()
+    # live peaks after the 30th group of adds: 29 x (5000 - 1000) + 5000 above Size -> 121 000 evictions; the last 1000
+    # removals come after the last insertion and leave the index 1000 short of full
+    assert st_m["live_keys"] == cap - 1000 and st_m["lru_evictions"] == 200_000 + 121_000, st_m
+    assert len(idx_c.lookup(gone[::1000])) == 0 and len(idx_c.lookup(fresh[::1000])) == 150
+    cfg5["index_at_capacity"]["mixed_batch"] = {
+        "ops": 180_000, "adds": 150_000, "removals_that_delete_a_key": 30_000, "flush_seconds": t_mix,
+        "ops_per_s": 180_000 / t_mix, "lru_evictions": st_m["lru_evictions"] - st_c["lru_evictions"],
+        "flushes_planned": st_m["flushes_planned"] - st_c["flushes_planned"],
+        "plan_fallbacks": st_m["plan_fallbacks"] - st_c["plan_fallbacks"]}
     idx_c.close()
 
     # ---- config #1: one prompt, 4 pods

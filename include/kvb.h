@@ -267,8 +267,8 @@ typedef struct kvb_index_stats {
   int64_t live_keys, tombstones, table_slots, engine_keys;
   int64_t ops_applied;        /* Add / Evict records applied on the device */
   int64_t flushes_parallel;   /* sorted, one thread per distinct key */
-  int64_t flushes_sequential; /* one thread in the reference's order (tiny batches; at capacity, batches that also
-                                 remove pods or whose eviction plan hit a conflict) */
+  int64_t flushes_sequential; /* one thread in the reference's order (tiny batches; at capacity, batches whose eviction
+                                 plan did not settle) */
   int64_t flushes_planned;    /* parallel flushes at capacity: LRU victims planned up front, same result as in order */
   int64_t plan_fallbacks;     /* planned flushes that had to be replayed sequentially */
   int64_t rehashes;           /* device-side table growth / tombstone purge */

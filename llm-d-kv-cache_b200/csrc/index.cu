@@ -363,25 +363,65 @@ __global__ void index_collect_order_kernel(TableRef t, unsigned long long* __res
   }
 }
 
-// ---- parallel apply AT CAPACITY (add-only batches).  The reference evicts the outer LRU's oldest key at every
-// insertion past Size (lru.Add, in_memory.go:197), one op at a time.  For a batch of adds the same victims can be
-// planned up front: live grows by one per NEW key, so eviction number e happens at the op of insertion number
-// slack + e (slack = Size - live before the batch), and its victim is the e-th record of the recency order that the
-// batch has not touched by then.  A record the batch touches BEFORE the eviction that would reach it has moved to the
-// newest end and survives; one it touches only AFTER is evicted and re-created from nothing by that later op — a
-// "conflict" key: it is a victim AND one more insertion, which shifts the plan, so the plan is iterated to a fixed
-// point (conflict keys only ever get added) and every member is re-verified in the final pass.  Victims are removed
-// before the apply kernel runs, so a conflict key is simply absent when its ops are replayed.
+// ---- parallel apply AT CAPACITY.  The reference evicts the outer LRU's oldest key at every insertion that pushes the
+// cache past Size (lru.Add, in_memory.go:197), one op at a time.  The same victims can be planned before anything is
+// applied.  Replaying each key's ops on its own (the sorted runs) tells which ops INSERT a key (+1) and which DELETE one
+// (its last pod leaves: -1); with net_t = live + the sum of those events up to op t, eviction number e happens at the
+// first op whose net reaches Size + e + 1 — evictions only ever trim the excess, so their count after op t is the
+// running maximum of net minus Size.  Its victim is the e-th record of the recency order that the batch has not touched
+// by then.  A record the batch touches BEFORE the eviction that would reach it has moved to the newest end and survives;
+// one it touches only AFTER is evicted and its later ops act on an absent key — a "conflict" key: a victim, and a
+// different event sequence (an insertion where there was a touch), which shifts the plan.  So the conflict set is
+// recomputed from scratch until the plan reproduces itself.  Victims are removed before the apply kernel runs, so a
+// conflict key is simply absent when its ops are replayed.
 //
-// classify: run heads whose key is absent append their first op index (= the op that inserts the key)
-__global__ void index_classify_kernel(TableRef t, const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx,
-                                      int64_t n, uint32_t* __restrict__ ins_ops, unsigned long long* __restrict__ cursor) {
+// events: the run head replays its key's ops on a register copy of the bucket (nothing is written to the table)
+__global__ void index_plan_events_kernel(TableRef t, const OpRec* __restrict__ ops, const uint32_t* __restrict__ ents,
+                                         const uint64_t* __restrict__ skey, const uint32_t* __restrict__ sidx, int64_t n,
+                                         const uint8_t* __restrict__ conflict, int32_t* __restrict__ ev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = skey[i];
   if (i > 0 && skey[i - 1] == key) return;
-  if (find_slot(t, key, nullptr) >= 0) return;
-  ins_ops[atomicAdd(cursor, 1ull)] = sidx[i];
+  const int64_t found = conflict[i] ? -1 : find_slot(t, key, nullptr);  // a conflict key is gone before its first op
+  uint32_t ent[kMaxEnt];
+  int cnt = 0;
+  bool present = found >= 0;
+  if (present) {
+    const Bucket& b = t.table[found];
+    cnt = (int)((ld_meta(&b) >> 8) & 0xffu);
+    for (int e = 0; e < kMaxEnt; ++e) ent[e] = b.ent[e];
+  }
+  for (int64_t j = i; j < n && skey[j] == key; ++j) {
+    const OpRec op = ops[sidx[j]];
+    if (op.type == kOpAdd) {
+      if (!present) {
+        present = true;
+        cnt = 0;
+        ev[sidx[j]] = 1;
+      }
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_add(ent, cnt, ents[op.ent_off + e], t.ppk);
+    } else if (present) {
+      for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_remove(ent, cnt, ents[op.ent_off + e]);
+      if (cnt == 0) {
+        present = false;
+        ev[sidx[j]] = -1;
+      }
+    }
+  }
+}
+
+// net[t] = events up to and including op t, top[t] = their running maximum.  An insertion that lifts live to a new
+// maximum above Size is the op of eviction number (that maximum - Size - 1).
+__global__ void index_evict_times_kernel(const int32_t* __restrict__ ev, const int32_t* __restrict__ net,
+                                         const int32_t* __restrict__ top, int64_t n, int64_t live0, int64_t max_keys,
+                                         uint32_t* __restrict__ evict_op) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || ev[i] <= 0) return;
+  const int64_t cur = live0 + net[i];
+  const int64_t prev_top = i > 0 ? (int64_t)top[i - 1] : 0;
+  const int64_t before = live0 + (prev_top > 0 ? prev_top : 0);
+  if (cur > max_keys && cur > before) evict_op[cur - max_keys - 1] = (uint32_t)i;
 }
 
 constexpr uint32_t kUntouched = 0xffffffffu;
@@ -419,12 +459,11 @@ __global__ void index_evict_flag_kernel(TableRef t, const unsigned long long* __
 // rank[p] = victims (under the current conflict set) before p in this window; `found` were taken from earlier
 // windows, `need` more are wanted.  Every touched record is decided afresh into conflict_next.
 // out[0] = records whose decision differs from the current set, out[1] = window position just past the last victim
-// taken, out[2] = victims taken here, out[3] = insertion cursor (conflict keys append their re-creating op)
+// taken, out[2] = victims taken here, out[3] = size of the next conflict set
 __global__ void index_evict_decide_kernel(const uint32_t* __restrict__ is_victim, const uint32_t* __restrict__ touch,
                                           const uint32_t* __restrict__ rank, int64_t w, int64_t pos,
                                           const uint32_t* __restrict__ order_slot, const uint32_t* __restrict__ sidx,
-                                          int64_t found, int64_t need, int64_t slack,
-                                          const uint32_t* __restrict__ ins_sorted, uint32_t* __restrict__ ins_ops,
+                                          int64_t found, int64_t need, const uint32_t* __restrict__ evict_op,
                                           uint8_t* __restrict__ conflict_next, uint32_t* __restrict__ victims,
                                           unsigned long long* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,12 +475,11 @@ __global__ void index_evict_decide_kernel(const uint32_t* __restrict__ is_victim
     if (vic && tch != kUntouched) atomicAdd(&out[0], 1ull);
     return;
   }
-  const uint32_t evict_op = ins_sorted[slack + found + r];  // the op whose insertion evicts victim number found + r
   if (tch != kUntouched) {
-    const bool c = sidx[tch] > evict_op;  // first touched only after the eviction reaches it
+    const bool c = sidx[tch] > evict_op[found + r];  // first touched only after the eviction reaches it
     if (c) {
       conflict_next[tch] = 1;
-      ins_ops[atomicAdd(&out[3], 1ull)] = sidx[tch];
+      atomicAdd(&out[3], 1ull);
     }
     if (c != vic) atomicAdd(&out[0], 1ull);
   }
@@ -895,63 +933,75 @@ int kvb_index::ensure_order(int64_t min_records) {
   return KVB_OK;
 }
 
-// Victims of an add-only batch at capacity, planned before anything is applied (see index_classify_kernel).
+// Victims of a batch at capacity, planned before anything is applied (see index_plan_events_kernel).
 // *ok = false: the batch needs the one-thread replay (the order array cannot supply enough records even after a
 // rebuild — an index smaller than the batch — or the plan did not settle).
 int kvb_index::plan_evictions(int64_t n, int64_t* n_victims, unsigned long long* new_head, unsigned long long* skipped,
                               bool* ok) {
   *ok = false;
   *n_victims = 0;
-  if (!d_ins_ops) KVB_CUDA_TRY(cudaMalloc(&d_ins_ops, 2 * kOpsCap * sizeof(uint32_t)));
-  if (!d_victims) KVB_CUDA_TRY(cudaMalloc(&d_victims, 2 * kOpsCap * sizeof(uint32_t)));
+  if (!d_ins_ops) KVB_CUDA_TRY(cudaMalloc(&d_ins_ops, 4 * kOpsCap * sizeof(uint32_t)));  // ev | net | top | evict_op
+  if (!d_victims) KVB_CUDA_TRY(cudaMalloc(&d_victims, kOpsCap * sizeof(uint32_t)));
   if (!d_win) KVB_CUDA_TRY(cudaMalloc(&d_win, 3 * kWinCap * sizeof(uint32_t)));
   if (!d_plan) KVB_CUDA_TRY(cudaMalloc(&d_plan, 8 * sizeof(unsigned long long)));
   if (!d_conflict) KVB_CUDA_TRY(cudaMalloc(&d_conflict, 2 * kOpsCap));
   const unsigned threads = 128;
-  KVB_CUDA_TRY(cudaMemsetAsync(d_plan, 0, 8 * sizeof(unsigned long long), stream));
-  KVB_CUDA_TRY(cudaMemsetAsync(d_conflict, 0, (size_t)n, stream));
-  KVB_LAUNCH(index_classify_kernel, (unsigned)((n + threads - 1) / threads), threads, stream, ref(), d_skey_out,
-             d_sidx_out, n, d_ins_ops, d_plan + 3);
-  KVB_CUDA_TRY(cudaGetLastError());
-  count_launch();
-  unsigned long long h_plan[5] = {};
-  KVB_CUDA_TRY(cudaMemcpyAsync(h_plan, d_plan, sizeof(h_plan), cudaMemcpyDeviceToHost, stream));
-  KVB_CUDA_TRY(cudaStreamSynchronize(stream));
-  const int64_t new_keys = (int64_t)h_plan[3];
-  const int64_t live0 = (int64_t)h_ctr.live;  // exact: read after the last launch that changes it
-  const int64_t slack = max_keys - live0;
-  if (new_keys - slack <= 0) {  // the batch fits: no eviction at all
-    *ok = true;
-    *new_head = h_ctr.order_head;
-    *skipped = 0;
-    return KVB_OK;
-  }
-  if (slack < 0) return KVB_OK;
-  uint32_t* ins_sorted = d_ins_ops + kOpsCap;
+  const unsigned grid_n = (unsigned)((n + threads - 1) / threads);
+  int32_t* ev = reinterpret_cast<int32_t*>(d_ins_ops);
+  int32_t* net = ev + kOpsCap;
+  int32_t* top = net + kOpsCap;
+  uint32_t* evict_op = d_ins_ops + 3 * kOpsCap;
   uint32_t *is_victim = d_win, *touch = d_win + kWinCap, *rank = d_win + 2 * kWinCap;
   uint8_t *conf_cur = d_conflict, *conf_next = d_conflict + kOpsCap;
-  int64_t n_conflicts = 0;  // size of the current conflict set; its ops sit behind the new keys' in d_ins_ops
+  KVB_CUDA_TRY(cudaMemsetAsync(conf_cur, 0, (size_t)n, stream));
+  const int64_t live0 = (int64_t)h_ctr.live;  // exact: read after the last launch that changes it
+  if (live0 > max_keys) return KVB_OK;
+  unsigned long long h_plan[4] = {};
+  int64_t n_conflicts = 0;
   bool rebuilt = false;
+  static const bool plan_debug = getenv("KVB_PLAN_DEBUG") != nullptr;
   for (int iter = 0; iter < 24; ++iter) {
-    const int64_t insertions = new_keys + n_conflicts;  // <= distinct keys of the batch <= kOpsCap
-    const int64_t want = insertions - slack;
+    // which ops insert / delete a key under the current conflict set, and from that the op of every eviction
+    KVB_CUDA_TRY(cudaMemsetAsync(ev, 0, (size_t)n * sizeof(int32_t), stream));
+    KVB_LAUNCH(index_plan_events_kernel, grid_n, threads, stream, ref(), d_ops, d_ents, d_skey_out, d_sidx_out, n,
+               conf_cur, ev);
+    KVB_CUDA_TRY(cudaGetLastError());
+    int32_t top_last = 0;
 #ifdef KVB_HOST_SIM
-    std::copy(d_ins_ops, d_ins_ops + insertions, ins_sorted);
-    std::sort(ins_sorted, ins_sorted + insertions);
+    for (int64_t i = 0, acc = 0, mx = INT32_MIN; i < n; ++i) {
+      acc += ev[i];
+      mx = std::max<int64_t>(mx, acc);
+      net[i] = (int32_t)acc;
+      top[i] = (int32_t)mx;
+    }
+    top_last = top[n - 1];
 #else
     {
-      size_t need = 0;
-      KVB_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, d_ins_ops, ins_sorted, (int)insertions, 0, 32, stream));
-      int rc = ensure_sort_tmp(need);
+      size_t need = 0, need2 = 0;
+      KVB_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, need, ev, net, (int)n, stream));
+      KVB_CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, need2, net, top, cub::Max(), (int)n, stream));
+      int rc = ensure_sort_tmp(std::max(need, need2));
       if (rc) return rc;
-      need = sort_tmp_bytes;
-      KVB_CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_sort_tmp, need, d_ins_ops, ins_sorted, (int)insertions, 0, 32, stream));
-      count_launch();
+      need = need2 = sort_tmp_bytes;
+      KVB_CUDA_TRY(cub::DeviceScan::InclusiveSum(d_sort_tmp, need, ev, net, (int)n, stream));
+      KVB_CUDA_TRY(cub::DeviceScan::InclusiveScan(d_sort_tmp, need2, net, top, cub::Max(), (int)n, stream));
+      KVB_CUDA_TRY(cudaMemcpyAsync(&top_last, top + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      KVB_CUDA_TRY(cudaStreamSynchronize(stream));
     }
 #endif
+    count_launch(3);
+    const int64_t want = std::max<int64_t>(0, live0 + std::max<int64_t>(top_last, 0) - max_keys);
+    if (want == 0) {  // live never passes Size under this conflict set (which is then empty: nothing was evicted)
+      if (n_conflicts != 0) return KVB_OK;
+      *ok = true;
+      *new_head = h_ctr.order_head;
+      *skipped = 0;
+      return KVB_OK;
+    }
+    KVB_LAUNCH(index_evict_times_kernel, grid_n, threads, stream, ev, net, top, n, live0, (int64_t)max_keys, evict_op);
+    KVB_CUDA_TRY(cudaGetLastError());
     KVB_CUDA_TRY(cudaMemsetAsync(conf_next, 0, (size_t)n, stream));
-    h_plan[3] = (unsigned long long)new_keys;  // the next set's ops are appended from here
-    KVB_CUDA_TRY(cudaMemcpyAsync(d_plan + 3, &h_plan[3], sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    KVB_CUDA_TRY(cudaMemsetAsync(d_plan + 3, 0, sizeof(unsigned long long), stream));
     const int64_t head0 = (int64_t)h_ctr.order_head;
     int64_t pos = head0, found = 0, end = -1, changed = 0;
     while (found < want && pos < order_n) {
@@ -975,10 +1025,10 @@ int kvb_index::plan_evictions(int64_t n, int64_t* n_victims, unsigned long long*
       KVB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_sort_tmp, need, is_victim, rank, (int)w, stream));
 #endif
       KVB_LAUNCH(index_evict_decide_kernel, grid, threads, stream, is_victim, touch, rank, w, pos, order_slot,
-                 d_sidx_out, found, want - found, slack, ins_sorted, d_ins_ops, conf_next, d_victims, d_plan);
+                 d_sidx_out, found, want - found, evict_op, conf_next, d_victims, d_plan);
       KVB_CUDA_TRY(cudaGetLastError());
       count_launch(3);
-      KVB_CUDA_TRY(cudaMemcpyAsync(h_plan, d_plan, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      KVB_CUDA_TRY(cudaMemcpyAsync(h_plan, d_plan, sizeof(h_plan), cudaMemcpyDeviceToHost, stream));
       KVB_CUDA_TRY(cudaStreamSynchronize(stream));
       changed += (int64_t)h_plan[0];
       found += (int64_t)h_plan[2];
@@ -988,12 +1038,11 @@ int kvb_index::plan_evictions(int64_t n, int64_t* n_victims, unsigned long long*
       }
       pos += w;
     }
-    const int64_t next_conflicts = (int64_t)h_plan[3] - new_keys;
-    static const bool plan_debug = getenv("KVB_PLAN_DEBUG") != nullptr;
+    const int64_t next_conflicts = (int64_t)h_plan[3];
     if (plan_debug)
-      fprintf(stderr, "plan n %lld new %lld slack %lld iter %d: want %lld found %lld end %lld changed %lld conflicts %lld -> %lld head %lld order_n %lld\n", (long long)n, (long long)new_keys, (long long)slack, iter,
-              (long long)want, (long long)found, (long long)end, (long long)changed, (long long)n_conflicts,
-              (long long)next_conflicts, (long long)head0, (long long)order_n);
+      fprintf(stderr, "plan n %lld live %lld iter %d: want %lld found %lld end %lld changed %lld conflicts %lld -> %lld head %lld order_n %lld\n",
+              (long long)n, (long long)live0, iter, (long long)want, (long long)found, (long long)end, (long long)changed,
+              (long long)n_conflicts, (long long)next_conflicts, (long long)head0, (long long)order_n);
     if (end >= 0 && changed == 0 && next_conflicts == n_conflicts) {  // the plan reproduces itself: these are the victims
       *ok = true;
       *n_victims = want;
@@ -1036,10 +1085,10 @@ int kvb_index::flush_locked() {
     may_evict = live_ub > max_keys;
   }
   const bool small = (int64_t)n_ops <= kSeqThreshold;
-  // at capacity an add-only batch still runs in parallel, with its evictions planned up front; batches that also
-  // remove pods (live moves both ways inside the batch) replay on one thread in the reference's order
+  // at capacity a batch still runs in parallel, with its evictions planned up front (plan_evictions); the one-thread
+  // replay in the reference's order remains for tiny batches and for plans that do not settle
   static const bool plan_off = getenv("KVB_INDEX_PLAN") != nullptr && getenv("KVB_INDEX_PLAN")[0] == '0';
-  bool planned = may_evict && !small && q_evicts == 0 && !plan_off;
+  bool planned = may_evict && !small && !plan_off;
   bool sequential = small || (may_evict && !planned);
   if (may_evict) {
     int rc = ensure_order((int64_t)n_ops);

@@ -339,6 +339,9 @@ def test_at_capacity_add_only_batches_are_planned_on_the_device(kvb, torch_cuda)
     assert st["flushes_planned"] > 50, st
     st = _random_traffic(kvb, kvb.lib, seed=5, size=3, ppk=2, n_keys=60, steps=300, max_batch=40)   # index smaller than a batch
     assert st["live_keys"] <= 3
+    st = _random_traffic(kvb, kvb.lib, seed=57, size=1967, ppk=3, n_keys=3421, steps=300, max_batch=429, lookup_frac=0.25,
+                         evict_frac=0.25)                     # a quarter of the ops remove pods: live moves both ways
+    assert st["flushes_planned"] > 30 and st["plan_fallbacks"] == 0, st
 
 
 def test_planned_eviction_walks_several_windows_of_stale_records(kvb, torch_cuda):

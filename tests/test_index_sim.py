@@ -128,6 +128,16 @@ def test_at_capacity_add_only_batches_are_planned_in_parallel(sim):
     assert st["flushes_planned"] > 20
 
 
+def test_at_capacity_mixed_add_evict_batches_are_planned_too(sim):
+    """A quarter of the ops remove pods (keys disappear when their last pod leaves), so `live` moves both ways inside a
+    batch: eviction times come from the running maximum of live, not from the insertion count."""
+    kvb, lib = sim
+    for seed, size, n_keys, mb in ((50, 1750, 3050, 380), (57, 1967, 3421, 429), (61, 2091, 3633, 457)):
+        st = _random_traffic(kvb, lib, seed=seed, size=size, ppk=3, n_keys=n_keys, steps=300, max_batch=mb, lookup_frac=0.25,
+                             evict_frac=0.25)
+        assert st["flushes_planned"] > 30 and st["plan_fallbacks"] == 0 and st["lru_evictions"] > 5000, st
+
+
 def test_planned_eviction_conflicts_and_survivors(sim):
     """The two cases the plan must tell apart (in_memory.go:186-199): an old key announced BEFORE the insertion that
     would have evicted it moves to the newest end and survives; announced AFTER, the reference evicts it and then
