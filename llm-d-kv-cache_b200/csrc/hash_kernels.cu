@@ -757,11 +757,14 @@ __global__ void __launch_bounds__(32 * (2 + (SCORE ? 1 : 0))) chain_kernel(const
     }
     constexpr uint32_t l00 = (uint32_t)(kFnvOffset & 1u), l01 = (uint32_t)((kFnvOffset >> 1) & 1u);
     // tokens arrive in chunks of 128 (one 16 B granule per lane: a single warp instruction moves 512 B, which matters
-    // when the source is pinned HOST memory read in place over PCIe); the prompt need not start on a 16 B boundary —
+    // when the source is pinned HOST memory read in place over PCIe); the prompt need not start on a granule boundary —
     // the granules are taken from the aligned superset, and granules that stick out of the caller's array fall back to
     // 4 B copies of the tokens that are inside it
     const uint32_t* tk = A.tokens + t0;
-    const int mis = (int)((reinterpret_cast<uintptr_t>(tk) >> 2) & 3u);  // tokens between the 16 B boundary and tk
+    // The chunk grid is aligned to 128 B lines, not just to the 16 B granule: sysmem is read a line at a time, and a chunk
+    // that straddles lines makes the link fetch its boundary lines twice (tools/micro/pinned_read_bw.cu: 1024 prompts of
+    // 4000 B in 512 B chunks — 105 us on a 16 B grid, 87 us on a 128 B grid, 86 us for a plain streaming read)
+    const int mis = (int)((reinterpret_cast<uintptr_t>(tk) >> 2) & 31u);  // tokens between the 128 B boundary and tk
     const uint32_t* tka = tk - mis;
     const int need_hi = mis + nblk * BS;                                  // aligned token indices [mis, need_hi) are needed
     auto fetch_chunk = [&](int c) {  // one commit group per chunk, empty past the end so the group count stays uniform

@@ -272,6 +272,55 @@ def test_pinned_token_buffer_scores_like_pageable(kvb, torch_cuda):
     buf.free()  # idempotent
 
 
+@pytest.mark.parametrize("bs", [16, 4])
+def test_large_pinned_batch_matches_pageable_and_oracle(kvb, torch_cuda, bs):
+    """701 prompts of pinned tokens read in place by ONE fused launch: ragged lengths, empty prompts, a pod filter; against
+    the oracle and against the same call on pageable tokens (which are copied first)."""
+    K = kvb.kvblock
+    rng = np.random.default_rng(77 + bs)
+    tp, otp = K.ChunkedTokenDatabase(bs, ""), o.TokenProcessor(bs, "")
+    idx, oidx = K.Index(), o.InMemoryIndex()
+    n = 701
+    lens = rng.integers(0, 40 * bs, n)
+    lens[[0, 350, 700]] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tokens = rng.integers(0, 128256, int(off[-1])).astype(np.uint32)
+    parents = np.full(n, tp.get_init_hash("m"), dtype=np.uint64)
+    prompts = [tokens[off[i]:off[i + 1]] for i in range(n)]
+    keys, koff = tp.tokens_to_kv_block_keys_batch(prompts, "m")
+    pods = ["pod-%d" % i for i in range(9)]
+    for i in range(0, n, 3):
+        nk = int(koff[i + 1] - koff[i])
+        if nk:
+            d = int(rng.integers(1, nk + 1))
+            ent = (pods[int(rng.integers(0, 9))], "gpu" if rng.random() < 0.7 else "cpu")
+            ks = [int(k) for k in keys[koff[i]:koff[i] + d]]
+            idx.add(None, ks, [K.PodEntry(*ent)])
+            oidx.add(None, ks, [o.PodEntry(*ent)])
+    buf = kvb.pool.PinnedBuffer(max(tokens.nbytes, 64))
+    pinned = buf.numpy(np.uint32)[:tokens.size]
+    pinned[:] = tokens
+    idx.flush()
+    launches0 = kvb.lib.kvb_launch_count()
+    got = idx.score_tokens_flat(bs, pinned, off, parents)
+    assert kvb.lib.kvb_launch_count() - launches0 == 1          # tokens -> scores is one launch
+    ref = idx.score_tokens_flat(bs, tokens, off, parents)        # pageable tokens: one launch
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    for i in range(0, n, 7):
+        ks = otp.tokens_to_kv_block_keys(0, [int(x) for x in prompts[i]], "m") or []
+        want = o.longest_prefix_score(ks, oidx.lookup(ks, []), {"gpu": 1.0, "cpu": 0.8}) if ks else {}
+        mine = {idx.pods.names[int(got[1][i * 13 + j])]: float(got[2][i * 13 + j]) for j in range(int(got[0][i]))}
+        assert mine == want, i
+    flt = ["pod-1", "pod-4"]
+    got_f = idx.score_tokens_flat(bs, pinned, off, parents, pod_identifiers=flt)
+    ref_f = idx.score_tokens_flat(bs, tokens, off, parents, pod_identifiers=flt)
+    for a, b in zip(ref_f, got_f):
+        assert np.array_equal(a, b)
+    del pinned
+    buf.free()
+
+
 def test_scoring_refreshes_recency_by_default(kvb, torch_cuda):
     """Capacity pressure with SCORING between adds: the reference's ScoreTokens goes through Lookup, whose data.Get
     refreshes every key it finds (in_memory.go:120), so which keys the outer LRU evicts depends on what was scored.
