@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Driver for ncu captures of the index kernels: a 1 M-key device-side build (sort + index_apply_par_kernel), then the
 fused tokens -> scores launch (chain_kernel<.., SCORE>) and the two-kernel form (hash + index_score_kernel) for 1024 prompts
-with pinned buffers, and one single-prompt call."""
+with pinned buffers, one single-prompt call and a 16-prompt call (the table kernel), then the eviction planner of an index at
+capacity (add-only batch, mixed batch)."""
 import importlib
 import os
 import sys
@@ -39,3 +40,23 @@ for _ in range(2):
     idx.score_tokens_flat(16, tok, off, parents, out=out, flags=L.SCORE_PINNED_IO | L.SCORE_TWO_KERNELS | L.SCORE_COPY_TOKENS)
     idx.score_tokens_flat(16, tok[:ntok], off[:2], parents[:1], out=out, flags=L.SCORE_PINNED_IO)
 print("done")
+# round 2, later: the table ("spec") kernel on 1 and 16 prompts (fused), and the eviction planner on an index at capacity
+# (an add-only batch, then one that mixes Add and Evict)
+for _ in range(2):
+    idx.score_tokens_flat(16, tok[:16 * ntok], off[:17], parents[:16], out=out, flags=L.SCORE_PINNED_IO)
+cap = 1 << 18
+idx_c = K.Index(size=cap, expected_keys=cap)
+fill = rng.integers(1, 1 << 62, cap + 60_000, dtype=np.int64).astype(np.uint64)
+ent = [K.PodEntry("pod-0", "gpu")]
+idx_c.add(None, fill[:cap], ent)
+idx_c.flush()
+idx_c.add(None, fill[cap:cap + 30_000], ent)
+idx_c.flush()
+for c in range(10):
+    idx_c.add(None, fill[cap + 30_000 + c * 3000:cap + 30_000 + (c + 1) * 3000], ent)
+    for k in fill[cap - 1000 * (c + 1):cap - 1000 * c:10]:
+        idx_c.evict(int(k), K.REQUEST_KEY, ent)
+idx_c.flush()
+st = idx_c.stats()
+assert st["flushes_planned"] == 2 and st["plan_fallbacks"] == 0, st
+print("planner done", st["lru_evictions"])
