@@ -283,3 +283,43 @@ def test_offset_basis_rides_on_position_zero():
         for i in range(1, m):
             total = (total + es[i] * pow(P, m - i, 1 << 64)) & M
         assert total == fnv(stream)
+
+
+def test_table_kernel_identity_fnv_is_linear_above_the_low_byte():
+    """hash_spec_kernel: with h = u + l (l = low byte of h),  fold(h, bytes) = u * P^m + fold(l, bytes)  exactly — the xor
+    touches only the low byte, and the low byte of a product depends only on the factors' low bytes.  So a block's tail
+    (array head | tokens | extra) is tabulated for the 256 values of l off the chain, and the chain folds only
+    83 | U(parent), looks l up and multiplies by P^m.  Checked on the kernel's own stream layout, chained over blocks,
+    against plain FNV-1a."""
+    rng = random.Random(11)
+
+    def fold(h, bs):
+        for b in bs:
+            h = ((h ^ b) * P) & M
+        return h
+
+    def cbor_uint(v):
+        if v < 24:
+            return [v]
+        if v < 0x100:
+            return [0x18, v]
+        if v < 0x10000:
+            return [0x19, v >> 8, v & 0xFF]
+        if v < 0x100000000:
+            return [0x1A] + [(v >> s) & 0xFF for s in (24, 16, 8, 0)]
+        return [0x1B] + [(v >> s) & 0xFF for s in range(56, -8, -8)]
+
+    for _ in range(40):
+        bs = rng.choice([1, 4, 16, 17, 64])
+        parent = rng.choice([0, 5, 70000, rng.getrandbits(33) | (1 << 32), rng.getrandbits(64)])
+        for _blk in range(6):
+            tokens = [rng.getrandbits(rng.choice([4, 8, 16, 17, 32])) for _ in range(bs)]
+            head = [0x80 | bs] if bs < 24 else [0x98, bs]
+            tail = head + [b for t in tokens for b in cbor_uint(t)] + [0xF6]
+            table = [fold(v, tail) for v in range(256)]                  # phase A: 256 plain FNV runs from a bare low byte
+            pm = pow(P, len(tail), 1 << 64)
+            st = fold(H0, [0x83] + cbor_uint(parent)) if parent >= 24 else fold(H0, [0x83, parent])   # phase B prefix
+            low = st & 0xFF
+            key = ((st - low) * pm + table[low]) & M
+            assert key == fnv([0x83] + cbor_uint(parent) + tail)
+            parent = key
