@@ -1116,8 +1116,10 @@ bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_siz
 // shrinks to the 10 prefix bytes plus one table look-up and one multiply by P^m (phase B: one thread per prompt):
 // ~170 cycles per block instead of ~1000 for the vote rounds.  The price is 256x the byte work, which idle SMs absorb
 // for small batches only (the vote kernels stay the choice from a few dozen prompts up).
-constexpr int kSpecThreads = 256;
-constexpr int kSpecPassRows = 20;   // table rows (blocks) per staging buffer; two buffers: 2 x 20 x 2 KiB
+constexpr int kSpecThreads = 128;   // each thread folds TWO start values (two independent chains: the warp's issue slots
+                                    // are half empty with one), so a 128-thread CTA tabulates a block
+constexpr int kSpecPassRows = 8;    // table rows (blocks) per staging buffer; two buffers: 2 x 8 x 2 KiB — small, so that
+                                    // six CTAs fit an SM while the tables are being built
 constexpr int kSpecChunk = 640;     // tail bytes staged per round (128 tokens x 5 B)
 constexpr int kSpecMaxPrompts = 64;
 constexpr int kSpecAutoPrompts = 16;  // chosen without being asked for up to this many prompts
@@ -1148,24 +1150,38 @@ __device__ __forceinline__ uint64_t pow_prime(uint32_t e) {
   return r;
 }
 
-// all threads fold the n staged bytes (same bytes for every thread: shared-memory broadcasts)
-__device__ __forceinline__ void spec_fold_chunk(Fnv& h, const uint32_t* words, int n) {
+// all threads fold the n staged bytes into both of their states (same bytes for every thread: shared-memory broadcasts)
+__device__ __forceinline__ void spec_fold_chunk(Fnv& h, Fnv& g, const uint32_t* words, int n) {
   const int nw = n >> 2;
   int i = 0;
   for (; i + 4 <= nw; i += 4) {
     const uint4 q = *reinterpret_cast<const uint4*>(words + i);
     fold4(h, q.x);
+    fold4(g, q.x);
     fold4(h, q.y);
+    fold4(g, q.y);
     fold4(h, q.z);
+    fold4(g, q.z);
     fold4(h, q.w);
+    fold4(g, q.w);
   }
-  for (; i < nw; ++i) fold4(h, words[i]);
+  for (; i < nw; ++i) {
+    fold4(h, words[i]);
+    fold4(g, words[i]);
+  }
   const int tail = n & 3;
   if (tail) {
     const uint32_t tw = words[nw];
     fold(h, tw & 0xffu);
-    if (tail > 1) fold(h, (tw >> 8) & 0xffu);
-    if (tail > 2) fold(h, (tw >> 16) & 0xffu);
+    fold(g, tw & 0xffu);
+    if (tail > 1) {
+      fold(h, (tw >> 8) & 0xffu);
+      fold(g, (tw >> 8) & 0xffu);
+    }
+    if (tail > 2) {
+      fold(h, (tw >> 16) & 0xffu);
+      fold(g, (tw >> 16) & 0xffu);
+    }
   }
 }
 
@@ -1224,7 +1240,7 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
       tok0 = s_poff[p];
     }
     const uint32_t* tk = A.tokens + tok0 + i * bs;
-    Fnv h{(uint32_t)tid, 0u};
+    Fnv h{(uint32_t)tid, 0u}, g{(uint32_t)tid + 128u, 0u};  // start values tid and tid + 128
     uint32_t m = 0;
     for (int t0 = 0; t0 < bs; t0 += 128) {
       // stage: [array head, first round only] + up to 128 tokens, compacted by a CTA-wide prefix sum of the lengths
@@ -1285,7 +1301,7 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
       }
       __syncthreads();
       const int n = s_n;
-      spec_fold_chunk(h, reinterpret_cast<const uint32_t*>(stage), n);
+      spec_fold_chunk(h, g, reinterpret_cast<const uint32_t*>(stage), n);
       m += (uint32_t)n;
       __syncthreads();
     }
@@ -1300,15 +1316,17 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
         const int n = (int)min((int64_t)kSpecChunk, e1 - e);
         for (int j = tid; j < n; j += kSpecThreads) stage[j] = A.extra[e + j];
         __syncthreads();
-        spec_fold_chunk(h, reinterpret_cast<const uint32_t*>(stage), n);
+        spec_fold_chunk(h, g, reinterpret_cast<const uint32_t*>(stage), n);
         m += (uint32_t)n;
         __syncthreads();
       }
     } else {
       fold(h, 0xf6u);
+      fold(g, 0xf6u);
       m += 1;
     }
     X.table[k * 256 + tid] = fnv_value(h);
+    X.table[k * 256 + 128 + tid] = fnv_value(g);
     if (tid == 0) X.pm[k] = pow_prime(m);
     __threadfence();
     __syncthreads();
@@ -1319,7 +1337,7 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
 
   if (tid == 0) SPROF(1);
   // ---- phase B: CTA p follows prompt p.  The queue is empty, so every table this CTA waits for is done or being computed
-  // by a running CTA.  Lane 0 of warp 0 walks the chain, warp 1 scores behind it, warps 2..7
+  // by a running CTA.  Lane 0 of warp 0 walks the chain, warp 1 scores behind it, warps 2..3
   // stage the table rows (two buffers of kSpecPassRows rows, cp.async) ahead of it.
   const int p = blockIdx.x;
   if (p >= X.n_prompts) return;
