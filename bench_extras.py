@@ -663,7 +663,7 @@ def run_index_configs(kvb):
                         "cpu_c_restatement_1_thread_s": t_build_cpu, "where": "Add/Evict applied by kernels, no host copy"},
     }
 
-    # ---- small batches against the same 10 M-key index: 4 / 16 / 64 prompts per call (the table kernel takes up to 16)
+    # ---- small batches against the same 10 M-key index: 4 / 16 / 64 prompts per call (the table kernel takes up to 32)
     small = {}
     for nb in (4, 16, 64):
         off_b, par_b = np.ascontiguousarray(off[:nb + 1]), np.ascontiguousarray(parents[:nb])

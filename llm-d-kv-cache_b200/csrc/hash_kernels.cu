@@ -1122,7 +1122,8 @@ constexpr int kSpecPassRows = 8;    // table rows (blocks) per staging buffer; t
                                     // six CTAs fit an SM while the tables are being built
 constexpr int kSpecChunk = 640;     // tail bytes staged per round (128 tokens x 5 B)
 constexpr int kSpecMaxPrompts = 64;
-constexpr int kSpecAutoPrompts = 16;  // chosen without being asked for up to this many prompts
+constexpr int kSpecAutoPrompts = 16;  // the small argument block holds this many prompts
+constexpr int kSpecDefaultPrompts = 32;  // chosen without being asked for up to this many prompts
 constexpr int kSpecKeyRing = 64;
 
 struct SpecArgs {
@@ -1133,11 +1134,15 @@ struct SpecArgs {
   unsigned* done;   // [n_prompts] tables finished per prompt; zero at launch, reset by the prompt's CTA
   unsigned* next_task;  // task counter: a launch with T tasks advances it by exactly T (one fetch per executed task)
   unsigned task_base;   // its value at launch
-  // up to kSpecAutoPrompts prompts travel in the launch arguments (no array to fetch before the first table can start —
-  // the fused call keeps these arrays in pinned HOST memory, a PCIe round trip per dependent read)
-  int32_t inl;
-  int64_t koff[kSpecAutoPrompts + 1], poff[kSpecAutoPrompts + 1];
-  uint64_t par[kSpecAutoPrompts];
+  int32_t inl;      // offsets / parents are in the SpecInline argument (else in the ChainArgs arrays)
+};
+// Prompt offsets, key offsets and parents in the launch arguments: no array to fetch before the first table can start (the
+// fused call otherwise keeps them in pinned HOST memory, a PCIe round trip per dependent read).  Two sizes, because the
+// argument block is copied at every launch: 16 prompts (0.4 KiB) for the common case, 64 (1.5 KiB) above.
+template <int N>
+struct SpecInline {
+  int64_t koff[N + 1], poff[N + 1];
+  uint64_t par[N];
 };
 
 __device__ __forceinline__ uint64_t pow_prime(uint32_t e) {
@@ -1193,8 +1198,8 @@ __device__ __forceinline__ void spec_wait_ge(const int* p, int v) {
 
 // A: the chain kernel's arguments (tokens may be pinned host memory read in place; `single` = one prompt whose offsets
 // travel in the arguments; SCORE adds lookup + longest-prefix scores by a scorer warp that follows the chain)
-template <bool SCORE>
-__global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs A, const SpecArgs X) {
+template <bool SCORE, int NIN>
+__global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs A, const SpecArgs X, const SpecInline<NIN> I) {
   extern __shared__ __align__(16) uint8_t spec_smem[];
   __shared__ int s_scan[kSpecThreads / 32];
   __shared__ int s_n;
@@ -1206,8 +1211,8 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
   const int bs = X.block_size;
   if (!A.single) {  // prompt and key offsets: one parallel fetch (launch arguments, or one read of the arrays)
     for (int i = tid; i <= X.n_prompts; i += kSpecThreads) {
-      s_koff[i] = X.inl ? X.koff[i] : A.key_off[i];
-      s_poff[i] = X.inl ? X.poff[i] : A.prompt_off[i];
+      s_koff[i] = X.inl ? I.koff[i] : A.key_off[i];
+      s_poff[i] = X.inl ? I.poff[i] : A.prompt_off[i];
     }
     __syncthreads();
   }
@@ -1424,7 +1429,7 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
 
   // ---------------------------------------------------------------------------------------------------- chain
   if (lane != 0) return;
-  uint64_t parent = A.single ? A.single_parent : (X.inl ? X.par[p] : A.parents[p]);
+  uint64_t parent = A.single ? A.single_parent : (X.inl ? I.par[p] : A.parents[p]);
   for (int q = 0; q < npass; ++q) {
     spec_wait_ge(&loaded, q + 1);
     if (q == 0) SPROF(4);
@@ -1503,19 +1508,24 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
     return true;
   };
   if (sc.max_grid == 0) {
-    cudaError_t e = cudaFuncSetAttribute(hash_spec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(hash_spec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
-    if (e != cudaSuccess) return fail("shared memory opt-in", e);
-    int per_sm = 0, per_sm2 = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_spec_kernel<false>, kSpecThreads, kSpecSmem);
-    if (e == cudaSuccess)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hash_spec_kernel<true>, kSpecThreads, kSpecSmem);
-    if (e != cudaSuccess || per_sm < 1 || per_sm2 < 1) return fail("occupancy query", e);
+    int per_sm = 1 << 30;
+    cudaError_t e = cudaSuccess;
+    auto prep = [&](auto kernel) {
+      if (e != cudaSuccess) return;
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
+      int n = 0;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kSpecThreads, kSpecSmem);
+      if (e == cudaSuccess) per_sm = std::min(per_sm, n);
+    };
+    prep(hash_spec_kernel<false, kSpecAutoPrompts>);
+    prep(hash_spec_kernel<true, kSpecAutoPrompts>);
+    prep(hash_spec_kernel<false, kSpecMaxPrompts>);
+    prep(hash_spec_kernel<true, kSpecMaxPrompts>);
+    if (e != cudaSuccess || per_sm < 1) return fail("kernel attributes / occupancy query", e);
     e = cudaMalloc(&sc.done, (kSpecMaxPrompts + 1) * sizeof(unsigned));
     if (e != cudaSuccess) return fail("counters", e);
     cudaMemset(sc.done, 0, (kSpecMaxPrompts + 1) * sizeof(unsigned));
-    sc.max_grid = std::min(per_sm, per_sm2) * sm_count(dev);  // one wave when the GPU is ours; not needed for progress
+    sc.max_grid = per_sm * sm_count(dev);  // one wave when the GPU is ours; not needed for progress
   }
   const size_t need = (size_t)total_keys * (256 + 1) * 8;
   if (need > sc.cap) {
@@ -1538,17 +1548,24 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
   x.next_task = sc.done + kSpecMaxPrompts;
   x.task_base = sc.task_base;
   sc.task_base += (unsigned)total_keys;  // wraps with the counter
-  if (h_prompt_off && h_key_off && h_parents && n_prompts <= kSpecAutoPrompts) {  // host copies at hand: in the arguments
-    x.inl = 1;
-    for (int i = 0; i <= n_prompts; ++i) {
-      x.koff[i] = h_key_off[i];
-      x.poff[i] = h_prompt_off[i];
-    }
-    for (int i = 0; i < n_prompts; ++i) x.par[i] = h_parents[i];
-  }
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(total_keys, n_prompts), sc.max_grid);
-  if (score) hash_spec_kernel<true><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x);
-  else hash_spec_kernel<false><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x);
+  const bool inl = h_prompt_off && h_key_off && h_parents;  // host copies at hand: they go into the arguments
+  x.inl = inl ? 1 : 0;
+  auto go = [&](auto tag) {
+    constexpr int N = decltype(tag)::value;
+    SpecInline<N> in{};
+    if (inl) {
+      for (int i = 0; i <= n_prompts; ++i) {
+        in.koff[i] = h_key_off[i];
+        in.poff[i] = h_prompt_off[i];
+      }
+      for (int i = 0; i < n_prompts; ++i) in.par[i] = h_parents[i];
+    }
+    if (score) hash_spec_kernel<true, N><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x, in);
+    else hash_spec_kernel<false, N><<<grid, kSpecThreads, kSpecSmem, s>>>(ca, x, in);
+  };
+  if (n_prompts <= kSpecAutoPrompts) go(std::integral_constant<int, kSpecAutoPrompts>{});
+  else go(std::integral_constant<int, kSpecMaxPrompts>{});
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch", e);
   count_launch();
@@ -1561,7 +1578,7 @@ static bool spec_wanted(int32_t n_prompts) {
   const char* f0 = std::getenv("KVB_HASH_KERNEL");
   const char* s0 = std::getenv("KVB_HASH_SPEC");
   if (f0 != nullptr) return std::strcmp(f0, "spec") == 0;
-  return !(s0 && s0[0] == '0') && n_prompts <= kSpecAutoPrompts;
+  return !(s0 && s0[0] == '0') && n_prompts <= kSpecDefaultPrompts;
 }
 
 // fused tokens -> scores for small batches (see launch_chain_score); false = not applicable
