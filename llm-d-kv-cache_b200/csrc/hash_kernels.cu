@@ -1112,10 +1112,10 @@ bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_siz
 //     fold(h, bytes[0..m)) = u * P^m + fold(l, bytes[0..m))                                    (mod 2^64, exactly)
 // A block's byte stream is  83 | U(parent) | tail  where  tail = array-head(bs) | tokens | extra  does not depend on
 // the chain.  So fold(v, tail) is tabulated for all 256 values of v — 256 independent plain FNV runs per block, in
-// parallel over every block of every prompt (phase A: one 256-thread CTA per block) — and the serial chain per block
-// shrinks to the 10 prefix bytes plus one table look-up and one multiply by P^m (phase B: one thread per prompt):
-// ~170 cycles per block instead of ~1000 for the vote rounds.  The price is 256x the byte work, which idle SMs absorb
-// for small batches only (the vote kernels stay the choice from a few dozen prompts up).
+// parallel over every block of every prompt (phase A: one 128-thread CTA per block, two start values per thread) —
+// and the serial chain per block shrinks to the 10 prefix bytes plus one table look-up and one multiply by P^m (phase B:
+// one thread per prompt): 309 cycles per block measured, against ~1000 for the vote rounds.  The price is 256x the byte
+// work, which idle SMs absorb for small batches only (the vote kernels stay the choice from a few dozen prompts up).
 constexpr int kSpecThreads = 128;   // each thread folds TWO start values (two independent chains: the warp's issue slots
                                     // are half empty with one), so a 128-thread CTA tabulates a block
 constexpr int kSpecPassRows = 8;    // table rows (blocks) per staging buffer; two buffers: 2 x 8 x 2 KiB — small, so that

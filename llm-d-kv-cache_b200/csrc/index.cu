@@ -744,7 +744,7 @@ struct kvb_index {
   bool order_valid = false;
   // eviction planner (parallel apply at capacity): one window of the order array at a time
   static constexpr int64_t kWinCap = 1 << 20;
-  uint32_t *d_ins_ops = nullptr, *d_victims = nullptr, *d_win = nullptr;  // d_win: is_victim | touch | rank
+  uint32_t *d_plan_ops = nullptr, *d_victims = nullptr, *d_win = nullptr;  // d_plan_ops: ev | net | top | evict_op; d_win: is_victim | touch | rank
   unsigned long long* d_plan = nullptr;                                     // see index_evict_decide_kernel
   uint8_t* d_conflict = nullptr;                                            // per sorted batch position
 
@@ -940,17 +940,17 @@ int kvb_index::plan_evictions(int64_t n, int64_t* n_victims, unsigned long long*
                               bool* ok) {
   *ok = false;
   *n_victims = 0;
-  if (!d_ins_ops) KVB_CUDA_TRY(cudaMalloc(&d_ins_ops, 4 * kOpsCap * sizeof(uint32_t)));  // ev | net | top | evict_op
+  if (!d_plan_ops) KVB_CUDA_TRY(cudaMalloc(&d_plan_ops, 4 * kOpsCap * sizeof(uint32_t)));  // ev | net | top | evict_op
   if (!d_victims) KVB_CUDA_TRY(cudaMalloc(&d_victims, kOpsCap * sizeof(uint32_t)));
   if (!d_win) KVB_CUDA_TRY(cudaMalloc(&d_win, 3 * kWinCap * sizeof(uint32_t)));
   if (!d_plan) KVB_CUDA_TRY(cudaMalloc(&d_plan, 8 * sizeof(unsigned long long)));
   if (!d_conflict) KVB_CUDA_TRY(cudaMalloc(&d_conflict, 2 * kOpsCap));
   const unsigned threads = 128;
   const unsigned grid_n = (unsigned)((n + threads - 1) / threads);
-  int32_t* ev = reinterpret_cast<int32_t*>(d_ins_ops);
+  int32_t* ev = reinterpret_cast<int32_t*>(d_plan_ops);
   int32_t* net = ev + kOpsCap;
   int32_t* top = net + kOpsCap;
-  uint32_t* evict_op = d_ins_ops + 3 * kOpsCap;
+  uint32_t* evict_op = d_plan_ops + 3 * kOpsCap;
   uint32_t *is_victim = d_win, *touch = d_win + kWinCap, *rank = d_win + 2 * kWinCap;
   uint8_t *conf_cur = d_conflict, *conf_next = d_conflict + kOpsCap;
   KVB_CUDA_TRY(cudaMemsetAsync(conf_cur, 0, (size_t)n, stream));
@@ -1331,7 +1331,7 @@ void kvb_index_destroy(kvb_index_t* idx) {
                   (void*)idx->d_ents, (void*)idx->d_skey_in, (void*)idx->d_skey_out, (void*)idx->d_sidx_in,
                   (void*)idx->d_sidx_out, idx->d_sort_tmp, (void*)idx->order_ts, (void*)idx->order_slot,
                   (void*)idx->order_ts_in, (void*)idx->order_slot_in, (void*)idx->d_cursor, (void*)idx->d_scratch,
-                  (void*)idx->d_filter, (void*)idx->d_done, (void*)idx->d_ins_ops, (void*)idx->d_victims,
+                  (void*)idx->d_filter, (void*)idx->d_done, (void*)idx->d_plan_ops, (void*)idx->d_victims,
                   (void*)idx->d_win, (void*)idx->d_plan, (void*)idx->d_conflict})
     if (p) cudaFree(p);
   for (void* p : {(void*)idx->h_ops, (void*)idx->h_ents, (void*)idx->h_scratch, (void*)idx->h_done})
