@@ -1469,7 +1469,9 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
 #undef SPROF
 }
 
-// per-device scratch of the spec kernel (tables are 2 KiB per key)
+// Scratch of the table kernel (2 KiB of table per key + the counters).  Launches that share one are stream-ordered: the
+// next launch reuses the tables.  An index and the host hash entry point own theirs (created on first use, released with
+// the owner); callers of the device-resident entry point get one per (device, stream) that lives as long as the process.
 struct SpecScratch {
   std::mutex mu;
   uint8_t* d = nullptr;
@@ -1478,9 +1480,14 @@ struct SpecScratch {
   unsigned task_base = 0;
   int max_grid = 0;
 };
-// one scratch per (device, stream): launches on one stream run in order, so the next launch may reuse the tables;
-// launches on different streams (two indexes, the hash entry points) must not share them
-static SpecScratch& spec_scratch(int device, cudaStream_t s) {
+SpecScratch* spec_scratch_create() { return new SpecScratch(); }
+void spec_scratch_destroy(SpecScratch* sc) {
+  if (!sc) return;
+  if (sc->d) cudaFree(sc->d);
+  if (sc->done) cudaFree(sc->done);
+  delete sc;
+}
+static SpecScratch& spec_scratch_shared(int device, cudaStream_t s) {
   static std::mutex mu;
   static std::map<std::pair<int, cudaStream_t>, std::unique_ptr<SpecScratch>> all;
   std::lock_guard<std::mutex> lk(mu);
@@ -1495,12 +1502,13 @@ constexpr int64_t kSpecMaxKeys = 16384;  // 32 MiB of tables
 // picks another kernel.
 static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int32_t block_size, int64_t total_keys,
                         cudaStream_t s, int* rc_out, const int64_t* h_prompt_off = nullptr,
-                        const int64_t* h_key_off = nullptr, const uint64_t* h_parents = nullptr) {
+                        const int64_t* h_key_off = nullptr, const uint64_t* h_parents = nullptr,
+                        SpecScratch* own = nullptr) {
   *rc_out = KVB_OK;
   if (n_prompts > kSpecMaxPrompts || total_keys <= 0 || total_keys > kSpecMaxKeys) return false;
   int dev = 0;
   cudaGetDevice(&dev);
-  SpecScratch& sc = spec_scratch(dev, s);
+  SpecScratch& sc = own ? *own : spec_scratch_shared(dev, s);
   std::lock_guard<std::mutex> lk(sc.mu);
   auto fail = [&](const char* what, cudaError_t e) {
     set_error("hash (spec kernel): %s: %s", what, cudaGetErrorString(e));
@@ -1583,7 +1591,8 @@ static bool spec_wanted(int32_t n_prompts) {
 
 // fused tokens -> scores for small batches (see launch_chain_score); false = not applicable
 bool launch_spec_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, int64_t total_keys, cudaStream_t s,
-                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents) {
+                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents,
+                       SpecScratch* scratch) {
   *rc_out = KVB_OK;
   if (!spec_wanted(n_prompts)) return false;
   // this chain hands over a key every ~0.16 us, a probe round costs ~1.5 us whatever its size: the scorer takes full
@@ -1591,7 +1600,7 @@ bool launch_spec_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size
   ChainArgs b = a;
   const char* e = std::getenv("KVB_SPEC_SCORE_BATCH");
   b.score_min_batch = e ? std::max(1, std::min(32, std::atoi(e))) : 32;
-  return launch_spec(b, true, n_prompts, block_size, total_keys, s, rc_out, h_prompt_off, h_key_off, h_parents);
+  return launch_spec(b, true, n_prompts, block_size, total_keys, s, rc_out, h_prompt_off, h_key_off, h_parents, scratch);
 }
 
 // getInitHash: H(seed_hash, nil, model_name) = FNV64a(83 | U(seed) | f6 | text(model))
@@ -1610,7 +1619,7 @@ __global__ void init_hash_kernel(uint64_t seed_hash, const uint8_t* __restrict__
 int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents, int32_t n_prompts,
                        int32_t block_size, const uint8_t* extra, const int64_t* extra_off, uint64_t* out_keys,
                        const int64_t* key_off, cudaStream_t s, int64_t total_keys, const int64_t* h_prompt_off,
-                       const int64_t* h_key_off, const uint64_t* h_parents) {
+                       const int64_t* h_key_off, const uint64_t* h_parents, SpecScratch* scratch) {
   if (n_prompts <= 0) return KVB_OK;
   if (total_keys > 0 && spec_wanted(n_prompts)) {  // small batches whose key count the caller knows: tables off the chain
     ChainArgs a{};
@@ -1622,7 +1631,7 @@ int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const 
     a.out_keys = out_keys;
     a.key_off = key_off;
     int rc = KVB_OK;
-    if (launch_spec(a, false, n_prompts, block_size, total_keys, s, &rc, h_prompt_off, h_key_off, h_parents)) return rc;
+    if (launch_spec(a, false, n_prompts, block_size, total_keys, s, &rc, h_prompt_off, h_key_off, h_parents, scratch)) return rc;
   }
   // small batches: 32-thread CTAs so the chains spread over the SMs; large: 128
   const int threads = n_prompts >= 148 * 128 ? 128 : 32;
@@ -1723,7 +1732,9 @@ struct HashScratch {
   uint8_t* h = nullptr;  // pinned on the GPU's NUMA node; holds everything but the keys
   size_t h_cap = 0;
   cudaStream_t stream = nullptr;  // for callers that pass no stream
+  SpecScratch* spec = nullptr;    // tables of the table kernel (small batches)
   int ensure(int device, size_t dev_bytes, size_t host_bytes) {
+    if (!spec) spec = spec_scratch_create();
     if (!stream) KVB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (dev_bytes > d_cap) {
       if (d) cudaFree(d);
@@ -1868,7 +1879,7 @@ int kvb_hash_token_blocks(int device, const uint32_t* tokens, const int64_t* pro
                             reinterpret_cast<uint64_t*>(D + o_par), n_prompts, block_size,
                             extra_off ? D + o_ext : nullptr, extra_off ? reinterpret_cast<int64_t*>(D + o_eoff) : nullptr,
                             reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s, total_keys,
-                            h_poff, out_key_off, parents);
+                            h_poff, out_key_off, parents, sc.spec);
     cudaError_t e = cudaSuccess;
     if (rc == KVB_OK) e = cudaMemcpyAsync(out_keys, D + o_keys, (size_t)total_keys * 8, cudaMemcpyDeviceToHost, s);
     const cudaError_t e2 = cudaStreamSynchronize(s);  // the scratch and the caller's buffers must outlive the copies

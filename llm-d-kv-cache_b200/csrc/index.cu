@@ -762,6 +762,9 @@ struct kvb_index {
   bool filter_valid = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
   float last_hash_us = 0.f, last_score_us = 0.f;
+#ifndef KVB_HOST_SIM
+  SpecScratch* spec = nullptr;  // tables of the table kernel (small scoring batches, small ingest rounds)
+#endif
 
   // statistics
   int64_t n_flush_par = 0, n_flush_seq = 0, n_rehash = 0, n_order_builds = 0, n_ops_total = 0;
@@ -1284,6 +1287,9 @@ int kvb_index_create(int device, int64_t max_keys, int32_t pods_per_key, int64_t
     KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_a, cudaEventDefault));
     KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_b, cudaEventDefault));
     KVB_CUDA_TRY(cudaEventCreateWithFlags(&idx->ev_c, cudaEventDefault));
+#ifndef KVB_HOST_SIM
+    idx->spec = spec_scratch_create();
+#endif
     KVB_CUDA_TRY(cudaMalloc(&idx->tier_w, 256 * sizeof(double)));
     KVB_CUDA_TRY(cudaMemcpy(idx->tier_w, idx->tier_w_host, 256 * sizeof(double), cudaMemcpyHostToDevice));
     KVB_CUDA_TRY(cudaMalloc(&idx->d_ctr, sizeof(Counters)));
@@ -1338,6 +1344,9 @@ void kvb_index_destroy(kvb_index_t* idx) {
     if (p) cudaFreeHost(p);
   for (cudaEvent_t e : {idx->q_free, idx->ev_a, idx->ev_b, idx->ev_c})
     if (e) cudaEventDestroy(e);
+#ifndef KVB_HOST_SIM
+  spec_scratch_destroy(idx->spec);
+#endif
   if (idx->stream) cudaStreamDestroy(idx->stream);
   delete idx;
 }
@@ -1509,7 +1518,8 @@ int kvb_index_ingest_events(kvb_index_t* idx, const kvb_kv_event_t* ev, int32_t 
       KVB_CUDA_TRY(cudaMemcpyAsync(D, H, in_end, cudaMemcpyHostToDevice, s));
       rc = launch_hash_blocks(reinterpret_cast<uint32_t*>(D + o_tok), reinterpret_cast<int64_t*>(D + o_poff),
                               reinterpret_cast<uint64_t*>(D + o_par), m, block_size, nullptr, nullptr,
-                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s, h_koff[m]);
+                              reinterpret_cast<uint64_t*>(D + o_keys), reinterpret_cast<int64_t*>(D + o_koff), s, h_koff[m], nullptr, nullptr, nullptr,
+                              idx->spec);
       if (rc) return rc;
       KVB_CUDA_TRY(cudaMemcpyAsync(H + o_keys, D + o_keys, (size_t)h_koff[m] * 8, cudaMemcpyDeviceToHost, s));
       KVB_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1839,7 +1849,7 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
     int spec_rc = KVB_OK;
     if (fuse && launch_spec_score(a, n_prompts, block_size, total_keys, s, &spec_rc,
                                   reinterpret_cast<const int64_t*>(H + o_poff), h_koff,
-                                  reinterpret_cast<const uint64_t*>(H + o_par))) {
+                                  reinterpret_cast<const uint64_t*>(H + o_par), idx->spec)) {
       if (spec_rc) return spec_rc;
       scored = true;
       watch_flag = a.done_counter != nullptr;
@@ -1851,7 +1861,7 @@ static int score_common(kvb_index* idx, const uint64_t* keys_host, const int64_t
       rc = launch_hash_blocks(tok_dev, a.prompt_off, a.parents, n_prompts, block_size, a.extra, a.extra_off,
                               reinterpret_cast<uint64_t*>(D + o_keys), a.key_off, s, total_keys,
                               reinterpret_cast<const int64_t*>(H + o_poff), h_koff,
-                              reinterpret_cast<const uint64_t*>(H + o_par));
+                              reinterpret_cast<const uint64_t*>(H + o_par), idx->spec);
       if (rc) return rc;
     }
   }

@@ -188,8 +188,10 @@ bool launch_chain_score(const ChainArgs& a, int32_t n_prompts, int32_t block_siz
 // the same for small batches by the table ("spec") kernel: any block size, total_keys = key_off[n_prompts];
 // false = not applicable (batch too large or switched off), true = launched or failed (*rc_out)
 // h_*: host-readable copies of prompt_off / key_off / parents
+struct SpecScratch;
 bool launch_spec_score(const ChainArgs& a, int32_t n_prompts, int32_t block_size, int64_t total_keys, cudaStream_t s,
-                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents);
+                       int* rc_out, const int64_t* h_prompt_off, const int64_t* h_key_off, const uint64_t* h_parents,
+                       SpecScratch* scratch);
 #endif  // !KVB_HOST_SIM
 
 }  // namespace kvb

@@ -122,11 +122,15 @@ int upload_ids(kvb_pool* pool, const int64_t* ids_host, int64_t n, cudaStream_t 
 int validate_ids(const kvb_pool* pool, const int64_t* ids_host, int64_t n);
 
 // hashing (device-resident arguments)
+struct SpecScratch;  // tables of the table kernel (hash_kernels.cu), owned by the caller
+SpecScratch* spec_scratch_create();
+void spec_scratch_destroy(SpecScratch* sc);
 int launch_hash_blocks(const uint32_t* tokens, const int64_t* prompt_off, const uint64_t* parents, int32_t n_prompts,
                        int32_t block_size, const uint8_t* extra, const int64_t* extra_off, uint64_t* out_keys,
                        const int64_t* key_off, cudaStream_t s, int64_t total_keys = -1,
                        const int64_t* h_prompt_off = nullptr, const int64_t* h_key_off = nullptr,
-                       const uint64_t* h_parents = nullptr);
+                       const uint64_t* h_parents = nullptr, SpecScratch* scratch = nullptr);
 // total_keys: key_off[n_prompts] if the caller knows it; h_*: host-readable copies of the three small arrays, if at hand
-// (a handful of prompts then travels in the launch arguments)
+// (a handful of prompts then travels in the launch arguments); scratch: the caller's table-kernel scratch (else a shared
+// one per device and stream)
 }  // namespace kvb
