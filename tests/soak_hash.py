@@ -28,8 +28,8 @@ def main():
     t_end = time.time() + args.seconds
     rounds = keys_checked = with_extra = 0
     while time.time() < t_end:
-        bs = int(rng.choice([4, 8, 16, 16, 16, 5, 17, 32, 64]))
-        n = int(rng.choice([1, 2, 31, 32, 33, int(rng.integers(1, 300)), 1536, 1537, 2100]))
+        bs = int(rng.choice([4, 8, 16, 16, 16, 5, 17, 32, 64, 130, 300]))
+        n = int(rng.choice([1, 2, 16, 17, 31, 32, 33, 64, 65, int(rng.integers(1, 300)), 1536, 1537, 2100]))
         if n > 600:
             lens = rng.integers(0, 6 * bs, n)
         else:
@@ -54,7 +54,7 @@ def main():
             extra = rng.integers(0, 256, max(int(extra_off[-1]), 1), dtype=np.uint8)
             with_extra += 1
         want, woff = oc.hash_batch(tokens, off, parents, bs, extra, extra_off)
-        for family in ("", "lanes", "wpc", "chain"):
+        for family in ("", "lanes", "wpc", "chain", "spec"):   # "spec": the table kernel wherever it applies (<= 64 prompts)
             if family:
                 os.environ["KVB_HASH_KERNEL"] = family
             else:
@@ -69,8 +69,8 @@ def main():
             assert np.array_equal(got[:nk], want), (family or "default", bs, n, int(np.argmax(got[:nk] != want)))
         os.environ.pop("KVB_HASH_KERNEL", None)
         rounds += 1
-        keys_checked += 2 * nk
-    print("hash fuzz ok: %d batches (%d with extras), %d keys compared with the C oracle across both kernel families"
+        keys_checked += 5 * nk
+    print("hash fuzz ok: %d batches (%d with extras), %d keys compared with the C oracle across the five kernel selections (default, lanes, wpc, chain, spec)"
           % (rounds, with_extra, keys_checked))
 
 
