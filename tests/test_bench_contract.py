@@ -93,6 +93,17 @@ def test_round2_line_tells_the_whole_truth():
     assert c3["bit_exact"] and r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert c3["e2e"]["bit_exact"] and c3["e2e"]["value"] > 0
     assert ex["ingest"]["bit_exact_vs_oracle"] and ex["manager_lookup"]["same_answer_as_the_loop"]
+    # later in round 2: the targets the review set (one prompt <= 50 us, 1024 prompts within reach of 0.12 ms), small batches
+    # and the index at capacity, each parity-asserted inside the bench before it reports a number
+    assert ex["config1"]["us_per_call"] <= 50 and c5["fused_tokens_to_scores_ms"] <= 0.13
+    sb = c5["small_batches"]
+    assert set(sb) == {"4", "16", "64"} and all(v["bit_exact_vs_oracle"] and v["us_per_call"] > 0 for v in sb.values())
+    cap = c5["index_at_capacity"]
+    assert cap["lru_evictions"] == cap["new_keys"] == 200_000 and cap["plan_fallbacks"] == 0 and cap["seconds"] < 0.1
+    mixed = cap["mixed_batch"]
+    assert mixed["lru_evictions"] == 121_000 and mixed["flushes_planned"] == 1 and mixed["plan_fallbacks"] == 0
+    burst = c5["hash_kernel"]["in_a_long_burst"]
+    assert burst["us"] and burst["sm_mhz"] >= 0.9 * burst["sm_max_mhz"]
 
 
 def test_round2_reference_arm_reports_what_it_moved():
