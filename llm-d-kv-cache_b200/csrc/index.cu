@@ -836,6 +836,7 @@ struct kvb_index {
   int ensure_sort_tmp(size_t need);
   int plan_evictions(int64_t n, int64_t* n_victims, unsigned long long* new_head, unsigned long long* skipped, bool* ok);
   int flush_locked();
+  int flush_piece(size_t first, size_t count, bool may_evict);
   int queue_ops(uint8_t type, const uint64_t* keys, int64_t n_keys, const kvb_pod_entry_t* entries, int32_t n_entries);
   int set_filter(const uint16_t* pods, int32_t n, uint8_t* h_stage, bool* staged, const uint32_t** out);
 };
@@ -1087,23 +1088,46 @@ int kvb_index::flush_locked() {
     if (rc) return rc;
     may_evict = live_ub > max_keys;
   }
-  const bool small = (int64_t)n_ops <= kSeqThreshold;
+  KVB_CUDA_TRY(cudaMemcpyAsync(d_ents, h_ents, n_ents * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  // At capacity a queue longer than half the index is applied in pieces of that length, each a batch of its own: a piece
+  // never needs more victims than the freshly built order array holds untouched records (Size - piece >= piece), so the
+  // eviction plan always has what it needs and the one-thread replay never has to scan the table for a minimum —
+  // except for indexes of a handful of keys, where the scan is a handful of slots.
+  size_t piece = n_ops;
+  if (may_evict && (int64_t)n_ops > max_keys / 2) piece = (size_t)std::max<int64_t>(max_keys / 2, 1);
+  for (size_t first = 0; first < n_ops; first += piece) {
+    int rc = flush_piece(first, std::min(piece, n_ops - first), may_evict);
+    if (rc) return rc;
+  }
+  KVB_CUDA_TRY(cudaEventRecord(q_free, stream));
+  q_busy = true;
+  n_ops_total += (int64_t)n_ops;
+  n_ops = n_ents = 0;
+  q_adds = q_evicts = 0;  // they stay counted inside live_ub / tomb_ub until the next exact read
+  if (may_evict) {
+    int rc = sync_counters();  // the order head moved; exact counts keep the bounds from drifting at capacity
+    if (rc) return rc;
+  }
+  return KVB_OK;
+}
+
+// ops [first, first + count) of the pinned queue as one batch
+int kvb_index::flush_piece(size_t first, size_t count, bool may_evict) {
+  const bool small = (int64_t)count <= kSeqThreshold;
   // at capacity a batch still runs in parallel, with its evictions planned up front (plan_evictions); the one-thread
   // replay in the reference's order remains for tiny batches and for plans that do not settle
   static const bool plan_off = getenv("KVB_INDEX_PLAN") != nullptr && getenv("KVB_INDEX_PLAN")[0] == '0';
   bool planned = may_evict && !small && !plan_off;
   bool sequential = small || (may_evict && !planned);
   if (may_evict) {
-    int rc = ensure_order((int64_t)n_ops);
+    int rc = first ? sync_counters() : KVB_OK;  // the previous piece moved the counters and the order head
+    if (rc == KVB_OK) rc = ensure_order((int64_t)count);
     if (rc) return rc;
   }
-  KVB_CUDA_TRY(cudaMemcpyAsync(d_ops, h_ops, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, stream));
-  KVB_CUDA_TRY(cudaMemcpyAsync(d_ents, h_ents, n_ents * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-  KVB_CUDA_TRY(cudaEventRecord(q_free, stream));
-  q_busy = true;
+  KVB_CUDA_TRY(cudaMemcpyAsync(d_ops, h_ops + first, count * sizeof(OpRec), cudaMemcpyHostToDevice, stream));
   const unsigned long long seq_base = seq;
-  seq += n_ops;
-  const int64_t n = (int64_t)n_ops;
+  seq += count;
+  const int64_t n = (int64_t)count;
   const unsigned threads = 128;
   const unsigned grid = (unsigned)((n + threads - 1) / threads);
   int64_t n_victims = 0;
@@ -1155,13 +1179,6 @@ int kvb_index::flush_locked() {
     KVB_CUDA_TRY(cudaGetLastError());
     count_launch();
     ++n_flush_par;
-  }
-  n_ops_total += n;
-  n_ops = n_ents = 0;
-  q_adds = q_evicts = 0;  // they stay counted inside live_ub / tomb_ub until the next exact read
-  if (may_evict) {
-    int rc = sync_counters();  // the order head moved; exact counts keep the bounds from drifting at capacity
-    if (rc) return rc;
   }
   return KVB_OK;
 }
