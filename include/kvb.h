@@ -20,7 +20,9 @@
  *       KVB_HASH_KERNEL=chain   hash with round 2's chain kernel in its hash-only form (it is the fused scoring launch's kernel)
  *       KVB_HASH_KERNEL=spec    the table kernel for every batch it can take (<= 64 prompts, <= 16384 keys; default: <= 32 prompts)
  *       KVB_HASH_SPEC=0         never pick the table kernel;  KVB_SPEC_SCORE_BATCH=1..32  keys its scorer warp waits for
- *       KVB_INDEX_PLAN=0        index at capacity: replay add-only batches on one thread instead of planning their evictions
+ *       KVB_INDEX_PLAN=0        index at capacity: replay batches on one thread instead of planning their evictions
+ *       KVB_INDEX_SCAN_MAX_SLOTS=n   largest table the one-thread replay may scan for its oldest key when the LRU order array
+ *                               runs out mid-batch (default 65536; larger tables stop, rebuild the order array and resume)
  *       KVB_HASH_MERGED=0|1     chain kernel: vote-free first two bits off / on (default: on up to 512 prompts)
  *       KVB_CHAIN_FETCH=128x2|256x2|256x4|128x6   chain kernel: token chunk size x chunks in flight
  *       KVB_HASH_ONE_WARP=1     hash with the one-warp lane kernel (read once)
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define KVB_ABI_VERSION 4
+#define KVB_ABI_VERSION 5
 
 #define KVB_OK 0
 #define KVB_ERR_INVALID (-1)   /* bad argument */
@@ -271,6 +273,7 @@ typedef struct kvb_index_stats {
                                  plan did not settle) */
   int64_t flushes_planned;    /* parallel flushes at capacity: LRU victims planned up front, same result as in order */
   int64_t plan_fallbacks;     /* planned flushes that had to be replayed sequentially */
+  int64_t replay_resumes;     /* sequential replays that stopped for a fresh LRU order array and resumed (large tables) */
   int64_t rehashes;           /* device-side table growth / tombstone purge */
   int64_t lru_evictions;      /* keys dropped because the index held `max_keys` (in_memory.go:197) */
   int64_t order_builds, order_stale_skipped, order_scans; /* LRU order array: sorts, stale records skipped, fallbacks */

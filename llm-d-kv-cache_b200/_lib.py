@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkvb.so")
 
 KVB_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 COPY_DEFAULT, COPY_LDG, COPY_BULK = 0, 1, 2
 TIER_FILE, TIER_HOST_ARENA = 0, 1
 MAX_PODS_PER_KEY = 13
@@ -42,7 +42,7 @@ class EngineStats(C.Structure):
 class IndexStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "live_keys", "tombstones", "table_slots", "engine_keys", "ops_applied", "flushes_parallel",
-        "flushes_sequential", "flushes_planned", "plan_fallbacks", "rehashes", "lru_evictions", "order_builds", "order_stale_skipped", "order_scans")] + [
+        "flushes_sequential", "flushes_planned", "plan_fallbacks", "replay_resumes", "rehashes", "lru_evictions", "order_builds", "order_stale_skipped", "order_scans")] + [
         ("last_hash_us", C.c_float), ("last_score_us", C.c_float)]
 
 

@@ -66,6 +66,8 @@ static_assert(sizeof(OpRec) == 16, "op record must be 16 B");
 
 struct Counters {  // device resident
   unsigned long long live, tombs, order_head, evicted, inserted, removed, stale_skipped, scans;
+  long long resume_at;            // sequential replay: first op not yet applied, -1 when the batch is done
+  unsigned long long pending_evict;  // an eviction the replay still owes (its order array ran out)
 };
 
 struct TableRef {
@@ -220,8 +222,11 @@ KVB_DEV inline void apply_run(const TableRef& t, const OpRec* ops, const uint32_
 }
 
 // ---- sequential path (one thread): the reference's order, including outer-LRU eviction at `max_keys`
-KVB_DEV inline void evict_oldest(const TableRef& t, const unsigned long long* order_ts,
-                                             const uint32_t* order_slot, unsigned long long order_n) {
+// false: the order array ran out and the table is too large to scan for the minimum — the caller stops, the host
+// rebuilds the order array and resumes (a scan per eviction is fine for a few thousand slots, not for 10^8)
+KVB_DEV inline bool evict_oldest(const TableRef& t, const unsigned long long* order_ts,
+                                             const uint32_t* order_slot, unsigned long long order_n,
+                                             unsigned long long scan_max_slots) {
   Counters& c = *t.ctr;
   while (c.order_head < order_n) {  // lazily validated order array
     const unsigned long long h = c.order_head++;
@@ -231,11 +236,13 @@ KVB_DEV inline void evict_oldest(const TableRef& t, const unsigned long long* or
       c.live--;
       c.tombs++;
       c.evicted++;
-      return;
+      return true;
     }
     c.stale_skipped++;
   }
-  // order exhausted (more insertions than the array held): the keys left are newer than every record — scan for the min
+  // order exhausted (more insertions than the array held, or lookups re-stamped what was left): the keys left are newer
+  // than every record
+  if (t.mask + 1 > scan_max_slots) return false;
   c.scans++;
   int64_t best = -1;
   unsigned long long best_ts = ~0ull;
@@ -250,14 +257,20 @@ KVB_DEV inline void evict_oldest(const TableRef& t, const unsigned long long* or
     c.tombs++;
     c.evicted++;
   }
+  return true;
 }
 
-KVB_DEV inline void apply_seq(const TableRef& t, const OpRec* ops, const uint32_t* ents, int64_t n,
+KVB_DEV inline void apply_seq(const TableRef& t, const OpRec* ops, const uint32_t* ents, int64_t start, int64_t n,
                                           unsigned long long seq_base, unsigned long long max_keys,
                                           const unsigned long long* order_ts, const uint32_t* order_slot,
-                                          unsigned long long order_n) {
+                                          unsigned long long order_n, unsigned long long scan_max_slots) {
   Counters& c = *t.ctr;
-  for (int64_t j = 0; j < n; ++j) {
+  if (c.pending_evict) {  // resumed after the order array was rebuilt: the eviction the previous launch still owed
+    c.pending_evict = 0;
+    evict_oldest(t, order_ts, order_slot, order_n, ~0ull);
+  }
+  c.resume_at = -1;
+  for (int64_t j = start; j < n; ++j) {
 #ifndef KVB_HOST_SIM
     constexpr int64_t kAhead = 12;  // the one thread walks dependent DRAM probes: pull the home buckets of the next ops into L2
     if (j + kAhead < n) {
@@ -283,7 +296,14 @@ KVB_DEV inline void apply_seq(const TableRef& t, const OpRec* ops, const uint32_
         if (was_tomb) c.tombs--;
         store_bucket(t, slot, op.key, ent, 0, true);
         t.ts[slot] = seq_base + j;  // newest before the eviction looks for the oldest
-        if (c.live > max_keys) evict_oldest(t, order_ts, order_slot, order_n);  // lru.Add past Size (in_memory.go:197)
+        if (c.live > max_keys && !evict_oldest(t, order_ts, order_slot, order_n, scan_max_slots)) {  // lru.Add past Size (in_memory.go:197)
+          // out of order records on a large table: finish this op, then hand back to the host for a fresh order array
+          for (uint32_t e = 0; e < op.ent_cnt; ++e) inner_add(ent, cnt, ents[op.ent_off + e], t.ppk);
+          store_bucket(t, slot, op.key, ent, cnt, true);
+          c.pending_evict = 1;
+          c.resume_at = j + 1;
+          return;
+        }
       } else {
         const Bucket& b = t.table[slot];
         cnt = (int)((ld_meta(&b) >> 8) & 0xffu);
@@ -320,11 +340,12 @@ __global__ void index_apply_par_kernel(TableRef t, const OpRec* __restrict__ ops
 }
 
 __global__ void index_apply_seq_kernel(TableRef t, const OpRec* __restrict__ ops, const uint32_t* __restrict__ ents,
-                                       int64_t n, unsigned long long seq_base, unsigned long long max_keys,
-                                       const unsigned long long* __restrict__ order_ts,
-                                       const uint32_t* __restrict__ order_slot, unsigned long long order_n) {
+                                       int64_t start, int64_t n, unsigned long long seq_base,
+                                       unsigned long long max_keys, const unsigned long long* __restrict__ order_ts,
+                                       const uint32_t* __restrict__ order_slot, unsigned long long order_n,
+                                       unsigned long long scan_max_slots) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  apply_seq(t, ops, ents, n, seq_base, max_keys, order_ts, order_slot, order_n);
+  apply_seq(t, ops, ents, start, n, seq_base, max_keys, order_ts, order_slot, order_n, scan_max_slots);
 }
 
 __global__ void index_sort_keys_kernel(const OpRec* __restrict__ ops, int64_t n, uint64_t* __restrict__ keys,
@@ -768,7 +789,7 @@ struct kvb_index {
 
   // statistics
   int64_t n_flush_par = 0, n_flush_seq = 0, n_rehash = 0, n_order_builds = 0, n_ops_total = 0;
-  int64_t n_flush_planned = 0, n_plan_fallbacks = 0;
+  int64_t n_flush_planned = 0, n_plan_fallbacks = 0, n_seq_resumes = 0;
 
   TableRef ref() const { return TableRef{table, ts, slots - 1, d_ctr, pods_per_key}; }
 
@@ -1159,10 +1180,29 @@ int kvb_index::flush_piece(size_t first, size_t count, bool may_evict) {
     }
   }
   if (sequential) {
-    KVB_LAUNCH(index_apply_seq_kernel, 1, 1, stream, ref(), d_ops, d_ents, n, seq_base, (unsigned long long)max_keys,
-               order_ts, order_slot, (unsigned long long)(may_evict ? order_n : 0));
-    KVB_CUDA_TRY(cudaGetLastError());
-    count_launch();
+    // a table of up to this many slots may be scanned for its oldest key when the order array runs out inside the
+    // replay; above it the replay stops, the order array is rebuilt and the replay resumes
+    static const unsigned long long scan_max_slots =
+        getenv("KVB_INDEX_SCAN_MAX_SLOTS") ? strtoull(getenv("KVB_INDEX_SCAN_MAX_SLOTS"), nullptr, 10) : 65536ull;
+    for (int64_t start = 0; start >= 0;) {
+      KVB_LAUNCH(index_apply_seq_kernel, 1, 1, stream, ref(), d_ops, d_ents, start, n, seq_base,
+                 (unsigned long long)max_keys, order_ts, order_slot, (unsigned long long)(may_evict ? order_n : 0),
+                 scan_max_slots);
+      KVB_CUDA_TRY(cudaGetLastError());
+      count_launch();
+      start = -1;
+      if (may_evict && slots > scan_max_slots) {
+        int rc = sync_counters();
+        if (rc) return rc;
+        if (h_ctr.resume_at >= 0 || h_ctr.pending_evict) {
+          start = h_ctr.resume_at >= 0 ? h_ctr.resume_at : n;
+          order_valid = false;
+          rc = ensure_order();
+          if (rc) return rc;
+          ++n_seq_resumes;
+        }
+      }
+    }
     ++n_flush_seq;
   } else {
     if (planned) {  // victims go first: a conflict key must be absent when its ops are replayed
@@ -1604,6 +1644,7 @@ int kvb_index_get_stats(kvb_index_t* idx, kvb_index_stats_t* out) {
     out->flushes_sequential = idx->n_flush_seq;
     out->flushes_planned = idx->n_flush_planned;
     out->plan_fallbacks = idx->n_plan_fallbacks;
+    out->replay_resumes = idx->n_seq_resumes;
     out->rehashes = idx->n_rehash;
     out->lru_evictions = (int64_t)idx->h_ctr.evicted;
     out->order_builds = idx->n_order_builds;

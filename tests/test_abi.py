@@ -27,7 +27,7 @@ def test_binding_covers_header(kvb):
 
 
 def test_abi_version_and_no_device_is_loud(kvb):
-    assert kvb.lib.kvb_abi_version() == kvb._lib.ABI_VERSION == 4
+    assert kvb.lib.kvb_abi_version() == kvb._lib.ABI_VERSION == 5
     if kvb.lib.kvb_device_count() == 0:
         # no CPU fallback: compute entry points must fail, not silently compute on the host
         tp = kvb.kvblock.ChunkedTokenDatabase(16, "")

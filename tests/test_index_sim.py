@@ -101,6 +101,34 @@ def test_tiny_capacity_exhausts_the_order_array(sim):
     assert st["order_scans"] > 0
 
 
+def test_sequential_replay_stops_and_resumes_instead_of_scanning(sim):
+    """With KVB_INDEX_SCAN_MAX_SLOTS=0 every table counts as too large to scan: when the order array runs out inside a
+    one-thread replay (KVB_INDEX_PLAN=0 sends every at-capacity batch there) the kernel stops, the host rebuilds the
+    order array and the replay resumes at the next op — same reads as the oracle, no scan.  Own process: both switches
+    are read once."""
+    import subprocess
+    code = (
+        "import sys, importlib, ctypes as C\n"
+        "sys.path.insert(0, %r)\n"
+        "import tests.test_index_sim as T\n"
+        "spec = importlib.util.spec_from_file_location('b', %r)\n"
+        "mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)\n"
+        "lib = C.CDLL(mod.build())\n"
+        "kvb = importlib.import_module('llm-d-kv-cache_b200')\n"
+        "kvb._lib.bind(lib, T.SIM_NAMES)\n"
+        "lib.kvb_last_error = lambda: b'(sim)'\n"
+        "tot = 0\n"
+        "for seed, size, nk, mb in ((5, 3, 60, 40), (123, 300, 500, 5), (11, 2000, 6000, 300)):\n"
+        "    st = T._random_traffic(kvb, lib, seed=seed, size=size, ppk=3, n_keys=nk, steps=400, max_batch=mb)\n"
+        "    assert st['order_scans'] == 0, st\n"
+        "    tot += st['replay_resumes']\n"
+        "assert tot > 10, tot\n"
+        "print('resumes', tot)\n") % (ROOT, os.path.join(ROOT, "tests", "cpp", "build_index_sim.py"))
+    env = dict(os.environ, KVB_INDEX_SCAN_MAX_SLOTS="0", KVB_INDEX_PLAN="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "resumes" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_parallel_path_big_batches_growth_and_tombstones(sim):
     """No capacity pressure, batches of up to 400 keys with many repeats: sorted per-key replay, device-side rehash
     (the table starts at 2048 slots) and tombstone reuse."""
