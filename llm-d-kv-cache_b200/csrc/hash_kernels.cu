@@ -1555,7 +1555,6 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
   x.done = sc.done;
   x.next_task = sc.done + kSpecMaxPrompts;
   x.task_base = sc.task_base;
-  sc.task_base += (unsigned)total_keys;  // wraps with the counter
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(total_keys, n_prompts), sc.max_grid);
   const bool inl = h_prompt_off && h_key_off && h_parents;  // host copies at hand: they go into the arguments
   x.inl = inl ? 1 : 0;
@@ -1575,7 +1574,8 @@ static bool launch_spec(const ChainArgs& ca, bool score, int32_t n_prompts, int3
   if (n_prompts <= kSpecAutoPrompts) go(std::integral_constant<int, kSpecAutoPrompts>{});
   else go(std::integral_constant<int, kSpecMaxPrompts>{});
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail("launch", e);
+  if (e != cudaSuccess) return fail("launch", e);  // nothing ran: the task counter has not moved either
+  sc.task_base += (unsigned)total_keys;            // the launch advances the counter by exactly one per task (wraps with it)
   count_launch();
   return true;
 }
