@@ -1372,7 +1372,13 @@ __global__ void __launch_bounds__(kSpecThreads) hash_spec_kernel(const ChainArgs
     constexpr int kLoaders = kSpecThreads - 64;
     if (lt == 0) {
       const volatile unsigned* d = X.done + p;
-      while (*d < (unsigned)nblk) __nanosleep(50);
+      unsigned long long t_wait0 = 0, t_now = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
+      while (*d < (unsigned)nblk) {
+        __nanosleep(50);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+        if (t_now - t_wait0 > 2000000000ull) __trap();  // the only wait on OTHER CTAs: fail the launch rather than hang the GPU
+      }
       __threadfence();
       SPROF(2);
     }
