@@ -598,6 +598,8 @@ def run_index_configs(kvb):
     # about the kernel.  ~0.3 s of back-to-back launches, the last 100 timed, clock read during them.
     hash_warm = {"us": None, "sm_mhz": None}
     try:
+        if os.environ.get("KVB_BENCH_NO_BURST"):   # 6 100 launches: far too many to replay under ncu
+            raise RuntimeError("skipped: KVB_BENCH_NO_BURST is set")
         import pynvml
         pynvml.nvmlInit()
         h_nv = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
